@@ -1,0 +1,148 @@
+/*
+ * maskplanner_b200.h -- C ABI of libmaskplanner_b200.so (sm_100a).
+ *
+ * The reference (gabrieletiboni/MaskPlanner) has no FFI layer: its boundary for this path is the
+ * Python module surface of models/pointnet2_utils.py and pytorch3d_chamfer.py.  Each entry point
+ * below is what a binding for one of those functions would call; the citation names the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - strides are in ELEMENTS (not bytes) so permuted torch views can be passed without a copy;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing allocates: the caller owns outputs and workspaces;
+ *   - return value: 0 on success, negative mpb_status otherwise; mpb_last_error_string() describes
+ *     the last failure on the calling thread.  Nothing throws, nothing synchronises the device.
+ *   - index tensors are int64 (torch.long), exactly as the reference returns them.
+ */
+#ifndef MASKPLANNER_B200_H_
+#define MASKPLANNER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MPB_API __attribute__((visibility("default")))
+#else
+#define MPB_API
+#endif
+
+typedef enum {
+    MPB_OK = 0,
+    MPB_ERR_INVALID_ARGUMENT = -1,
+    MPB_ERR_UNSUPPORTED = -2,
+    MPB_ERR_CUDA = -3,
+    MPB_ERR_WORKSPACE = -4
+} mpb_status;
+
+MPB_API int mpb_version(void);
+MPB_API const char *mpb_last_error_string(void);
+/* Number of SMs / compute capability (major*10+minor) of the current device; <0 on error. */
+MPB_API int mpb_device_sm_count(void);
+MPB_API int mpb_device_arch(void);
+
+/* ---- a1: farthest_point_sample(xyz, npoint)            models/pointnet2_utils.py:65-86 -------
+ * xyz [B,N,3] f32 through (sb,sn,sc); seed_idx [B] i64 = the reference's CPU randint draw (:77),
+ * made by the caller; out_idx [B,npoint] i64.  Distance ((dx*dx)+(dy*dy))+(dz*dz), every op
+ * rounded; strict '<' running minimum from 1e10; lowest index among equal maxima.
+ * Register/cluster-resident up to N = 131072; beyond that `workspace` must hold B*N floats.
+ * mpb_fps_workspace_bytes() returns the workspace the call needs (0 if none). */
+MPB_API int64_t mpb_fps_workspace_bytes(int B, int N);
+MPB_API int mpb_fps_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                        const int64_t *seed_idx, int npoint, int64_t *out_idx, void *workspace,
+                        void *stream);
+
+/* ---- a2: square_distance(src, dst)                     models/pointnet2_utils.py:21-42 -------
+ * Expanded form ((-2*dot)+|s|^2)+|d|^2 with dot = fma(s2,d2,fma(s1,d1,s0*d0)); C = 3 only (the
+ * reference's other use, C = feature dim in feature propagation, is off the path).
+ * src [B,N,3], dst [B,M,3] contiguous; out [B,N,M] f32. */
+MPB_API int mpb_square_distance_f32(const float *src, const float *dst, int B, int N, int M,
+                                    float *out, void *stream);
+
+/* ---- a3: query_ball_point(radius, nsample, xyz, new_xyz)   models/pointnet2_utils.py:89-109 --
+ * First `nsample` point indices in ascending order with !(d > r2), d as in a2, padded with the
+ * first hit; a query with an empty ball gets N in every slot, like the reference.
+ * r2 is fp32(radius**2), rounded by the caller exactly as torch rounds the Python scalar. */
+MPB_API int mpb_ball_query_f32(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                               const float *new_xyz, int64_t qsb, int64_t qsn, int64_t qsc,
+                               int B, int N, int S, float r2, int nsample, int64_t *out_idx,
+                               void *stream);
+
+/* ---- stress config: kNN grouping (no reference function; SURVEY.md 8d defines it as
+ * square_distance + topk(k, smallest, sorted)).  Ties go to the lowest index.  k <= 64.
+ * out_dist may be NULL. */
+MPB_API int mpb_knn_group_f32(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                              const float *new_xyz, int64_t qsb, int64_t qsn, int64_t qsc,
+                              int B, int N, int S, int k, int64_t *out_idx, float *out_dist,
+                              void *stream);
+
+/* ---- a4: index_points(points, idx)                     models/pointnet2_utils.py:45-62 -------
+ * out[b,m,:] = points[b, idx[b,m], :]; points [B,N,C] through strides, idx [B,M] i64 (M = S or
+ * S*K), out [B,M,C] contiguous.  Out-of-range indices (the reference would raise) produce zeros.
+ * _bwd: grad_points[b, idx[b,m], :] += grad_out[b,m,:] (grad_points [B,N,C] contiguous, caller
+ * zero-fills it first). */
+MPB_API int mpb_index_points_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B,
+                                 int N, int C, const int64_t *idx, int64_t M, float *out,
+                                 void *stream);
+MPB_API int mpb_index_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int C,
+                                     int64_t M, float *grad_points, void *stream);
+
+/* ---- a5: sample_and_group's gather/centre/concat       models/pointnet2_utils.py:133-141 -----
+ * out[b,s,k,0:3]   = xyz[b, idx[b,s,k], :] - new_xyz[b,s,:]
+ * out[b,s,k,3:3+D] = feats[b, idx[b,s,k], :]          (feats may be NULL, D = 0)
+ * out is [B,S,K,ldo] f32 with ldo >= 3+D (columns beyond 3+D are zero-filled: GEMM K padding).
+ * _bwd scatters grad_out[..., 3:3+D] into grad_feats [B,N,D] (contiguous, caller zero-fills);
+ * xyz carries no gradient in the reference model (input cloud / index-selected coordinates are
+ * never parameters), grad_xyz may be NULL; when given it receives the :134 terms too. */
+MPB_API int mpb_group_points_f32(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                                 const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                                 const float *new_xyz, const int64_t *idx, int B, int N, int S,
+                                 int K, int D, int ldo, float *out, void *stream);
+MPB_API int mpb_group_points_bwd_f32(const float *grad_out, int ldo, const int64_t *idx, int B,
+                                     int N, int S, int K, int D, float *grad_feats,
+                                     float *grad_xyz, float *grad_new_xyz, void *stream);
+
+/* ---- a8: chamfer_distance's nearest-neighbour core     pytorch3d_chamfer.py:257-258 ----------
+ * (pytorch3d.ops.knn.knn_points with K = 1, both directions from one launch.)
+ * x [N,P1,D], y [N,P2,D] f32 contiguous; x_len / y_len [N] i64 or NULL (= full length).
+ * dist_x/idx_x [N,P1] : for every x point the squared distance to / index of its nearest y point
+ * among the first y_len[n]; rows >= x_len[n] are written as 0.  dist_y/idx_y [N,P2] likewise.
+ * Either output pair may be NULL: that direction is skipped (asymmetric modes, :329-332).
+ * Squared distance in direct form, fma-accumulated over d = 0..D-1; strict '<' => lowest index
+ * wins ties.  D <= 64. */
+MPB_API int mpb_chamfer_nn_f32(const float *x, const float *y, int N, int P1, int P2, int D,
+                               const int64_t *x_len, const int64_t *y_len, float *dist_x,
+                               int64_t *idx_x, float *dist_y, int64_t *idx_y, void *stream);
+
+/* Backward of the above (pytorch3d knn_points_backward, K = 1):
+ * grad_x[n,i] = 2*gdx[n,i]*(x[n,i]-y[n,idx_x[n,i]]) + sum_{j: idx_y[n,j]=i} 2*gdy[n,j]*(x[n,i]-y[n,j])
+ * and symmetrically for grad_y.  gdx/gdy (and their idx) may be NULL.  grad_x / grad_y are
+ * fully written (no pre-zeroing needed). */
+MPB_API int mpb_chamfer_nn_bwd_f32(const float *x, const float *y, int N, int P1, int P2, int D,
+                                   const int64_t *x_len, const int64_t *y_len, const int64_t *idx_x,
+                                   const int64_t *idx_y, const float *gdx, const float *gdy,
+                                   float *grad_x, float *grad_y, void *stream);
+
+/* General-K variant for the K = 2 branches (pytorch3d_chamfer.py:205-206): one direction,
+ * dists/idx [N,P1,K] sorted ascending, K <= 8. */
+MPB_API int mpb_knn_points_f32(const float *p1, const float *p2, int N, int P1, int P2, int D,
+                               const int64_t *len1, const int64_t *len2, int K, float *dists,
+                               int64_t *idx, void *stream);
+MPB_API int mpb_knn_points_bwd_f32(const float *p1, const float *p2, int N, int P1, int P2, int D,
+                                   const int64_t *len1, const int64_t *len2, const int64_t *idx,
+                                   int K, const float *grad_dists, float *grad_p1, float *grad_p2,
+                                   void *stream);
+
+/* `padded=True` length scan                              pytorch3d_chamfer.py:138-149 ----------
+ * first[n] = first j with y[n,j,0] == sentinel, else P2; *any_flag (int32, caller zero-fills) is
+ * set to 1 if any sample is padded.  No host synchronisation (the reference does 2N of them). */
+MPB_API int mpb_padded_lengths_f32(const float *y, int N, int P2, int D, float sentinel,
+                                   int64_t *first, int32_t *any_flag, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASKPLANNER_B200_H_ */

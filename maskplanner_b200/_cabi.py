@@ -1,0 +1,94 @@
+"""ctypes binding of libmaskplanner_b200.so (the C ABI declared in include/maskplanner_b200.h).
+
+There is NO fallback: if the library is missing (and cannot be built because nvcc is absent) or a
+call fails, this module raises.  Tensors are passed as raw device pointers plus sizes/strides; the
+current torch CUDA stream is passed as the stream argument, so work is enqueued exactly where
+stock torch ops would enqueue it.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_F = ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/maskplanner_b200.h
+SIGNATURES = {
+    "mpb_version": (_I, []),
+    "mpb_last_error_string": (ctypes.c_char_p, []),
+    "mpb_device_sm_count": (_I, []),
+    "mpb_device_arch": (_I, []),
+    "mpb_fps_workspace_bytes": (_L, [_I, _I]),
+    "mpb_fps_f32": (_I, [_P, _L, _L, _L, _I, _I, _P, _I, _P, _P, _P]),
+    "mpb_square_distance_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "mpb_ball_query_f32": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _F, _I, _P, _P]),
+    "mpb_knn_group_f32": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P]),
+    "mpb_index_points_f32": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _L, _P, _P]),
+    "mpb_index_points_bwd_f32": (_I, [_P, _P, _I, _I, _I, _L, _P, _P]),
+    "mpb_group_points_f32": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "mpb_group_points_bwd_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "mpb_chamfer_nn_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "mpb_chamfer_nn_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mpb_knn_points_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "mpb_knn_points_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "mpb_padded_lengths_f32": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc exists).  Raises on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as e:  # no silent degradation: surface why the native path is unavailable
+            raise ImportError(
+                "libmaskplanner_b200.so is missing and could not be built (%s). maskplanner_b200 has no "
+                "CPU or pure-torch fallback; run `python -m maskplanner_b200.build`." % (e,)) from e
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class MpbError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mpb_last_error_string()
+        raise MpbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("maskplanner_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                               "got a %s tensor" % t.device)

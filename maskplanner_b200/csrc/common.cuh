@@ -1,0 +1,85 @@
+// Shared helpers for the libmaskplanner_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/maskplanner_b200.h"
+
+namespace mpb {
+
+void set_error(const char *fmt, ...);
+
+inline int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return MPB_ERR_CUDA;
+    }
+    return MPB_OK;
+}
+
+#define MPB_REQUIRE(cond, msg)                                          \
+    do {                                                                \
+        if (!(cond)) {                                                  \
+            ::mpb::set_error("%s: %s", __func__, msg);                  \
+            return MPB_ERR_INVALID_ARGUMENT;                            \
+        }                                                               \
+    } while (0)
+
+#define MPB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            ::mpb::set_error("%s: %s -> %s", __func__, #call, cudaGetErrorString(e_)); \
+            return MPB_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+int sm_count();
+
+// ---- warp-level integer reductions (REDUX.*; one instruction on sm_80+) ----------------------
+__device__ __forceinline__ int redux_max_s32(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ int redux_min_s32(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned redux_min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+
+// ---- thread-block-cluster primitives (raw PTX, no cooperative_groups dependency) --------------
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive_release()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire()
+{
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Address of `smem_ptr` (a shared-memory address of this CTA) as seen in CTA `rank` of the cluster.
+__device__ __forceinline__ unsigned map_shared_rank(const void *smem_ptr, unsigned rank)
+{
+    unsigned local = (unsigned)__cvta_generic_to_shared(smem_ptr), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void st_shared_cluster_v4(unsigned addr, int a, int b, int c, int d)
+{
+    asm volatile("st.shared::cluster.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_s32(unsigned addr, int a)
+{
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+
+}  // namespace mpb

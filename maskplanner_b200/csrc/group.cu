@@ -1,0 +1,142 @@
+// Gather / grouping kernels for sm_100a.
+// Reference: models/pointnet2_utils.py:45-62 (index_points), :133-141 (gather + centre + concat
+// inside sample_and_group).  The reference issues four advanced-indexing gathers, a subtract and a
+// cat, each materialised; mpb_group_points_f32 produces the concatenated [B,S,K,3+D] tensor (with
+// optional zero K-padding for the GEMM that consumes it) in one pass.
+//
+// These are pure data movement (HBM/L2-bound): one thread per output element, channel index
+// fastest so that both the gathered row read and the output write are coalesced.
+#include "common.cuh"
+
+namespace mpb {
+
+__global__ void index_points_kernel(const float *__restrict__ pts, int64_t sb, int64_t sn, int64_t sc, int N, int C,
+                                    const int64_t *__restrict__ idx, int64_t M, int64_t total, float *__restrict__ out)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const int64_t row = e / C;  // b*M + m
+        const int64_t b = row / M;
+        const int64_t i = idx[row];
+        out[e] = (i >= 0 && i < N) ? pts[b * sb + i * sn + c * sc] : 0.f;
+    }
+}
+
+__global__ void index_points_bwd_kernel(const float *__restrict__ go, const int64_t *__restrict__ idx, int N, int C,
+                                        int64_t M, int64_t total, float *__restrict__ gp)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const int64_t row = e / C;
+        const int64_t b = row / M;
+        const int64_t i = idx[row];
+        if (i >= 0 && i < N) atomicAdd(gp + (b * N + i) * C + c, go[e]);
+    }
+}
+
+__global__ void group_points_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                                    const float *__restrict__ feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                                    const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int S,
+                                    int K, int D, int ldo, int64_t total, float *__restrict__ out)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % ldo);
+        const int64_t row = e / ldo;   // (b*S + s)*K + k
+        const int64_t bs = row / K;    // b*S + s
+        const int64_t b = bs / S;
+        const int64_t i = idx[row];
+        const bool ok = i >= 0 && i < N;
+        float v = 0.f;
+        if (c < 3) {
+            if (ok) v = __fsub_rn(xyz[b * xsb + i * xsn + c * xsc], new_xyz[bs * 3 + c]);  // :134
+        } else if (c < 3 + D) {
+            if (ok) v = feats[b * fsb + i * fsn + (int64_t)(c - 3) * fsc];               // :137-138
+        }
+        out[e] = v;
+    }
+}
+
+__global__ void group_points_bwd_kernel(const float *__restrict__ go, int ldo, const int64_t *__restrict__ idx, int N,
+                                        int S, int K, int D, int64_t total, float *__restrict__ gfeats,
+                                        float *__restrict__ gxyz, float *__restrict__ gnew)
+{
+    const int W = 3 + D;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % W);
+        const int64_t row = e / W;
+        const int64_t bs = row / K;
+        const int64_t b = bs / S;
+        const int64_t i = idx[row];
+        if (i < 0 || i >= N) continue;
+        const float g = go[row * ldo + c];
+        if (c < 3) {
+            if (gxyz) atomicAdd(gxyz + (b * N + i) * 3 + c, g);
+            if (gnew) atomicAdd(gnew + bs * 3 + c, -g);
+        } else if (gfeats) {
+            atomicAdd(gfeats + (b * N + i) * D + (c - 3), g);
+        }
+    }
+}
+
+static inline unsigned grid_for(int64_t total, int threads)
+{
+    int64_t blocks = (total + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace mpb
+
+extern "C" int mpb_index_points_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,
+                                    const int64_t *idx, int64_t M, float *out, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && N >= 0 && C >= 0 && M >= 0, "negative size");
+    const int64_t total = (int64_t)B * M * C;
+    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(points && idx && out, "null pointer");
+    index_points_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(points, sb, sn, sc, N, C, idx, M, total, out);
+    return check_launch("index_points_kernel");
+}
+
+extern "C" int mpb_index_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int64_t M,
+                                        float *grad_points, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && N >= 0 && C >= 0 && M >= 0, "negative size");
+    const int64_t total = (int64_t)B * M * C;
+    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(grad_out && idx && grad_points, "null pointer");
+    index_points_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, N, C, M, total, grad_points);
+    return check_launch("index_points_bwd_kernel");
+}
+
+extern "C" int mpb_group_points_f32(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats,
+                                    int64_t fsb, int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx,
+                                    int B, int N, int S, int K, int D, int ldo, float *out, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "negative size");
+    MPB_REQUIRE(ldo >= 3 + D, "ldo < 3 + D");
+    const int64_t total = (int64_t)B * S * K * ldo;
+    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
+    MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
+    group_points_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc,
+                                                                               new_xyz, idx, N, S, K, D, ldo, total, out);
+    return check_launch("group_points_kernel");
+}
+
+extern "C" int mpb_group_points_bwd_f32(const float *grad_out, int ldo, const int64_t *idx, int B, int N, int S, int K,
+                                        int D, float *grad_feats, float *grad_xyz, float *grad_new_xyz, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "negative size");
+    MPB_REQUIRE(ldo >= 3 + D, "ldo < 3 + D");
+    const int64_t total = (int64_t)B * S * K * (3 + D);
+    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(grad_out && idx, "null pointer");
+    group_points_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, ldo, idx, N, S, K, D, total,
+                                                                                   grad_feats, grad_xyz, grad_new_xyz);
+    return check_launch("group_points_bwd_kernel");
+}

@@ -1,0 +1,270 @@
+"""Drop-in for the reference's ``models/pointnet2_utils.py`` on B200 (sm_100a).
+
+Same names, argument order, shapes, dtypes and error behaviour as the reference module
+(/root/reference/models/pointnet2_utils.py); every function enqueues hand-written CUDA kernels from
+libmaskplanner_b200.so on the current torch stream through the C ABI (include/maskplanner_b200.h).
+CUDA tensors only -- there is no CPU or pure-torch fallback for the hot ops.
+
+    square_distance          :21-42     index_points           :45-62
+    farthest_point_sample    :65-86     query_ball_point       :89-109
+    sample_and_group         :112-148   sample_and_group_all   :151-168
+    PointNetSetAbstraction   :171-216
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+from ._cabi import check, ptr, require_cuda, stream_ptr
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (the reference path is fp32); got %s" % (name, t.dtype))
+    return t
+
+
+def _strides3(t):
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+# ---------------------------------------------------------------------------------------------
+# a2  square_distance
+# ---------------------------------------------------------------------------------------------
+def square_distance(src, dst):
+    """Pairwise squared distance, expanded form (reference :21-42).  src [B,N,C], dst [B,M,C] -> [B,N,M].
+
+    C == 3 (the only case on the hot path) runs the bit-exact kernel; other C (feature-space
+    distances in the off-path feature-propagation module) use the same three torch ops as the
+    reference."""
+    B, N, C = src.shape
+    M = dst.shape[1]
+    if C != 3 or src.requires_grad or dst.requires_grad:
+        d = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+        d += torch.sum(src ** 2, -1).view(B, N, 1)
+        d += torch.sum(dst ** 2, -1).view(B, 1, M)
+        return d
+    require_cuda(src, dst)
+    s, d = _f32(src, "src").contiguous(), _f32(dst, "dst").contiguous()
+    out = torch.empty(B, N, M, dtype=torch.float32, device=src.device)
+    check(_cabi.load().mpb_square_distance_f32(ptr(s), ptr(d), B, N, M, ptr(out), stream_ptr()), "mpb_square_distance_f32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# a4  index_points
+# ---------------------------------------------------------------------------------------------
+class _IndexPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        B, N, C = points.shape
+        idx_c = idx.contiguous()
+        M = idx_c.numel() // max(B, 1)
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=points.dtype, device=points.device)
+        sb, sn, sc = _strides3(points)
+        check(_cabi.load().mpb_index_points_f32(ptr(points), sb, sn, sc, B, N, C, ptr(idx_c), M, ptr(out), stream_ptr()),
+              "mpb_index_points_f32")
+        ctx.save_for_backward(idx_c)
+        ctx.shape = (B, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (idx_c,) = ctx.saved_tensors
+        B, N, C = ctx.shape
+        go = go.contiguous()
+        gp = torch.zeros(B, N, C, dtype=go.dtype, device=go.device)
+        check(_cabi.load().mpb_index_points_bwd_f32(ptr(go), ptr(idx_c), B, N, C, idx_c.numel() // max(B, 1), ptr(gp),
+                                                    stream_ptr()), "mpb_index_points_bwd_f32")
+        return gp, None
+
+
+def index_points(points, idx):
+    """points [B,N,C] (any strides), idx [B,S] or [B,S,K] int64 -> [B,S,C] / [B,S,K,C] (reference :45-62)."""
+    require_cuda(points, idx)
+    _f32(points, "points")
+    if idx.dtype != torch.int64:
+        idx = idx.long()
+    return _IndexPoints.apply(points, idx)
+
+
+# ---------------------------------------------------------------------------------------------
+# a1  farthest_point_sample
+# ---------------------------------------------------------------------------------------------
+def draw_fps_seed(B, N, device):
+    """The reference's seed draw (:77): ONE torch.randint(0, N, (B,)) from the CPU generator, then
+    moved to the device -- identical RNG-stream consumption, so seeded runs pick the same seeds."""
+    return torch.randint(0, N, (B,), dtype=torch.long).to(device)
+
+
+def farthest_point_sample(xyz, npoint, seed_idx=None):
+    """xyz [B,N,3] f32 -> centroids [B,npoint] int64, bit-exact vs the reference (:65-86).
+
+    `seed_idx` (extension, default None = reference behaviour) supplies the first index per cloud
+    instead of drawing it."""
+    require_cuda(xyz)
+    _f32(xyz, "xyz")
+    B, N, C = xyz.shape
+    assert C == 3, "farthest_point_sample expects [B, N, 3]"
+    seed = draw_fps_seed(B, N, xyz.device) if seed_idx is None else seed_idx.to(device=xyz.device, dtype=torch.long).contiguous()
+    out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
+    lib = _cabi.load()
+    ws_bytes = lib.mpb_fps_workspace_bytes(B, N)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=xyz.device) if ws_bytes else None
+    sb, sn, sc = _strides3(xyz)
+    check(lib.mpb_fps_f32(ptr(xyz), sb, sn, sc, B, N, ptr(seed), npoint, ptr(out), ptr(ws), stream_ptr()), "mpb_fps_f32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# a3  query_ball_point (+ kNN grouping for the stress configuration)
+# ---------------------------------------------------------------------------------------------
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """xyz [B,N,3], new_xyz [B,S,3] -> group_idx [B,S,nsample] int64, bit-exact vs the reference (:89-109)."""
+    require_cuda(xyz, new_xyz)
+    _f32(xyz, "xyz"), _f32(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
+    r2 = float(np.float32(radius ** 2))  # torch compares fp32 tensors against fp32(radius ** 2) (:104)
+    check(_cabi.load().mpb_ball_query_f32(ptr(xyz), *_strides3(xyz), ptr(new_xyz), *_strides3(new_xyz), B, N, S, r2,
+                                          nsample, ptr(out), stream_ptr()), "mpb_ball_query_f32")
+    return out
+
+
+def knn_group(k, xyz, new_xyz, return_dist=False):
+    """k nearest points (expanded-form distance, ascending, lowest index on ties) -> [B,S,k] int64.
+    Stress-configuration grouping; the reference has no such function."""
+    require_cuda(xyz, new_xyz)
+    _f32(xyz, "xyz"), _f32(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty(B, S, k, dtype=torch.long, device=xyz.device)
+    dist = torch.empty(B, S, k, dtype=torch.float32, device=xyz.device) if return_dist else None
+    check(_cabi.load().mpb_knn_group_f32(ptr(xyz), *_strides3(xyz), ptr(new_xyz), *_strides3(new_xyz), B, N, S, k,
+                                         ptr(out), ptr(dist), stream_ptr()), "mpb_knn_group_f32")
+    return (out, dist) if return_dist else out
+
+
+# ---------------------------------------------------------------------------------------------
+# a5  sample_and_group: fused gather + centre + concat
+# ---------------------------------------------------------------------------------------------
+class _GroupPoints(torch.autograd.Function):
+    """out[b,s,k] = cat(xyz[b,idx] - new_xyz[b,s], feats[b,idx]) in one kernel (reference :133-138)."""
+
+    @staticmethod
+    def forward(ctx, xyz, feats, new_xyz, idx, ldo):
+        B, N, _ = xyz.shape
+        _, S, K = idx.shape
+        D = 0 if feats is None else feats.shape[2]
+        ldo = max(ldo, 3 + D)
+        new_c = new_xyz.contiguous()
+        idx_c = idx.contiguous()
+        out = torch.empty(B, S, K, ldo, dtype=torch.float32, device=xyz.device)
+        fs = _strides3(feats) if feats is not None else (0, 0, 0)
+        check(_cabi.load().mpb_group_points_f32(ptr(xyz), *_strides3(xyz), ptr(feats), *fs, ptr(new_c), ptr(idx_c),
+                                                B, N, S, K, D, ldo, ptr(out), stream_ptr()), "mpb_group_points_f32")
+        ctx.save_for_backward(idx_c)
+        ctx.dims = (B, N, S, K, D, ldo)
+        ctx.has_feats = feats is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (idx_c,) = ctx.saved_tensors
+        B, N, S, K, D, ldo = ctx.dims
+        go = go.contiguous()
+        need_xyz, need_f, need_new = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_feats, ctx.needs_input_grad[2]
+        gf = torch.zeros(B, N, D, dtype=torch.float32, device=go.device) if need_f else None
+        gx = torch.zeros(B, N, 3, dtype=torch.float32, device=go.device) if need_xyz else None
+        gn = torch.zeros(B, S, 3, dtype=torch.float32, device=go.device) if need_new else None
+        if need_f or need_xyz or need_new:
+            check(_cabi.load().mpb_group_points_bwd_f32(ptr(go), ldo, ptr(idx_c), B, N, S, K, D, ptr(gf), ptr(gx), ptr(gn),
+                                                        stream_ptr()), "mpb_group_points_bwd_f32")
+        return gx, gf, gn, None, None
+
+
+def group_points(xyz, points, new_xyz, idx, ldo=0):
+    """Fused form of reference :133-138.  `ldo` > 3+D zero-pads the last dimension (GEMM K padding)."""
+    return _GroupPoints.apply(xyz, points, new_xyz, idx, ldo)
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, full_points=None, seed_idx=None):
+    """Reference :112-148.  xyz [B,N,3], points [B,N,D]|None -> new_xyz [B,S,3], new_points [B,S,K,3+D]
+    (or [B,S,K,C_full] with `full_points`; 4-tuple with `returnfps`)."""
+    B, N, C = xyz.shape
+    S = npoint
+    fps_idx = farthest_point_sample(xyz, npoint, seed_idx)       # :130
+    new_xyz = index_points(xyz, fps_idx)                          # :131
+    idx = query_ball_point(radius, nsample, xyz, new_xyz)         # :132
+    if points is not None:
+        new_points = group_points(xyz, points, new_xyz, idx)      # :133-138 fused
+    elif full_points is not None:
+        new_points = index_points(full_points, idx)               # :139-141
+    else:
+        new_points = group_points(xyz, None, new_xyz, idx)        # :143
+    if returnfps:
+        return new_xyz, new_points, index_points(xyz, idx), fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """Reference :151-168: new_xyz = zeros [B,1,3]; new_points = cat(xyz, points) as one group [B,1,N,3+D]."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+    grouped_xyz = xyz.reshape(B, 1, N, C)
+    if points is not None:
+        new_points = torch.cat([grouped_xyz, points.reshape(B, 1, N, -1)], dim=-1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points
+
+
+# ---------------------------------------------------------------------------------------------
+# a7  PointNetSetAbstraction
+# ---------------------------------------------------------------------------------------------
+class PointNetSetAbstraction(nn.Module):
+    """Reference :171-216.  Same constructor, attributes and parameter names/shapes
+    (``mlp_convs.{i}.weight [Cout,Cin,1,1]``, ``.bias``, ``mlp_bns.{i}.*``) so state_dicts interchange.
+
+    forward(xyz [B,3,N], points [B,D,N]|None, full_points=None) -> (new_xyz [B,3,S], new_points [B,D',S])
+    """
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last_channel = out_channel
+        self.group_all = group_all
+
+    def forward(self, xyz, points, full_points=None, seed_idx=None):
+        xyz = xyz.permute(0, 2, 1)                                                      # :196
+        if points is not None:
+            points = points.permute(0, 2, 1)
+        if full_points is not None:
+            full_points = full_points.permute(0, 2, 1)
+        if self.group_all:
+            new_xyz, new_points = sample_and_group_all(xyz, points)                     # :203
+        else:
+            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points,
+                                                   full_points=full_points, seed_idx=seed_idx)   # :205
+        new_points = self._shared_mlp_max(new_points)                                   # :208-214
+        return new_xyz.permute(0, 2, 1), new_points
+
+    def _shared_mlp_max(self, grouped):
+        """grouped [B,S,K,C] -> [B,C',S]: per-layer relu(bn(conv1x1)) then max over K (reference :208-214).
+
+        The grouped tensor is already position-major, i.e. the channels-last image [B,C,S,K]; a 1x1
+        conv, BatchNorm and the max over K do not care about the order of the two spatial axes."""
+        x = grouped.permute(0, 3, 1, 2)  # [B,C,S,K] view, channels_last-contiguous
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            x = F.relu(bn(conv(x)))
+        return torch.max(x, 3)[0]
