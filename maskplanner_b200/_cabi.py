@@ -72,10 +72,16 @@ class MpbError(RuntimeError):
     pass
 
 
-def check(rc, what):
+KERNEL_LAUNCHES = 0  # kernels of libmaskplanner_b200.so enqueued so far (bench.py reports the per-step delta)
+
+
+def check(rc, what, launches=1):
+    """Raise on a failed C-ABI call; otherwise account for the kernels it enqueued."""
+    global KERNEL_LAUNCHES
     if rc != 0:
         msg = load().mpb_last_error_string()
         raise MpbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+    KERNEL_LAUNCHES += launches
 
 
 def stream_ptr():

@@ -244,6 +244,10 @@ class PointNetSetAbstraction(nn.Module):
             self.mlp_bns.append(nn.BatchNorm2d(out_channel))
             last_channel = out_channel
         self.group_all = group_all
+        # The reference returns a contiguous [B,C',S] tensor.  Internally features are produced
+        # position-major ([B,S,C']); a caller that immediately feeds the next SA layer (which
+        # permutes back, reference :196-198) can set this to False and skip the transpose copy.
+        self.contiguous_output = True
 
     def forward(self, xyz, points, full_points=None, seed_idx=None):
         xyz = xyz.permute(0, 2, 1)                                                      # :196
@@ -264,7 +268,9 @@ class PointNetSetAbstraction(nn.Module):
 
         The grouped tensor is already position-major, i.e. the channels-last image [B,C,S,K]; a 1x1
         conv, BatchNorm and the max over K do not care about the order of the two spatial axes."""
-        x = grouped.permute(0, 3, 1, 2)  # [B,C,S,K] view, channels_last-contiguous
+        x = grouped  # [B,S,K,C], rows = neighbourhood positions
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            x = F.relu(bn(conv(x)))
-        return torch.max(x, 3)[0]
+            x = F.linear(x, conv.weight.view(conv.out_channels, -1), conv.bias)     # 1x1 conv == row-wise GEMM (strict fp32)
+            x = F.relu(bn(x.permute(0, 3, 1, 2))).permute(0, 2, 3, 1)               # BN over all B*S*K rows per channel
+        out = torch.max(x, 2)[0].permute(0, 2, 1)                                    # [B,S,C'] -> [B,C',S]
+        return out.contiguous() if self.contiguous_output else out

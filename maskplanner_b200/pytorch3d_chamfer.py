@@ -61,7 +61,7 @@ class _ChamferNN(torch.autograd.Function):
         check(_cabi.load().mpb_chamfer_nn_bwd_f32(
             ptr(x), ptr(y), N, P1, P2, D, ptr(x_len), ptr(y_len), ptr(ix) if use_x else None, ptr(iy) if use_y else None,
             ptr(gdx.contiguous()) if use_x else None, ptr(gdy.contiguous()) if use_y else None, ptr(gx), ptr(gy),
-            stream_ptr()), "mpb_chamfer_nn_bwd_f32")
+            stream_ptr()), "mpb_chamfer_nn_bwd_f32", launches=2 + int(use_x) + int(use_y))
         return gx, gy, None, None, None, None
 
 
