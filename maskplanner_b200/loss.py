@@ -1,0 +1,122 @@
+"""The MaskPlanner training loss around the chamfer drop-in (caller side of the hot path).
+
+``asymm_v6_chamfer_with_stroke_masks`` mirrors ``LossHandler.get_asymm_v6_chamfer_with_stroke_masks``
+(loss_handler.py:596-666) with the resolved weights of config=[maskplanner,<cat>,longx_v2]
+(configs/maskplanner/asymm_chamfer_v9.yaml:10-14):
+
+    1. 100 * mean over (B, out_segments) of the pred->GT segment chamfer, no reduction, with matching  (:604-611)
+    2. 100 * GT->pred POINT chamfer on the poses (reverse_asymmetric, mean/mean)                          (:631-636)
+    3. 100 * GT->pred SEGMENT chamfer (reverse_asymmetric, mean/mean)                                    (:642-645)
+    4. stroke-mask loss: Hungarian-matched BCE on masks + weighted BCE on mask confidences              (:816-935)
+
+Terms 1 and 3 use the same tensor pair; ``fused=True`` (default) evaluates both directions of that
+pair in ONE nearest-neighbour launch instead of two full chamfer calls; ``fused=False``
+issues the reference's three ``chamfer_distance`` calls literally (parity tests use both).
+
+The mask loss needs a linear assignment per sample (<= 22 x 22).  The reference builds each cost
+matrix with Python loops and moves it to the host one sample at a time (:860-875).  Here all cost
+matrices come from one batched GEMM on the device (BCE-with-logits against a binary target is
+softplus(x) - x*y, so cost[p,t] = sum_i softplus(x[p,i]) - sum_{i in stroke t} x[p,i]); the
+assignment itself runs on the host with scipy from ONE device->host copy per step.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import pytorch3d_chamfer as CH
+
+
+@dataclass
+class LossConfig:
+    """Resolved loss weights (asymm_chamfer_v9.yaml:10-14, default.yaml explicit_* entries)."""
+    weight_asymm_segment_chamfer: float = 1.0
+    weight_reverse_asymm_point_chamfer: float = 100.0
+    weight_reverse_asymm_segment_chamfer: float = 0.01
+    explicit_weight_stroke_masks: float = 1.0            # target value after delayMasksLoss (delayMasksLoss.yaml:5)
+    explicit_weight_stroke_masks_confidence: float = 100.0
+    explicit_no_stroke_weight: float = 1.0
+    pose_dim: int = 6                                    # get_dim_traj_points(['orientnorm'])
+
+
+def chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=True):
+    """Terms 1-3.  Returns (term1, term2, term3, nn_distance [B,P1], pred_to_gt_match [B,P1] int64)."""
+    B = y_pred.shape[0]
+    points_pred = y_pred.reshape(B, -1, cfg.pose_dim)
+    if fused:
+        x = y_pred.float().contiguous()
+        yy = y.float().contiguous()
+        x_len = torch.full((B,), x.shape[1], dtype=torch.int64, device=x.device)
+        y_len = CH.padded_lengths(yy, None, False)
+        d_x, match, d_y, _ = CH._ChamferNN.apply(x, yy, x_len, y_len, True, True)
+        term1 = 100 * d_x.mean()
+        term3 = 100 * (d_y.sum(1) / y_len).sum() / B
+    else:
+        d_x, _, match, _ = CH.chamfer_distance(y_pred, y, padded=True, asymmetric=True, return_matching=True,
+                                               point_reduction=None, batch_reduction=None)
+        term1 = 100 * d_x.mean()
+        term3 = 100 * CH.chamfer_distance(y_pred, y, padded=True, reverse_asymmetric=True)[0]
+    term2 = 100 * CH.chamfer_distance(points_pred, traj_as_pc, padded=True, reverse_asymmetric=True)[0]
+    return term1, term2, term3, d_x, match
+
+
+def mask_cost_matrices(pred_stroke_masks, target_ids, n_ids):
+    """cost[b,p,t] = sum_i BCEWithLogits(pred[b,p,i], [target_ids[b,i] == t]) and present[b,t] (stroke t
+    owns at least one predicted segment).  Equivalent to loss_handler.py:865-873 for every sample at once."""
+    onehot = F.one_hot(target_ids, n_ids).to(pred_stroke_masks.dtype)            # [B, S, T]
+    sp = F.softplus(pred_stroke_masks).sum(-1, keepdim=True)                     # [B, P, 1]
+    cost = sp - torch.bmm(pred_stroke_masks, onehot)                             # [B, P, T]
+    present = onehot.sum(1) > 0                                                  # [B, T]
+    return cost, present, onehot
+
+
+def hungarian_host(cost, present):
+    """scipy linear_sum_assignment per sample on the present columns (loss_handler.py:875).
+    Returns (batch_idx, pred_idx, target_id) int64 CPU tensors, concatenated over the batch."""
+    from scipy.optimize import linear_sum_assignment
+    c = cost.detach().cpu().numpy()
+    pres = present.cpu().numpy()
+    bi, pi, ti = [], [], []
+    for b in range(c.shape[0]):
+        cols = np.nonzero(pres[b])[0]
+        r, k = linear_sum_assignment(c[b][:, cols])
+        bi.append(np.full(len(r), b, dtype=np.int64))
+        pi.append(r.astype(np.int64))
+        ti.append(cols[k].astype(np.int64))
+    return (torch.from_numpy(np.concatenate(bi)), torch.from_numpy(np.concatenate(pi)), torch.from_numpy(np.concatenate(ti)))
+
+
+def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, cfg):
+    """loss_handler.py:816-935 with smooth_targets=False (binary masks, BCE)."""
+    dev = pred_stroke_masks.device
+    B, n_pred_masks, out_segments = pred_stroke_masks.shape
+    ids = stroke_ids.to(dev).gather(1, pred_to_gt_match)                         # :838  [B, out_segments], float
+    ids = ids.long()                                                             # the -1 padding id is never matched (:852)
+    n_ids = n_pred_masks                                                         # ids < max_n_strokes == n_pred_masks
+    with torch.no_grad():
+        cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids.clamp_min(0), n_ids)
+        b_idx, p_idx, t_idx = hungarian_host(cost, present)                      # :860-877
+        b_idx, p_idx, t_idx = b_idx.to(dev), p_idx.to(dev), t_idx.to(dev)
+    matched_pred = pred_stroke_masks[b_idx, p_idx]                               # :886  [M, out_segments]
+    matched_tgt = onehot.transpose(1, 2)[b_idx, t_idx]                           # :902  [M, out_segments]
+    mask_loss = F.binary_cross_entropy_with_logits(matched_pred, matched_tgt, reduction="none").sum(-1).mean()   # :906
+    target_scores = torch.zeros_like(scores)                                     # :920-921
+    target_scores[b_idx, p_idx] = 1.0
+    weights = torch.full_like(scores, cfg.explicit_no_stroke_weight)             # :924-925
+    weights[b_idx, p_idx] = 1.0
+    conf_loss = F.binary_cross_entropy_with_logits(scores, target_scores, reduction="none", weight=weights).mean()   # :930
+    return cfg.explicit_weight_stroke_masks * mask_loss + cfg.explicit_weight_stroke_masks_confidence * conf_loss
+
+
+def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores, stroke_ids, traj_as_pc, cfg=None,
+                                       fused=True, return_terms=False):
+    """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config."""
+    cfg = cfg or LossConfig()
+    t1, t2, t3, _, match = chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=fused)
+    masks = stroke_masks_loss(match, pred_stroke_masks, mask_scores, stroke_ids, cfg)
+    loss = (cfg.weight_asymm_segment_chamfer * t1 + cfg.weight_reverse_asymm_point_chamfer * t2
+            + cfg.weight_reverse_asymm_segment_chamfer * t3 + masks)
+    if return_terms:
+        return loss, dict(asymm_segment=t1.detach(), reverse_point=t2.detach(), reverse_segment=t3.detach(), masks=masks.detach())
+    return loss

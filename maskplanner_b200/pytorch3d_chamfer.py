@@ -58,10 +58,14 @@ class _ChamferNN(torch.autograd.Function):
         use_y = gdy is not None and iy is not None
         gx = torch.empty_like(x)
         gy = torch.empty_like(y)
+        # keep the contiguous copies alive until the launch is enqueued (a temporary would be handed
+        # back to the caching allocator and could be recycled by the next allocation)
+        gdx_c = gdx.contiguous() if use_x else None
+        gdy_c = gdy.contiguous() if use_y else None
         check(_cabi.load().mpb_chamfer_nn_bwd_f32(
             ptr(x), ptr(y), N, P1, P2, D, ptr(x_len), ptr(y_len), ptr(ix) if use_x else None, ptr(iy) if use_y else None,
-            ptr(gdx.contiguous()) if use_x else None, ptr(gdy.contiguous()) if use_y else None, ptr(gx), ptr(gy),
-            stream_ptr()), "mpb_chamfer_nn_bwd_f32", launches=2 + int(use_x) + int(use_y))
+            ptr(gdx_c), ptr(gdy_c), ptr(gx), ptr(gy), stream_ptr()),
+            "mpb_chamfer_nn_bwd_f32", launches=2 + int(use_x) + int(use_y))
         return gx, gy, None, None, None, None
 
 
@@ -87,8 +91,9 @@ class _KnnPoints(torch.autograd.Function):
         P2 = p2.shape[1]
         g1 = torch.empty_like(p1)
         g2 = torch.empty_like(p2)
+        gd_c = gd.contiguous()
         check(_cabi.load().mpb_knn_points_bwd_f32(ptr(p1), ptr(p2), N, P1, P2, D, ptr(len1), ptr(len2), ptr(i), i.shape[2],
-                                                  ptr(gd.contiguous()), ptr(g1), ptr(g2), stream_ptr()),
+                                                  ptr(gd_c), ptr(g1), ptr(g2), stream_ptr()),
               "mpb_knn_points_bwd_f32")
         return g1, g2, None, None, None
 

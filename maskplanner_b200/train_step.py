@@ -1,0 +1,129 @@
+"""The MaskPlanner training-step body on B200, batch-sharded data parallel (one process per GPU).
+
+Mirrors the step of the reference loop (train_maskplanner.py:183-227): zero_grad -> permute + H2D of
+the batch (:207-208) -> model forward (:210) -> loss (:212-218) -> backward (:220) -> Adam step (:221)
+-> loss.item() (:223).  The reference is single-process; the data-parallel plumbing added here is the
+only collective of the path: every rank owns whole samples (a cloud or a chamfer problem
+never spans GPUs) and the flat fp32 gradient is all-reduced (averaged) once per step with NCCL over
+NVLink.  Parameter gradients are views into ONE flat buffer, so the all-reduce needs no packing
+copies, and the head gradients (>90 % of the parameters, produced first by backward) are reduced on a
+side stream while the encoder backward is still running.
+
+BatchNorm semantics: replica semantics (each rank normalises over its own samples), the standard DDP
+behaviour; single-process-equivalent statistics would need SyncBN and are out of scope for round 1.
+"""
+import torch
+import torch.distributed as dist
+
+from . import loss as L
+from . import regressor
+
+
+class FlatGradBuckets:
+    """All parameter .grad tensors as views into one flat fp32 buffer, split into two buckets:
+    `heads` (everything outside sa1/sa2/sa3) and `encoder`."""
+
+    def __init__(self, model):
+        named = list(model.named_parameters())
+        heads = [p for n, p in named if not n.startswith(("sa1.", "sa2.", "sa3."))]
+        enc = [p for n, p in named if n.startswith(("sa1.", "sa2.", "sa3."))]
+        self.params = heads + enc
+        n_heads = sum(p.numel() for p in heads)
+        total = n_heads + sum(p.numel() for p in enc)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.heads = self.flat[:n_heads]
+        self.encoder = self.flat[n_heads:]
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.head_params = heads
+
+    def zero(self):
+        self.flat.zero_()
+
+
+def shard_range(global_batch, rank, world_size):
+    """Samples [lo, hi) owned by `rank`: contiguous, whole samples, sizes differ by at most one."""
+    base, rem = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_mean_(flat, world_size, group=None):
+    """In-place mean over ranks of a flat gradient bucket (SUM then scale: works on NCCL and gloo)."""
+    if world_size > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world_size)
+    return flat
+
+
+class Trainer:
+    """model + Adam(lr=1e-3) (train_maskplanner.py:159) + loss, optionally data parallel."""
+
+    def __init__(self, category="windows_v2", device=None, lr=1e-3, seed=0, loss_cfg=None, world_size=1, fused_loss=True):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        torch.manual_seed(seed)                       # identical initial weights on every rank
+        self.model = regressor.maskplanner_model(category).to(self.device)
+        self.model.train()
+        self.loss_cfg = loss_cfg or L.LossConfig()
+        self.world_size = world_size
+        self.fused_loss = fused_loss
+        self.buckets = FlatGradBuckets(self.model)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)
+        self.comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
+        self._heads_ready = None
+        self._heads_pending = 0
+        if world_size > 1:
+            # launch the head-bucket all-reduce on the side stream as soon as backward has produced the
+            # LAST head gradient (counted, so no assumption about autograd's execution order)
+            n_heads = len(self.buckets.head_params)
+
+            def hook(_p):
+                self._heads_pending += 1
+                if self._heads_pending == n_heads:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    self.comm_stream.wait_event(ev)
+                    with torch.cuda.stream(self.comm_stream):
+                        all_reduce_mean_(self.buckets.heads, self.world_size)
+                    self._heads_ready = torch.cuda.Event()
+                    self._heads_ready.record(self.comm_stream)
+            for p in self.buckets.head_params:
+                p.register_post_accumulate_grad_hook(hook)
+
+    def to_device(self, host_batch):
+        """The step's H2D boundary (train_maskplanner.py:207-208, loss_handler.py:628-629): pinned -> device, async."""
+        out = {}
+        for k in ("point_cloud", "traj", "traj_as_pc", "stroke_ids"):
+            out[k] = host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True)
+        return out
+
+    def step(self, batch, fps_seeds=None):
+        """One optimisation step on a device-resident batch.  Returns the loss as a 0-d device tensor."""
+        self.buckets.zero()                                                       # model.zero_grad()  (:184)
+        cloud = batch["point_cloud"].permute(0, 2, 1)                             # :207
+        pred, masks, scores, _ = self.model(cloud, fps_seeds)                     # :210
+        loss = L.asymm_v6_chamfer_with_stroke_masks(pred, batch["traj"], masks, scores, batch["stroke_ids"],
+                                                    batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss)   # :212-218
+        self._heads_pending = 0
+        loss.backward()                                                           # :220
+        if self.world_size > 1:
+            all_reduce_mean_(self.buckets.encoder, self.world_size)
+            if self._heads_ready is not None:
+                torch.cuda.current_stream().wait_event(self._heads_ready)
+                self._heads_ready = None
+            else:  # hooks did not all fire (a head without gradient): reduce the bucket here
+                all_reduce_mean_(self.buckets.heads, self.world_size)
+        self.opt.step()                                                           # :221
+        return loss.detach()
+
+    def step_from_host(self, host_batch, fps_seeds=None):
+        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223)."""
+        loss = self.step(self.to_device(host_batch), fps_seeds)
+        return float(loss.item())
+
+
+def pin_batch(batch):
+    return {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}

@@ -222,6 +222,90 @@ def chamfer_fixtures(RC):
     print("chamfer_small.npz:", len(cases), "arrays")
 
 
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def reference_loss_config():
+    """Resolved values of config=[maskplanner,<cat>,longx_v2] that loss_handler.py reads
+    (asymm_chamfer_v9.yaml, default.yaml; mask weights at their post-delay targets, delayMasksLoss.yaml:5-6)."""
+    return _Cfg(lambda_points=4, extra_data=["orientnorm"], per_segment_confidence=False, smooth_target_stroke_masks=False,
+                weight_asymm_segment_chamfer=1.0, weight_reverse_asymm_point_chamfer=100, weight_reverse_asymm_segment_chamfer=0.01,
+                explicit_weight_stroke_masks=1.0, explicit_weight_stroke_masks_confidence=100., explicit_no_stroke_weight=1.0,
+                weight_asymm_v6_chamfer_with_stroke_masks=1.0, soft_attraction=False)
+
+
+def step_fixture():
+    """Whole model + loss + one Adam step: the REAL reference model and LossHandler (CPU, cuda calls shimmed)
+    against oracle/step_oracle.py -- asserted bit-identical, then frozen as scalars / small samples."""
+    from oracle import step_oracle as SO
+    SSG = ref_loader.pointnet2_cls_ssg()
+    LH = ref_loader.loss_handler()
+    cases = {}
+    B = 2
+    batch = synthetic.make_batch(B, "windows_v2", seed0=0)
+    torch.manual_seed(0)
+    ref = SSG.PointNet2Regressor_StrokeMasks(out_vectors=449, outdim=12, outdim_orient=12, weight_orient=0.25,
+                                             hidden_size=[1024, 1024], pred_stroke_masks=True, n_stroke_masks=22,
+                                             mask_confidence_scores=True, segment_confidence_scores=False)
+    mine = SO.Regressor(449, n_stroke_masks=22)
+    mine.load_state_dict(ref.state_dict())
+    lh = LH.LossHandler(["asymm_v6_chamfer_with_stroke_masks"], reference_loss_config())
+    opt_r = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    opt_m = torch.optim.Adam(mine.parameters(), lr=1e-3)
+    cloud = batch["point_cloud"].permute(0, 2, 1).float()
+    ref.train(), mine.train()
+    torch.manual_seed(11)
+    ref.zero_grad()
+    pred, masks, scores, seg = ref(cloud)
+    with ref_loader.cpu_cuda_shim():
+        loss_r, _ = lh.compute(y_pred=pred, y=batch["traj"].clone(), pred_stroke_masks=masks, mask_scores=scores, seg_logits=seg,
+                               stroke_ids=batch["stroke_ids"], traj_as_pc=batch["traj_as_pc"].clone())
+    loss_r.backward()
+    opt_r.step()
+    torch.manual_seed(11)
+    loss_m = SO.train_step(mine, opt_m, batch)            # draws the two FPS seeds and the dropout masks in the same order
+    assert float(loss_r) == loss_m, (float(loss_r), loss_m)
+    for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+        assert torch.equal(p, q), n
+    cases["train/loss"] = np.float64(loss_m)
+    torch.manual_seed(11)
+    s1 = torch.randint(0, 5120, (B,), dtype=torch.long)
+    s2 = torch.randint(0, 512, (B,), dtype=torch.long)
+    cases["seeds1"], cases["seeds2"] = s1.numpy(), s2.numpy()
+    # eval-mode forward on the updated weights: frozen as strided samples of every output
+    ref.eval(), mine.eval()
+    torch.manual_seed(12)
+    with torch.no_grad():
+        a = ref(cloud)
+    torch.manual_seed(12)
+    e1 = torch.randint(0, 5120, (B,), dtype=torch.long)
+    e2 = torch.randint(0, 512, (B,), dtype=torch.long)
+    with torch.no_grad():
+        b = mine(cloud, (e1, e2))
+    for name, x, y in zip(("traj_pred", "masks", "scores"), a[:3], b[:3]):
+        assert torch.equal(x, y), name
+        cases["eval/" + name + "_sample"] = x.reshape(-1)[::97].numpy()
+        cases["eval/" + name + "_sum"] = np.float64(x.double().sum())
+    cases["eval/seeds1"], cases["eval/seeds2"] = e1.numpy(), e2.numpy()
+    # loss terms for fixed predictions (no model involved)
+    g = torch.Generator().manual_seed(0)
+    pred = synthetic.noisy_predictions(batch["traj"], 449, seed=1)
+    masks, scores = torch.randn(B, 22, 449, generator=g), torch.randn(B, 22, generator=g)
+    with ref_loader.cpu_cuda_shim():
+        lr_, _ = lh.compute(y_pred=pred, y=batch["traj"].clone(), pred_stroke_masks=masks, mask_scores=scores, seg_logits=None,
+                            stroke_ids=batch["stroke_ids"], traj_as_pc=batch["traj_as_pc"].clone())
+    lm, terms = SO.asymm_v6_loss(pred, batch["traj"].clone(), masks, scores, batch["stroke_ids"], batch["traj_as_pc"].clone(),
+                                 return_terms=True)
+    assert torch.equal(lr_, lm)
+    cases["loss/total"] = np.float64(lm)
+    for k in ("asymm_segment", "reverse_point", "reverse_segment", "masks"):
+        cases["loss/" + k] = np.float64(terms[k])
+    cases["loss/match"] = terms["match"].numpy().astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "step_small.npz"), **cases)
+    print("step_small.npz:", len(cases), "arrays")
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference tree not found at %s" % ref_loader.REF)
@@ -232,6 +316,7 @@ def main():
     encoder_model_shapes(R)
     sa_module_fixture(R)
     chamfer_fixtures(RC)
+    step_fixture()
 
 
 if __name__ == "__main__":

@@ -68,3 +68,45 @@ def pytorch3d_chamfer():
         sys.modules["pytorch3d.structures.pointclouds"].Pointclouds = Pointclouds
         _cache["cham"] = _load("ref_pytorch3d_chamfer", os.path.join(REF, "pytorch3d_chamfer.py"))
     return _cache["cham"]
+
+
+def loss_handler():
+    """The reference loss_handler.py over MagicMock stubs for its plotting / config imports.
+    Several of its methods hard-code CUDA (`stroke_ids.cuda()`, `.to('cuda')`, `.get_device()`):
+    use `cpu_cuda_shim()` around calls to run them on CPU tensors."""
+    if "loss" not in _cache:
+        from unittest.mock import MagicMock
+        pytorch3d_chamfer()
+        sys.modules["pytorch3d_chamfer"] = _cache["cham"]
+        for name in ("omegaconf", "omegaconf.listconfig", "seaborn", "matplotlib", "matplotlib.pyplot", "matplotlib.path",
+                     "matplotlib.patches", "point_cloud_utils", "pyvista", "wandb"):
+            sys.modules.setdefault(name, MagicMock())
+        if REF not in sys.path:
+            sys.path.insert(0, REF)
+        _cache["loss"] = _load("ref_loss_handler", os.path.join(REF, "loss_handler.py"))
+    return _cache["loss"]
+
+
+class cpu_cuda_shim:
+    """Context manager: makes `.cuda()`, `.to('cuda', ...)` and `.get_device()` no-ops on CPU tensors so the
+    reference's hard-coded device moves can be exercised without a GPU (test infrastructure only)."""
+
+    def __enter__(self):
+        import torch
+        self._t = torch
+        self._cuda, self._to, self._gd = torch.Tensor.cuda, torch.Tensor.to, torch.Tensor.get_device
+        orig_to = self._to
+
+        def to(self_, *a, **k):
+            a = tuple(x for x in a if not (isinstance(x, str) and x.startswith("cuda")) and not (isinstance(x, int) and not isinstance(x, bool)))
+            k = {kk: v for kk, v in k.items() if not (kk == "device" and str(v).startswith("cuda"))}
+            return orig_to(self_, *a, **k) if (a or k) else self_
+
+        torch.Tensor.cuda = lambda self_, *a, **k: self_
+        torch.Tensor.to = to
+        torch.Tensor.get_device = lambda self_: 0
+        return self
+
+    def __exit__(self, *exc):
+        self._t.Tensor.cuda, self._t.Tensor.to, self._t.Tensor.get_device = self._cuda, self._to, self._gd
+        return False

@@ -1,0 +1,155 @@
+"""GPU parity of the caller layer: regressor forward, asymm_v6 loss and one full optimisation step
+against the CPU oracle (oracle/step_oracle.py, itself pinned bit-for-bit to the reference model and
+loss_handler).  fp32 tolerance: rel 1e-4 on outputs / loss terms, 1e-3 on gradients (atomics reorder sums)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import step_oracle as SO
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(category, seed=0):
+    from maskplanner_b200 import regressor, synthetic
+    torch.manual_seed(seed)
+    mine = regressor.maskplanner_model(category)
+    cfg = synthetic.CATEGORIES[category]
+    ref = SO.Regressor(synthetic.out_vectors(cfg["n_pred_traj_points"]), n_stroke_masks=cfg["max_n_strokes"])
+    missing = ref.load_state_dict(mine.state_dict(), strict=True)   # identical names/shapes (checkpoint contract)
+    return mine.cuda(), ref
+
+
+def _close(a, b, rtol, atol_frac=1e-5):
+    a, b = a.detach().cpu().numpy(), b.detach().numpy()
+    return np.allclose(a, b, rtol=rtol, atol=atol_frac * max(np.abs(b).max(), 1e-6))
+
+
+@pytest.mark.parametrize("category", ["windows_v2", "cuboids_v2"])
+def test_regressor_forward_eval_matches_oracle(category):
+    from maskplanner_b200 import synthetic
+    mine, ref = _pair(category)
+    mine.eval(), ref.eval()
+    B = 3
+    cloud = synthetic.make_clouds(B, 5120, seed0=77).permute(0, 2, 1).contiguous()
+    seeds = (torch.tensor([1, 2000, 5119]), torch.tensor([0, 17, 511]))
+    with torch.no_grad():
+        got = mine(cloud.cuda(), seeds)
+        want = ref(cloud, seeds)
+    for g, w in zip(got[:3], want[:3]):
+        assert tuple(g.shape) == tuple(w.shape)
+        assert _close(g, w, 1e-4, 1e-4)
+    assert got[3] is None
+
+
+def test_loss_terms_match_oracle_fused_and_unfused():
+    from maskplanner_b200 import loss as L
+    from maskplanner_b200 import synthetic
+    B = 4
+    batch = synthetic.make_batch(B, "windows_v2", seed0=3)
+    g = torch.Generator().manual_seed(0)
+    pred = synthetic.noisy_predictions(batch["traj"], 449, seed=1)
+    masks = torch.randn(B, 22, 449, generator=g)
+    scores = torch.randn(B, 22, generator=g)
+    want, wt = SO.asymm_v6_loss(pred.clone().requires_grad_(True), batch["traj"].clone(), masks, scores, batch["stroke_ids"],
+                                batch["traj_as_pc"].clone(), return_terms=True)
+    for fused in (True, False):
+        p = pred.clone().cuda().requires_grad_(True)
+        m = masks.clone().cuda().requires_grad_(True)
+        s = scores.clone().cuda().requires_grad_(True)
+        got, gt = L.asymm_v6_chamfer_with_stroke_masks(p, batch["traj"].cuda(), m, s, batch["stroke_ids"].cuda(),
+                                                       batch["traj_as_pc"].cuda(), fused=fused, return_terms=True)
+        for k in ("asymm_segment", "reverse_point", "reverse_segment", "masks"):
+            assert np.isclose(float(gt[k]), float(wt[k]), rtol=1e-4), (fused, k, float(gt[k]), float(wt[k]))
+        assert np.isclose(float(got), float(want), rtol=1e-4)
+        got.backward()
+        if fused:
+            po = pred.clone().requires_grad_(True)
+            mo = masks.clone().requires_grad_(True)
+            so = scores.clone().requires_grad_(True)
+            SO.asymm_v6_loss(po, batch["traj"].clone(), mo, so, batch["stroke_ids"], batch["traj_as_pc"].clone()).backward()
+            assert _close(p.grad, po.grad, 1e-3) and _close(m.grad, mo.grad, 1e-3) and _close(s.grad, so.grad, 1e-3)
+
+
+def test_hungarian_assignment_matches_reference_style_loop():
+    from maskplanner_b200 import loss as L
+    from maskplanner_b200 import synthetic
+    B = 6
+    batch = synthetic.make_batch(B, "cuboids_v2", seed0=9)
+    g = torch.Generator().manual_seed(5)
+    pred = synthetic.noisy_predictions(batch["traj"], 999, seed=2)
+    masks = torch.randn(B, 6, 999, generator=g)
+    scores = torch.randn(B, 6, generator=g)
+    _, terms = SO.asymm_v6_loss(pred, batch["traj"].clone(), masks, scores, batch["stroke_ids"], batch["traj_as_pc"].clone(), return_terms=True)
+    bi, pi, ti = terms["assignment"]          # ti indexes the sample's sorted distinct ids
+    ids = batch["stroke_ids"].gather(1, terms["match"]).long()
+    cost, present, _ = L.mask_cost_matrices(masks.cuda(), ids.cuda(), 6)
+    gb, gp, gt = L.hungarian_host(cost, present)
+    assert torch.equal(gb, bi) and torch.equal(gp, pi)
+    # map the oracle's "k-th distinct id" to the id itself
+    want_ids = torch.stack([torch.unique(ids[b])[t] for b, t in zip(bi.tolist(), ti.tolist())])
+    assert torch.equal(gt, want_ids)
+
+
+def test_full_training_step_matches_oracle():
+    """One optimisation step, dropout disabled (CPU and CUDA generators differ), same FPS seeds:
+    loss, a sample of gradients and the updated parameters."""
+    from maskplanner_b200 import synthetic
+    from maskplanner_b200.train_step import Trainer
+    B = 4
+    tr = Trainer("windows_v2", torch.device("cuda", 0), seed=3)
+    cfg = synthetic.CATEGORIES["windows_v2"]
+    ref = SO.Regressor(synthetic.out_vectors(cfg["n_pred_traj_points"]), n_stroke_masks=cfg["max_n_strokes"])
+    ref.load_state_dict(tr.model.state_dict())
+    tr.model.dropout.p = 0.0
+    ref.dropout.p = 0.0
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    batch = synthetic.make_batch(B, "windows_v2", seed0=21)
+    seeds = (torch.tensor([5, 50, 500, 5000]), torch.tensor([1, 10, 100, 511]))
+    want = SO.train_step(ref, opt, batch, seeds)
+    got = float(tr.step(tr.to_device(batch), seeds).item())
+    assert np.isclose(got, want, rtol=2e-4), (got, want)
+    ref_params = dict(ref.named_parameters())
+    for n, p in tr.model.named_parameters():
+        w = ref_params[n]
+        gscale = float(w.grad.abs().max())
+        assert np.allclose(p.grad.cpu().numpy(), w.grad.numpy(), rtol=5e-3, atol=2e-3 * gscale + 1e-12), n
+    # BatchNorm running statistics of the encoder updated identically (momentum 0.1, unbiased variance)
+    sd_r = ref.state_dict()
+    for k, v in tr.model.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            assert np.allclose(v.cpu().numpy(), sd_r[k].numpy(), rtol=1e-3, atol=1e-5), k
+
+
+def test_step_golden_from_the_real_reference(golden):
+    """Eval forward and loss terms against values frozen from the REAL reference model / LossHandler."""
+    from maskplanner_b200 import loss as L
+    from maskplanner_b200 import regressor, synthetic
+    g = golden("step_small.npz")
+    B = 2
+    batch = synthetic.make_batch(B, "windows_v2", seed0=0)
+    gen = torch.Generator().manual_seed(0)
+    pred = synthetic.noisy_predictions(batch["traj"], 449, seed=1)
+    masks, scores = torch.randn(B, 22, 449, generator=gen), torch.randn(B, 22, generator=gen)
+    total, terms = L.asymm_v6_chamfer_with_stroke_masks(pred.cuda(), batch["traj"].cuda(), masks.cuda(), scores.cuda(),
+                                                        batch["stroke_ids"].cuda(), batch["traj_as_pc"].cuda(), return_terms=True)
+    assert np.isclose(float(total), float(g["loss/total"]), rtol=1e-4)
+    for k in ("asymm_segment", "reverse_point", "reverse_segment", "masks"):
+        assert np.isclose(float(terms[k]), float(g["loss/" + k]), rtol=1e-4), k
+    # replay the reference's training step on the CPU oracle to get the post-step weights, then compare eval forwards
+    torch.manual_seed(0)
+    ref = SO.Regressor(449, n_stroke_masks=22)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    ref.train()
+    torch.manual_seed(11)
+    assert SO.train_step(ref, opt, batch) == float(g["train/loss"])
+    mine = regressor.maskplanner_model("windows_v2")
+    mine.load_state_dict(ref.state_dict())
+    mine.cuda().eval()
+    with torch.no_grad():
+        out = mine(batch["point_cloud"].permute(0, 2, 1).cuda(), (torch.from_numpy(g["eval/seeds1"]), torch.from_numpy(g["eval/seeds2"])))
+    for name, x in zip(("traj_pred", "masks", "scores"), out[:3]):
+        want = g["eval/" + name + "_sample"]
+        got = x.reshape(-1)[::97].cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max()), name

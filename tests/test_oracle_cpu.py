@@ -213,3 +213,62 @@ def test_live_reference_chamfer_wrapper():
         assert torch.equal(a[0], b[0])
         if kw.get("return_matching"):
             assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+
+
+def test_step_oracle_matches_golden(golden):
+    """Whole model + loss + Adam step, frozen from the real reference model and LossHandler (step_small.npz)."""
+    from maskplanner_b200 import synthetic
+    from oracle import step_oracle as SO
+    g = golden("step_small.npz")
+    B = 2
+    batch = synthetic.make_batch(B, "windows_v2", seed0=0)
+    torch.manual_seed(0)
+    m = SO.Regressor(449, n_stroke_masks=22)       # same construction order as the reference class => same init draw
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    m.train()
+    torch.manual_seed(11)
+    loss = SO.train_step(m, opt, batch)
+    assert loss == float(g["train/loss"])
+    m.eval()
+    with torch.no_grad():
+        out = m(batch["point_cloud"].permute(0, 2, 1).float(), (torch.from_numpy(g["eval/seeds1"]), torch.from_numpy(g["eval/seeds2"])))
+    for name, x in zip(("traj_pred", "masks", "scores"), out[:3]):
+        assert np.array_equal(x.reshape(-1)[::97].numpy(), g["eval/" + name + "_sample"]), name
+    gen = torch.Generator().manual_seed(0)
+    pred = synthetic.noisy_predictions(batch["traj"], 449, seed=1)
+    masks, scores = torch.randn(B, 22, 449, generator=gen), torch.randn(B, 22, generator=gen)
+    total, terms = SO.asymm_v6_loss(pred, batch["traj"].clone(), masks, scores, batch["stroke_ids"], batch["traj_as_pc"].clone(),
+                                    return_terms=True)
+    assert float(total) == float(g["loss/total"])
+    for k in ("asymm_segment", "reverse_point", "reverse_segment", "masks"):
+        assert float(terms[k]) == float(g["loss/" + k]), k
+    assert np.array_equal(terms["match"].numpy(), g["loss/match"])
+
+
+@needs_ref
+def test_live_reference_model_and_loss_handler():
+    """The real PointNet2Regressor_StrokeMasks + LossHandler (its .cuda() calls shimmed to CPU) vs the oracle."""
+    from maskplanner_b200 import synthetic
+    from oracle import step_oracle as SO
+    from oracle.make_golden import reference_loss_config
+    SSG, LH = ref_loader.pointnet2_cls_ssg(), ref_loader.loss_handler()
+    torch.manual_seed(4)
+    ref = SSG.PointNet2Regressor_StrokeMasks(out_vectors=999, outdim=12, outdim_orient=12, weight_orient=0.25, hidden_size=[1024, 1024],
+                                             pred_stroke_masks=True, n_stroke_masks=6, mask_confidence_scores=True)
+    mine = SO.Regressor(999, n_stroke_masks=6)
+    mine.load_state_dict(ref.state_dict())
+    ref.eval(), mine.eval()
+    batch = synthetic.make_batch(2, "cuboids_v2", seed0=8)
+    cloud = batch["point_cloud"].permute(0, 2, 1)
+    torch.manual_seed(1)
+    a = ref(cloud)
+    torch.manual_seed(1)
+    s = (torch.randint(0, 5120, (2,)), torch.randint(0, 512, (2,)))
+    b = mine(cloud, s)
+    assert all(torch.equal(x, y) for x, y in zip(a[:3], b[:3]))
+    lh = LH.LossHandler(["asymm_v6_chamfer_with_stroke_masks"], reference_loss_config())
+    with ref_loader.cpu_cuda_shim():
+        lr_, _ = lh.compute(y_pred=a[0], y=batch["traj"].clone(), pred_stroke_masks=a[1], mask_scores=a[2], seg_logits=None,
+                            stroke_ids=batch["stroke_ids"], traj_as_pc=batch["traj_as_pc"].clone())
+    lm = SO.asymm_v6_loss(b[0], batch["traj"].clone(), b[1], b[2], batch["stroke_ids"], batch["traj_as_pc"].clone())
+    assert torch.equal(lr_, lm)
