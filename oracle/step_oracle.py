@@ -76,18 +76,18 @@ def stroke_masks_loss(match, pred_masks, scores, stroke_ids, w_masks=1.0, w_conf
         for pm, tm in zip(pred_masks, tgt_masks):                                              # :862
             nt = tm.shape[0]
             a = pm.repeat_interleave(nt, dim=0)                                                # :867
-            b = tm.repeat(P, 1).float()                                                        # :868
+            b = tm.repeat(P, 1).to(pm.dtype)                                                  # :868
             cost = F.binary_cross_entropy_with_logits(a, b, reduction="none").sum(-1).view(P, nt)   # :871-873
             pairs.append(linear_sum_assignment(cost.numpy()))                                  # :875
     bi = torch.cat([torch.full((len(r),), i, dtype=torch.int64) for i, (r, _) in enumerate(pairs)])
     pi = torch.cat([torch.as_tensor(r, dtype=torch.int64) for r, _ in pairs])
     ti = torch.cat([torch.as_tensor(c, dtype=torch.int64) for _, c in pairs])
     matched_pred = pred_masks[bi, pi]                                                          # :886
-    matched_tgt = torch.stack([tgt_masks[b][t] for b, t in zip(bi.tolist(), ti.tolist())]).float()    # :896-902
+    matched_tgt = torch.stack([tgt_masks[b][t] for b, t in zip(bi.tolist(), ti.tolist())]).to(pred_masks.dtype)    # :896-902
     mask_loss = F.binary_cross_entropy_with_logits(matched_pred, matched_tgt, reduction="none").sum(-1).mean()   # :906
-    tgt_scores = torch.zeros(scores.shape)                                                     # :920-921
+    tgt_scores = torch.zeros(scores.shape, dtype=scores.dtype)                                 # :920-921
     tgt_scores[bi, pi] = 1.0
-    w = no_stroke_weight * torch.ones(scores.shape)                                            # :924-925
+    w = no_stroke_weight * torch.ones(scores.shape, dtype=scores.dtype)                        # :924-925
     w[bi, pi] = 1.0
     conf = F.binary_cross_entropy_with_logits(scores, tgt_scores, reduction="none", weight=w).mean()   # :930
     return w_masks * mask_loss + w_conf * conf, (bi, pi, ti)

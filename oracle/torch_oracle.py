@@ -139,8 +139,18 @@ class _KnnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, p1, p2, len1, len2, K):
-        d, i = c_oracle.knn(p1, p2, len1, len2, K=K, use_fma=True)
-        d, i = torch.from_numpy(d), torch.from_numpy(i)
+        if p1.dtype == torch.float64:
+            # float64 "ground truth" variant (tests use it to separate conditioning from kernel error):
+            # brute force in torch, same candidate/length/tie rules (stable sort => lowest index first)
+            full = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+            full = full.masked_fill(torch.arange(p2.shape[1])[None, None, :] >= len2[:, None, None], float("inf"))
+            d, i = torch.sort(full, dim=-1, stable=True)
+            d, i = d[:, :, :K].clone(), i[:, :, :K].clone()
+            dead = (torch.arange(p1.shape[1])[None, :, None] >= len1[:, None, None]) | torch.isinf(d)
+            d, i = d.masked_fill(dead, 0.0), i.masked_fill(dead, 0)
+        else:
+            d, i = c_oracle.knn(p1, p2, len1, len2, K=K, use_fma=True)
+            d, i = torch.from_numpy(d), torch.from_numpy(i)
         ctx.save_for_backward(p1, p2, len1, len2, i)
         ctx.mark_non_differentiable(i)
         return d, i
@@ -170,7 +180,8 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
         lengths1 = torch.full((N,), P1, dtype=torch.int64)
     if lengths2 is None:
         lengths2 = torch.full((N,), P2, dtype=torch.int64)
-    d, i = _KnnFn.apply(p1.contiguous().float(), p2.contiguous().float(), lengths1.long(), lengths2.long(), K)
+    keep = torch.float64 if p1.dtype == torch.float64 else torch.float32
+    d, i = _KnnFn.apply(p1.contiguous().to(keep), p2.contiguous().to(keep), lengths1.long(), lengths2.long(), K)
     nn_pts = knn_gather(p2, i, lengths2) if return_nn else None
     return KNN(d, i, nn_pts)
 

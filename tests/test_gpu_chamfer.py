@@ -95,11 +95,11 @@ def test_padded_lengths_on_device(CH):
     y[3, 0:] = -100
     y[4, 39:] = -100
     got = CH.padded_lengths(y.cuda(), None, False).cpu()
-    assert got.tolist() == [40, 10, 0, 40, 39]
+    assert got.tolist() == [40, 10, 40, 0, 39]
     # caller-supplied lengths are only overwritten when some sample is padded (reference :140)
     user = torch.tensor([7, 7, 7, 7, 7]).cuda()
     assert CH.padded_lengths(torch.randn(5, 40, 6).cuda(), user.clone(), True).cpu().tolist() == [7] * 5
-    assert CH.padded_lengths(y.cuda(), user.clone(), True).cpu().tolist() == [40, 10, 0, 40, 39]
+    assert CH.padded_lengths(y.cuda(), user.clone(), True).cpu().tolist() == [40, 10, 40, 0, 39]
 
 
 @pytest.mark.parametrize("D", [2, 5, 16, 33])

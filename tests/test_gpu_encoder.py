@@ -173,8 +173,8 @@ def test_index_points_and_group_backward_match_autograd(P):
     w = torch.rand(B, S, K, 3 + D, generator=g)
 
     def run(ix_fn, grp_fn, dev):
-        x = xyz.to(dev).requires_grad_(True)
-        f = feats.to(dev).requires_grad_(True)
+        x = xyz.detach().clone().to(dev).requires_grad_(True)
+        f = feats.detach().clone().to(dev).requires_grad_(True)
         new_xyz = ix_fn(x, fidx.to(dev))
         out = grp_fn(x, f, new_xyz, idx.to(dev))
         (out * w.to(dev)).sum().backward()
@@ -218,9 +218,12 @@ def test_set_abstraction_module_golden(P, golden, mode):
         grads = torch.autograd.grad(loss, [feats] + list(sa.parameters()))
         scale = np.abs(g["train/grad_feats"]).max()
         assert np.allclose(grads[0].cpu().numpy(), g["train/grad_feats"], rtol=1e-3, atol=1e-4 * scale)
+        gmax = max(np.abs(g["train/grad/sa." + n]).max() for n, _ in sa.named_parameters())
         for (n, _), gr in zip(sa.named_parameters(), grads[1:]):
             want = g["train/grad/sa." + n]
-            assert np.allclose(gr.cpu().numpy(), want, rtol=1e-3, atol=1e-4 * max(np.abs(want).max(), 1e-3)), n
+            # conv biases feed a training-mode BatchNorm: their true gradient is 0 and both sides hold
+            # rounding noise, so the absolute floor is tied to the layer-wide gradient scale
+            assert np.allclose(gr.cpu().numpy(), want, rtol=1e-3, atol=1e-5 * gmax), n
         for k, v in sa.state_dict().items():
             assert np.allclose(v.cpu().numpy(), g["sa.after_train/" + k], rtol=1e-4, atol=1e-6), k
 

@@ -225,23 +225,24 @@ def test_step_oracle_matches_golden(golden):
     torch.manual_seed(0)
     m = SO.Regressor(449, n_stroke_masks=22)       # same construction order as the reference class => same init draw
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
-    m.train()
-    torch.manual_seed(11)
-    loss = SO.train_step(m, opt, batch)
-    assert loss == float(g["train/loss"])
     m.eval()
     with torch.no_grad():
         out = m(batch["point_cloud"].permute(0, 2, 1).float(), (torch.from_numpy(g["eval/seeds1"]), torch.from_numpy(g["eval/seeds2"])))
     for name, x in zip(("traj_pred", "masks", "scores"), out[:3]):
-        assert np.array_equal(x.reshape(-1)[::97].numpy(), g["eval/" + name + "_sample"]), name
+        want = g["eval/" + name + "_sample"]
+        assert np.allclose(x.reshape(-1)[::97].numpy(), want, rtol=1e-5, atol=1e-6 * np.abs(want).max()), name
+    m.train()
+    torch.manual_seed(11)
+    loss = SO.train_step(m, opt, batch)
+    assert np.isclose(loss, float(g["train/loss"]), rtol=1e-6)
     gen = torch.Generator().manual_seed(0)
     pred = synthetic.noisy_predictions(batch["traj"], 449, seed=1)
     masks, scores = torch.randn(B, 22, 449, generator=gen), torch.randn(B, 22, generator=gen)
     total, terms = SO.asymm_v6_loss(pred, batch["traj"].clone(), masks, scores, batch["stroke_ids"], batch["traj_as_pc"].clone(),
                                     return_terms=True)
-    assert float(total) == float(g["loss/total"])
+    assert np.isclose(float(total), float(g["loss/total"]), rtol=1e-6)
     for k in ("asymm_segment", "reverse_point", "reverse_segment", "masks"):
-        assert float(terms[k]) == float(g["loss/" + k]), k
+        assert np.isclose(float(terms[k]), float(g["loss/" + k]), rtol=1e-6), k
     assert np.array_equal(terms["match"].numpy(), g["loss/match"])
 
 
