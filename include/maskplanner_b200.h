@@ -136,7 +136,57 @@ MPB_API int mpb_knn_points_bwd_f32(const float *p1, const float *p2, int N, int 
                                    int K, const float *grad_dists, float *grad_p1, float *grad_p2,
                                    void *stream);
 
-/* `padded=True` length scan                              pytorch3d_chamfer.py:138-149 ----------
+/* ---- a7: PointNetSetAbstraction's shared MLP        models/pointnet2_utils.py:208-214 -------------
+ * relu(bn(conv1x1(x))) per layer then max over the K neighbours.  The 1x1 conv over [B,C,K,S] is the
+ * row-wise GEMM Z[M,Cout] = A[M,Cin] * W[Cout,Cin]^T (M = B*S*K); activations travel as bf16 [M,C]
+ * row-major with C a multiple of 64 (zero padded), accumulation / statistics in fp32.
+ *
+ * mpb_group_points_bf16 / _bwd_bf16: a5 with bf16 output (the GEMM's A operand, zero padded to ldo).
+ * mpb_gemm_bf16_tn:    C[M,N] = A[M,K] * B[N,K]^T   (tcgen05 + TMA; K % 64 == 0, N % 32 == 0;
+ *                      C is bf16, or fp32 when out_fp32 != 0).  Forward (B = W) and dgrad (A = dZ, B = W^T).
+ * mpb_gemm_bf16_wgrad: dW[N,K] (fp32, caller zero-fills) += dZ[M,N]^T * A[M,K]   (K % 64 == 0, N % 8 == 0).
+ * mpb_bn_*:            training-mode BatchNorm2d statistics, normalise + ReLU (+ max-pool with arg-max),
+ *                      and the matching backward; `partials` is a [nparts, 2, C] fp32 workspace with
+ *                      nparts = mpb_bn_stat_partials(rows, C).  running_mean / running_var are updated in
+ *                      place (momentum, unbiased variance) like nn.BatchNorm2d; the conv bias only enters
+ *                      the running mean.  coef is a [3, C] fp32 workspace produced by _bwd_finalize. */
+MPB_API int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                                  const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                                  const float *new_xyz, const int64_t *idx, int B, int N, int S,
+                                  int K, int D, int ldo, void *out, void *stream);
+MPB_API int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const int64_t *idx, int B,
+                                      int N, int S, int K, int D, float *grad_feats,
+                                      float *grad_xyz, float *grad_new_xyz, void *stream);
+MPB_API int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, int N, int K,
+                             int out_fp32, void *stream);
+MPB_API int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int M, int N, int K,
+                                void *stream);
+MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
+MPB_API int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *partials, int nparts,
+                                 void *stream);
+MPB_API int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int64_t M,
+                                const float *bias, const float *gamma, const float *beta,
+                                float *running_mean, float *running_var, float momentum, float eps,
+                                float *scale, float *shift, float *mean, float *rstd, void *stream);
+MPB_API int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *shift, int64_t M,
+                             int C, void *A, void *stream);
+MPB_API int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const float *shift, int64_t G,
+                                 int K, int C, float *out, int32_t *argmax, void *stream);
+/* Backward: exactly one of dA (dense upstream gradient, bf16 [M,C]) and dOut (pooled upstream gradient,
+ * fp32 [M/K, C], with argmax and K) is non-NULL. */
+MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,
+                                  const void *Z, const float *scale, const float *shift,
+                                  const float *mean, const float *rstd, int64_t M, int C,
+                                  float *partials, int nparts, void *stream);
+MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int64_t M,
+                                    const float *gamma, const float *rstd, float *dgamma,
+                                    float *dbeta, float *coef, void *stream);
+MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,
+                                  const void *Z, const float *scale, const float *shift,
+                                  const float *mean, const float *rstd, const float *coef,
+                                  int64_t M, int C, void *dZ, void *stream);
+
+/* `padded=True` length scan                             pytorch3d_chamfer.py:138-149 ----------
  * first[n] = first j with y[n,j,0] == sentinel, else P2; *any_flag (int32, caller zero-fills) is
  * set to 1 if any sample is padded.  No host synchronisation (the reference does 2N of them). */
 MPB_API int mpb_padded_lengths_f32(const float *y, int N, int P2, int D, float sentinel,

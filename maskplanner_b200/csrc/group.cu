@@ -6,6 +6,8 @@
 //
 // These are pure data movement (HBM/L2-bound): one thread per output element, channel index
 // fastest so that both the gathered row read and the output write are coalesced.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mpb {
@@ -34,10 +36,16 @@ __global__ void index_points_bwd_kernel(const float *__restrict__ go, const int6
     }
 }
 
+__device__ __forceinline__ void store_as(float *p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float load_as(const float *p) { return *p; }
+__device__ __forceinline__ float load_as(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+template <typename OutT>
 __global__ void group_points_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc,
                                     const float *__restrict__ feats, int64_t fsb, int64_t fsn, int64_t fsc,
                                     const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int S,
-                                    int K, int D, int ldo, int64_t total, float *__restrict__ out)
+                                    int K, int D, int ldo, int64_t total, OutT *__restrict__ out)
 {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(e % ldo);
@@ -52,11 +60,12 @@ __global__ void group_points_kernel(const float *__restrict__ xyz, int64_t xsb, 
         } else if (c < 3 + D) {
             if (ok) v = feats[b * fsb + i * fsn + (int64_t)(c - 3) * fsc];               // :137-138
         }
-        out[e] = v;
+        store_as(out + e, v);
     }
 }
 
-__global__ void group_points_bwd_kernel(const float *__restrict__ go, int ldo, const int64_t *__restrict__ idx, int N,
+template <typename InT>
+__global__ void group_points_bwd_kernel(const InT *__restrict__ go, int ldo, const int64_t *__restrict__ idx, int N,
                                         int S, int K, int D, int64_t total, float *__restrict__ gfeats,
                                         float *__restrict__ gxyz, float *__restrict__ gnew)
 {
@@ -68,7 +77,7 @@ __global__ void group_points_bwd_kernel(const float *__restrict__ go, int ldo, c
         const int64_t b = bs / S;
         const int64_t i = idx[row];
         if (i < 0 || i >= N) continue;
-        const float g = go[row * ldo + c];
+        const float g = load_as(go + row * ldo + c);
         if (c < 3) {
             if (gxyz) atomicAdd(gxyz + (b * N + i) * 3 + c, g);
             if (gnew) atomicAdd(gnew + bs * 3 + c, -g);
@@ -122,7 +131,7 @@ extern "C" int mpb_group_points_f32(const float *xyz, int64_t xsb, int64_t xsn, 
     if (total == 0) return MPB_OK;
     MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
     MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
-    group_points_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc,
+    group_points_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc,
                                                                                new_xyz, idx, N, S, K, D, ldo, total, out);
     return check_launch("group_points_kernel");
 }
@@ -136,7 +145,39 @@ extern "C" int mpb_group_points_bwd_f32(const float *grad_out, int ldo, const in
     const int64_t total = (int64_t)B * S * K * (3 + D);
     if (total == 0) return MPB_OK;
     MPB_REQUIRE(grad_out && idx, "null pointer");
-    group_points_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, ldo, idx, N, S, K, D, total,
+    group_points_bwd_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, ldo, idx, N, S, K, D, total,
                                                                                    grad_feats, grad_xyz, grad_new_xyz);
     return check_launch("group_points_bwd_kernel");
+}
+
+// bf16 variants feeding / fed by the tensor-core shared MLP (sa_gemm.cu): same gather + centre + concat,
+// rounded to bf16 on the way out, last dimension zero-padded to `ldo` (the GEMM's K padding).
+extern "C" int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats,
+                                     int64_t fsb, int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx, int B,
+                                     int N, int S, int K, int D, int ldo, void *out, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "negative size");
+    MPB_REQUIRE(ldo >= 3 + D, "ldo < 3 + D");
+    const int64_t total = (int64_t)B * S * K * ldo;
+    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
+    MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
+    group_points_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total, (__nv_bfloat16 *)out);
+    return check_launch("group_points_kernel<bf16>");
+}
+
+extern "C" int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const int64_t *idx, int B, int N, int S, int K, int D,
+                                         float *grad_feats, float *grad_xyz, float *grad_new_xyz, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "negative size");
+    MPB_REQUIRE(ldo >= 3 + D, "ldo < 3 + D");
+    const int64_t total = (int64_t)B * S * K * (3 + D);
+    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(grad_out && idx, "null pointer");
+    group_points_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total, grad_feats, grad_xyz, grad_new_xyz);
+    return check_launch("group_points_bwd_kernel<bf16>");
 }
