@@ -164,7 +164,8 @@ MPB_API int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int M,
 MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
 MPB_API int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *partials, int nparts,
                                  void *stream);
-MPB_API int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int64_t M,
+/* C_valid <= C: channels >= C_valid are alignment padding (scale = shift = 0, no parameter access). */
+MPB_API int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                 const float *bias, const float *gamma, const float *beta,
                                 float *running_mean, float *running_var, float momentum, float eps,
                                 float *scale, float *shift, float *mean, float *rstd, void *stream);
@@ -178,7 +179,7 @@ MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32
                                   const void *Z, const float *scale, const float *shift,
                                   const float *mean, const float *rstd, int64_t M, int C,
                                   float *partials, int nparts, void *stream);
-MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int64_t M,
+MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                     const float *gamma, const float *rstd, float *dgamma,
                                     float *dbeta, float *coef, void *stream);
 MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,

@@ -82,12 +82,17 @@ colstats_kernel(const __nv_bfloat16 *__restrict__ Z, int64_t M, int C, float *__
 
 // One CTA.  Training: batch statistics -> scale/shift/mean/rstd, running stats updated in place.
 // (conv bias only moves the mean: BN(z + b) == BN(z); it enters the running mean, reference :210-212.)
-__global__ void bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, double M, const float *__restrict__ bias,
-                                   const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var, float momentum, float eps, float *__restrict__ scale,
-                                   float *__restrict__ shift, float *__restrict__ mean_out, float *__restrict__ rstd_out)
+__global__ void bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
+                                   const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float *__restrict__ running_mean, float *__restrict__ running_var, float momentum, float eps,
+                                   float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
+                                   float *__restrict__ rstd_out)
 {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (c >= C_valid) {  // zero-padded channel (GEMM alignment): contributes exact zeros downstream
+            scale[c] = shift[c] = mean_out[c] = rstd_out[c] = 0.f;
+            continue;
+        }
         double s = 0.0, q = 0.0;
         for (int p = 0; p < nparts; ++p) {
             s += (double)partials[(size_t)p * 2 * C + c];
@@ -191,11 +196,15 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
 }
 
 // dgamma = sum dY*zhat, dbeta = sum dY; coef[0][c] = gamma*rstd, coef[1][c] = mean(dY), coef[2][c] = mean(dY*zhat)
-__global__ void bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, double M, const float *__restrict__ gamma,
-                                    const float *__restrict__ rstd, float *__restrict__ dgamma, float *__restrict__ dbeta,
-                                    float *__restrict__ coef)
+__global__ void bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
+                                    const float *__restrict__ gamma, const float *__restrict__ rstd, float *__restrict__ dgamma,
+                                    float *__restrict__ dbeta, float *__restrict__ coef)
 {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (c >= C_valid) {
+            coef[c] = coef[C + c] = coef[2 * C + c] = 0.f;
+            continue;
+        }
         double s = 0.0, q = 0.0;
         for (int p = 0; p < nparts; ++p) {
             s += (double)partials[(size_t)p * 2 * C + c];
@@ -274,14 +283,15 @@ extern "C" int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *part
     return check_launch("colstats_kernel");
 }
 
-extern "C" int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int64_t M, const float *bias, const float *gamma,
-                                   const float *beta, float *running_mean, float *running_var, float momentum, float eps,
-                                   float *scale, float *shift, float *mean, float *rstd, void *stream)
+extern "C" int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M, const float *bias,
+                                   const float *gamma, const float *beta, float *running_mean, float *running_var, float momentum,
+                                   float eps, float *scale, float *shift, float *mean, float *rstd, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(partials && scale && shift && mean && rstd && C > 0 && nparts > 0 && M > 0, "bad argument");
-    bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, (double)M, bias, gamma, beta, running_mean, running_var,
-                                                            momentum, eps, scale, shift, mean, rstd);
+    MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
+    bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, bias, gamma, beta, running_mean,
+                                                            running_var, momentum, eps, scale, shift, mean, rstd);
     return check_launch("bn_finalize_kernel");
 }
 
@@ -330,12 +340,13 @@ extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const in
     return check_launch("bwd_stats kernel");
 }
 
-extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int64_t M, const float *gamma, const float *rstd,
-                                       float *dgamma, float *dbeta, float *coef, void *stream)
+extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M, const float *gamma,
+                                       const float *rstd, float *dgamma, float *dbeta, float *coef, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(partials && rstd && coef && C > 0 && nparts > 0 && M > 0, "bad argument");
-    bwd_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, (double)M, gamma, rstd, dgamma, dbeta, coef);
+    MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
+    bwd_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, rstd, dgamma, dbeta, coef);
     return check_launch("bwd_finalize_kernel");
 }
 

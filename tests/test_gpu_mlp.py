@@ -1,0 +1,156 @@
+"""Tensor-core shared MLP (tcgen05 GEMMs + bf16 BN/ReLU/max-pool kernels, maskplanner_b200.shared_mlp):
+GEMM kernels against fp32 matmul, and the fused forward/backward against a torch emulation that rounds to
+bf16 at exactly the same points (so what is compared is the kernels, not the conditioning of the network).
+Tolerances: fp32-output GEMM rel 1e-5; bf16-output GEMM rel 1e-2 (one bf16 rounding = 2^-9); fused stack
+rel-L2 1e-2 on outputs and gradients."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from maskplanner_b200 import _cabi
+    return _cabi
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 128, 192), (4096, 256, 128), (8192, 512, 320), (8192, 1024, 512),
+                                   (300, 160, 64), (70000, 64, 64), (5, 32, 64)])
+def test_gemm_tn_matches_fp32_matmul(M, N, K):
+    c = _lib()
+    lib = c.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    want = A.float() @ B.float().t()
+    for f32, tol in ((1, 1e-5), (0, 1e-2)):
+        C = torch.empty(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+        c.check(lib.mpb_gemm_bf16_tn(c.ptr(A), c.ptr(B), c.ptr(C), M, N, K, f32, c.stream_ptr()), "gemm")
+        err = float((C.float() - want).abs().max() / want.abs().max())
+        assert err < tol, (f32, err)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 64), (1024, 64, 64), (5000, 128, 192), (100000, 256, 128), (8192, 1024, 512),
+                                   (8192, 256, 320), (777, 64, 64)])
+def test_gemm_wgrad_matches_fp32_matmul(M, N, K):
+    c = _lib()
+    lib = c.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    dZ = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    dW = torch.zeros(N, K, device="cuda")
+    c.check(lib.mpb_gemm_bf16_wgrad(c.ptr(dZ), c.ptr(A), c.ptr(dW), M, N, K, c.stream_ptr()), "wgrad")
+    want = dZ.float().t() @ A.float()
+    assert float((dW - want).abs().max() / want.abs().max()) < 1e-4
+
+
+def _emulate(a0, K, convs, bns):
+    """Same math as the kernels in plain torch, rounding to bf16 where the kernels store bf16."""
+    x = a0.float()
+    M = x.shape[0]
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        cout, cin = conv.weight.shape[:2]
+        w = conv.weight.view(cout, cin).bfloat16().float()
+        z = (x[:, :cin] @ w.t()).bfloat16().float()
+        mean, var = z.mean(0), z.var(0, unbiased=False)
+        s = bn.weight / torch.sqrt(var + bn.eps)
+        x = F.relu(z * s + (bn.bias - mean * s))
+        if i < len(convs) - 1:
+            x = x.bfloat16().float()
+    return x.view(M // K, K, -1).max(1)[0]
+
+
+def _rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+@pytest.mark.parametrize("G,K,cin,mlp", [(64, 12, 9, [16, 24, 32]), (2, 40, 35, [32, 48]), (512, 32, 3, [64, 64, 128]),
+                                          (256, 64, 131, [128, 128, 256]), (4, 128, 259, [256, 512, 1024])])
+def test_fused_stack_forward_backward_matches_emulation(G, K, cin, mlp):
+    from maskplanner_b200.shared_mlp import pad64, shared_mlp_max
+    torch.manual_seed(G + K)
+    convs, bns, c = nn.ModuleList(), nn.ModuleList(), cin
+    for co in mlp:
+        convs.append(nn.Conv2d(c, co, 1))
+        bns.append(nn.BatchNorm2d(co))
+        c = co
+    convs.cuda(), bns.cuda()
+    for bn in bns:
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.uniform_(-0.3, 0.3)
+    M = G * K
+    a0 = F.pad(torch.randn(M, cin, device="cuda"), (0, pad64(cin) - cin)).bfloat16()
+    wout = torch.randn(G, mlp[-1], device="cuda")
+    params = list(convs.parameters()) + list(bns.parameters())
+    rm0 = [bn.running_mean.clone() for bn in bns]
+    a1 = a0.clone().requires_grad_(True)
+    out1 = shared_mlp_max(a1, K, convs, bns, True)
+    (out1 * wout).sum().backward()
+    g1 = [a1.grad.float()] + [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    a2 = a0.clone().float().requires_grad_(True)
+    out2 = _emulate(a2, K, convs, bns)
+    (out2 * wout).sum().backward()
+    g2 = [a2.grad] + [(p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for p in params]
+    assert tuple(out1.shape) == (G, mlp[-1])
+    assert _rel_l2(out1, out2) < 1e-3
+    names = ["a0"] + ["conv." + n for n, _ in convs.named_parameters()] + ["bn." + n for n, _ in bns.named_parameters()]
+    for n, x, y in zip(names, g1, g2):
+        if n.startswith("conv.") and n.endswith("bias"):
+            assert float(x.abs().max()) == 0.0, n          # exact zero: training-mode BN removes the conv bias
+            continue
+        assert _rel_l2(x, y) < 1e-2, (n, _rel_l2(x, y))
+    # running statistics: momentum update with the unbiased variance and the conv bias folded into the mean
+    for i, bn in enumerate(bns):
+        assert int(bn.num_batches_tracked) == 1
+        assert not torch.equal(bn.running_mean, rm0[i])
+
+
+def test_running_stats_update_matches_batchnorm2d():
+    from maskplanner_b200.shared_mlp import pad64, shared_mlp_max
+    torch.manual_seed(1)
+    conv, bn = nn.Conv2d(20, 40, 1).cuda(), nn.BatchNorm2d(40).cuda()
+    ref_bn = nn.BatchNorm2d(40).cuda()
+    M, K = 960, 8
+    a0 = F.pad(torch.randn(M, 20, device="cuda"), (0, 44)).bfloat16()
+    shared_mlp_max(a0, K, [conv], [bn], True)
+    z = (a0.float()[:, :20] @ conv.weight.view(40, 20).bfloat16().float().t()).bfloat16().float() + conv.bias
+    ref_bn.train()
+    ref_bn(z.t().reshape(1, 40, M, 1))
+    assert torch.allclose(bn.running_mean, ref_bn.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-4, atol=1e-5)
+
+
+def test_short_training_run_tracks_fp32_path():
+    """Functional check of the benchmarked configuration: 12 optimisation steps on one batch, bf16
+    tensor-core MLP vs strict-fp32 MLP from identical initial weights (dropout off).  Whole-network
+    gradients are ill-conditioned at random init (nine training-mode BatchNorms; even fp32 CPU vs fp64
+    differs by 5e-3), so the criterion is the optimisation trajectory, not element-wise gradients."""
+    from maskplanner_b200 import pointnet2_utils as P
+    from maskplanner_b200 import synthetic
+    from maskplanner_b200.train_step import Trainer
+    old = P.get_mlp_precision()
+    try:
+        curves = {}
+        batch = synthetic.make_batch(8, "windows_v2", seed0=5)
+        for prec in ("fp32", "bf16"):
+            P.set_mlp_precision(prec)
+            tr = Trainer("windows_v2", torch.device("cuda", 0), seed=11)
+            tr.model.dropout.p = 0.0
+            dev_batch = tr.to_device(batch)
+            gen = torch.Generator().manual_seed(3)
+            losses = []
+            for _ in range(12):
+                seeds = (torch.randint(0, 5120, (8,), generator=gen), torch.randint(0, 512, (8,), generator=gen))
+                losses.append(float(tr.step(dev_batch, seeds).item()))
+            curves[prec] = losses
+        f, b = curves["fp32"], curves["bf16"]
+        assert np.isclose(b[0], f[0], rtol=1e-2)                 # same starting loss
+        assert f[-1] < 0.5 * f[0] and b[-1] < 0.5 * b[0]          # both optimise
+        assert abs(b[-1] - f[-1]) < 0.25 * f[-1], (f, b)          # and end up in the same place
+    finally:
+        P.set_mlp_precision(old)
