@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU (weak scaling)")
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured step")
     return ap.parse_args()
 
 
@@ -141,6 +142,7 @@ def workload_config(args, n, cpu=False):
                         "+ asymm_v6 chamfer/stroke-mask loss + backward + Adam" % args.category,
             "per_gpu_batch": args.ref_batch if cpu else args.batch, "global_batch": (args.ref_batch if cpu else args.batch * n),
             "pc_points": 5120, "parallelism": "cpu" if cpu else "dp%d" % n,
+            "launch": "cpu threads" if cpu else ("eager (one launch per kernel)" if args.no_graph else "whole step captured once, one CUDA-graph replay per step"),
             "arithmetic": "fp32 (reference CPU path)" if cpu else
                           "shared-MLP GEMMs bf16 on tcgen05 with fp32 accumulation/statistics; FPS, ball query, grouping, chamfer, heads, Adam fp32",
             "l2": "no flush: per-step working set (activations + 0.42 GB of parameter/optimizer state) exceeds the 126 MB L2"}
@@ -220,7 +222,8 @@ def run_ours(args, ws, rank, local):
     _cabi.load()
     peak, peak_src = peaks()
     B = args.batch
-    trainer = Trainer(args.category, dev, world_size=ws)
+    trainer = Trainer(args.category, dev, world_size=ws, use_graph=not args.no_graph)
+    args.warmup = max(args.warmup, 3) if not args.no_graph else args.warmup   # 2 eager steps + the capture step
     # distinct synthetic batches per rank (weak scaling: every rank owns B whole samples)
     host = [pin_batch(synthetic.make_batch(B, args.category, seed0=10000 * rank + 100 * i)) for i in range(3)]
     resident = [trainer.to_device(h) for h in host]
@@ -245,7 +248,7 @@ def run_ours(args, ws, rank, local):
     b.record()
     barrier()
     ms = a.elapsed_time(b)
-    launches = (_cabi.KERNEL_LAUNCHES - l0) // max(args.steps, 1)
+    launches = getattr(trainer, "kernels_per_step", None) or (_cabi.KERNEL_LAUNCHES - l0) // max(args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if ws > 1:

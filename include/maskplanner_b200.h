@@ -193,6 +193,14 @@ MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32
 MPB_API int mpb_padded_lengths_f32(const float *y, int N, int P2, int D, float sentinel,
                                    int64_t *first, int32_t *any_flag, void *stream);
 
+/* ---- f1 (next row): the mask loss's per-sample Hungarian matching   loss_handler.py:860-877 ------
+ * One warp per sample solves min sum_t cost[b, row(t), t] over injective row(.) for the PRESENT
+ * targets t (present[b,t] != 0; the reference's per-sample torch.unique), fp64 like scipy's
+ * linear_sum_assignment.  cost [B,P,T] f32, present [B,T] u8, out_row [B,T] i64 (-1 for absent
+ * targets).  Needs #present <= P <= 32, T <= 32.  Replaces B device->host copies per step. */
+MPB_API int mpb_lap_f32(const float *cost, const uint8_t *present, int B, int P, int T,
+                        int64_t *out_row, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

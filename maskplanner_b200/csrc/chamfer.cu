@@ -310,7 +310,7 @@ static int launch_generic(const float *p1, const float *p2, int N, int P1, int P
     const size_t smem = ((size_t)kChThreads * (D + 1) + (size_t)tile_rows * D) * sizeof(float);
     dim3 grid((P1 + kChThreads - 1) / kChThreads, N);
     auto kern = knn_generic_kernel<8>;
-    if (smem > 48 * 1024) MPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) MPB_ENSURE_DYN_SMEM(kern, smem);
     kern<<<grid, kChThreads, smem, st>>>(p1, p2, P1, P2, D, l1, l2, K, dists, idx, tile_rows);
     return check_launch("knn_generic_kernel");
 }

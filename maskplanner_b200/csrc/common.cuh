@@ -39,6 +39,17 @@ inline int check_launch(const char *what)
 
 int sm_count();
 
+// Opt a kernel into `bytes` of dynamic shared memory once (cached per call site): after the first call
+// no cudaFuncSetAttribute is issued any more, which keeps later launches legal inside CUDA-graph capture.
+#define MPB_ENSURE_DYN_SMEM(kernel, bytes)                                                               \
+    do {                                                                                                 \
+        static int configured_ = 0;                                                                      \
+        if ((int)(bytes) > configured_) {                                                                \
+            MPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            configured_ = (int)(bytes);                                                                  \
+        }                                                                                                \
+    } while (0)
+
 // ---- warp-level integer reductions (REDUX.*; one instruction on sm_80+) ----------------------
 __device__ __forceinline__ int redux_max_s32(int v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ int redux_min_s32(int v) { return __reduce_min_sync(0xffffffffu, v); }

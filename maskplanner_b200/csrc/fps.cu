@@ -209,8 +209,12 @@ static int launch_resident(const FpsPlan &p, const float *xyz, int64_t sb, int64
 {
     auto kern = fps_resident_kernel<PPT>;
     const size_t smem = (size_t)3 * p.threads * PPT * sizeof(float);
-    MPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (p.cluster > 8) MPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    MPB_ENSURE_DYN_SMEM(kern, smem);
+    static bool nonportable_ok = false;
+    if (p.cluster > 8 && !nonportable_ok) {
+        MPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        nonportable_ok = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * p.cluster));
     cfg.blockDim = dim3((unsigned)p.threads);

@@ -331,11 +331,11 @@ extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, in
     cudaStream_t st = (cudaStream_t)stream;
     if (out_fp32) {
         auto kern = gemm_tn_kernel<true>;
-        MPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
         kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
     } else {
         auto kern = gemm_tn_kernel<false>;
-        MPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
         kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
     }
     return check_launch("gemm_tn_kernel");
@@ -363,7 +363,7 @@ extern "C" int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int
     const int stage_bytes = (2 + 4) * 64 * 128;  // worst case NU = 256
     const int stages = 4;
     const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmSmemTail) + 1024;
-    MPB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MPB_ENSURE_DYN_SMEM(wgrad_kernel, 227 * 1024);
     wgrad_kernel<<<n_tiles * k_tiles * m_splits, kGemmThreads, smem, (cudaStream_t)stream>>>(tmZ, tmA, dW, M, N, K, K, k_tiles, m_splits,
                                                                                             rows_per_split, stages);
     return check_launch("wgrad_kernel");

@@ -64,7 +64,8 @@ def chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=True):
 def mask_cost_matrices(pred_stroke_masks, target_ids, n_ids):
     """cost[b,p,t] = sum_i BCEWithLogits(pred[b,p,i], [target_ids[b,i] == t]) and present[b,t] (stroke t
     owns at least one predicted segment).  Equivalent to loss_handler.py:865-873 for every sample at once."""
-    onehot = F.one_hot(target_ids, n_ids).to(pred_stroke_masks.dtype)            # [B, S, T]
+    classes = torch.arange(n_ids, device=target_ids.device)
+    onehot = (target_ids[:, :, None] == classes[None, None, :]).to(pred_stroke_masks.dtype)   # [B, S, T] (no value check => no sync)
     sp = F.softplus(pred_stroke_masks).sum(-1, keepdim=True)                     # [B, P, 1]
     cost = sp - torch.bmm(pred_stroke_masks, onehot)                             # [B, P, T]
     present = onehot.sum(1) > 0                                                  # [B, T]
@@ -87,13 +88,43 @@ def hungarian_host(cost, present):
     return (torch.from_numpy(np.concatenate(bi)), torch.from_numpy(np.concatenate(pi)), torch.from_numpy(np.concatenate(ti)))
 
 
-def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, cfg):
-    """loss_handler.py:816-935 with smooth_targets=False (binary masks, BCE)."""
+def hungarian_device(cost, present):
+    """The same assignment on the device: one warp per sample (mpb_lap_f32), no host synchronisation.
+    Returns row [B, T] int64: predicted mask matched to target stroke t, -1 where the stroke is absent."""
+    from . import _cabi
+    B, P, T = cost.shape
+    cost = cost.detach().float().contiguous()
+    pres = present.to(torch.uint8).contiguous()
+    row = torch.empty(B, T, dtype=torch.int64, device=cost.device)
+    _cabi.check(_cabi.load().mpb_lap_f32(_cabi.ptr(cost), _cabi.ptr(pres), B, P, T, _cabi.ptr(row), _cabi.stream_ptr()), "mpb_lap_f32")
+    return row
+
+
+def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, cfg, matcher="device"):
+    """loss_handler.py:816-935 with smooth_targets=False (binary masks, BCE).
+
+    matcher="device" (default): batched on-device assignment and fixed-shape masked reductions -- no
+    host round trip, CUDA-graph capturable.  matcher="host": scipy on the host from one D2H copy (the
+    reference's own solver; used by the parity tests)."""
     dev = pred_stroke_masks.device
     B, n_pred_masks, out_segments = pred_stroke_masks.shape
     ids = stroke_ids.to(dev).gather(1, pred_to_gt_match)                         # :838  [B, out_segments], float
     ids = ids.long()                                                             # the -1 padding id is never matched (:852)
     n_ids = n_pred_masks                                                         # ids < max_n_strokes == n_pred_masks
+    if matcher == "device":
+        with torch.no_grad():
+            cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids.clamp_min(0), n_ids)
+            row = hungarian_device(cost, present)                                # [B, T]  (:860-877)
+            pres_f = present.to(pred_stroke_masks.dtype)
+            row_c = row.clamp_min(0)
+        # matched pairs as dense [B, T] slots, absent strokes masked out (the reference stacks them, :886-902)
+        sel = pred_stroke_masks.gather(1, row_c[:, :, None].expand(B, n_ids, out_segments))          # pred mask matched to stroke t
+        bce = F.binary_cross_entropy_with_logits(sel, onehot.transpose(1, 2), reduction="none").sum(-1)   # [B, T]
+        mask_loss = (bce * pres_f).sum() / pres_f.sum()                          # :906  mean over all matched pairs in the batch
+        target_scores = torch.zeros_like(scores).scatter_add_(1, row_c, pres_f)  # :920-921 (each mask matched at most once)
+        weights = cfg.explicit_no_stroke_weight + (1.0 - cfg.explicit_no_stroke_weight) * target_scores   # :924-925
+        conf_loss = F.binary_cross_entropy_with_logits(scores, target_scores, reduction="none", weight=weights).mean()   # :930
+        return cfg.explicit_weight_stroke_masks * mask_loss + cfg.explicit_weight_stroke_masks_confidence * conf_loss
     with torch.no_grad():
         cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids.clamp_min(0), n_ids)
         b_idx, p_idx, t_idx = hungarian_host(cost, present)                      # :860-877
@@ -110,11 +141,11 @@ def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, c
 
 
 def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores, stroke_ids, traj_as_pc, cfg=None,
-                                       fused=True, return_terms=False):
+                                       fused=True, return_terms=False, matcher="device"):
     """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config."""
     cfg = cfg or LossConfig()
     t1, t2, t3, _, match = chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=fused)
-    masks = stroke_masks_loss(match, pred_stroke_masks, mask_scores, stroke_ids, cfg)
+    masks = stroke_masks_loss(match, pred_stroke_masks, mask_scores, stroke_ids, cfg, matcher=matcher)
     loss = (cfg.weight_asymm_segment_chamfer * t1 + cfg.weight_reverse_asymm_point_chamfer * t2
             + cfg.weight_reverse_asymm_segment_chamfer * t3 + masks)
     if return_terms:

@@ -9,6 +9,11 @@ NVLink.  Parameter gradients are views into ONE flat buffer, so the all-reduce n
 copies, and the head gradients (>90 % of the parameters, produced first by backward) are reduced on a
 side stream while the encoder backward is still running.
 
+No step of the body synchronises with the host (the reference's padding scan, per-sample Hungarian
+and .cpu() calls are all on the device here), so with ``use_graph=True`` the whole step -- forward,
+loss, backward, all-reduce, Adam -- is captured once into a CUDA graph and replayed: one launch per
+step instead of ~600, which is what makes a ~5 ms step possible at all from Python.
+
 BatchNorm semantics: replica semantics (each rank normalises over its own samples), the standard DDP
 behaviour; single-process-equivalent statistics would need SyncBN and are out of scope for round 1.
 """
@@ -16,7 +21,8 @@ import torch
 import torch.distributed as dist
 
 from . import loss as L
-from . import regressor
+from . import regressor, synthetic
+from .pointnet2_utils import draw_fps_seed
 
 
 class FlatGradBuckets:
@@ -59,10 +65,31 @@ def all_reduce_mean_(flat, world_size, group=None):
     return flat
 
 
-class Trainer:
-    """model + Adam(lr=1e-3) (train_maskplanner.py:159) + loss, optionally data parallel."""
+def pad_batch(batch, max_segments, max_poses):
+    """Pad the GT tensors to fixed maxima with the loader's own sentinels (-100 rows, stroke id -1;
+    utils/dataset/paintnet_ODv1.py:738-747).  Extra sentinel rows change nothing: every consumer derives
+    the per-sample length from the first sentinel row.  Fixed shapes are what CUDA-graph replay needs."""
+    def pad(t, n, value):
+        if t.shape[1] == n:
+            return t
+        assert t.shape[1] < n, "batch exceeds the configured maximum (%d > %d)" % (t.shape[1], n)
+        out = t.new_full((t.shape[0], n) + tuple(t.shape[2:]), value)
+        out[:, :t.shape[1]] = t
+        return out
+    out = dict(batch)
+    out["traj"] = pad(batch["traj"], max_segments, synthetic.PAD)
+    out["stroke_ids"] = pad(batch["stroke_ids"], max_segments, -1.0)
+    out["traj_as_pc"] = pad(batch["traj_as_pc"], max_poses, synthetic.PAD)
+    return out
 
-    def __init__(self, category="windows_v2", device=None, lr=1e-3, seed=0, loss_cfg=None, world_size=1, fused_loss=True):
+
+class Trainer:
+    """model + Adam(lr=1e-3) (train_maskplanner.py:159) + loss, optionally data parallel / CUDA-graphed."""
+
+    KEYS = ("point_cloud", "traj", "traj_as_pc", "stroke_ids")
+
+    def __init__(self, category="windows_v2", device=None, lr=1e-3, seed=0, loss_cfg=None, world_size=1, fused_loss=True,
+                 use_graph=False, graph_warmup_steps=2):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         torch.manual_seed(seed)                       # identical initial weights on every rank
         self.model = regressor.maskplanner_model(category).to(self.device)
@@ -70,11 +97,20 @@ class Trainer:
         self.loss_cfg = loss_cfg or L.LossConfig()
         self.world_size = world_size
         self.fused_loss = fused_loss
+        cfg = synthetic.CATEGORIES[category]
+        self.max_segments = synthetic.out_vectors(cfg["n_pred_traj_points"])   # GT segments never exceed the prediction budget
+        self.max_poses = cfg["n_pred_traj_points"]
         self.buckets = FlatGradBuckets(self.model)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True, capturable=use_graph)
         self.comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         self._heads_ready = None
         self._heads_pending = 0
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+        self._static_loss = None
+        self._calls = 0
+        self._graph_warmup_steps = graph_warmup_steps
         if world_size > 1:
             # launch the head-bucket all-reduce on the side stream as soon as backward has produced the
             # LAST head gradient (counted, so no assumption about autograd's execution order)
@@ -95,13 +131,9 @@ class Trainer:
 
     def to_device(self, host_batch):
         """The step's H2D boundary (train_maskplanner.py:207-208, loss_handler.py:628-629): pinned -> device, async."""
-        out = {}
-        for k in ("point_cloud", "traj", "traj_as_pc", "stroke_ids"):
-            out[k] = host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True)
-        return out
+        return {k: host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True) for k in self.KEYS}
 
-    def step(self, batch, fps_seeds=None):
-        """One optimisation step on a device-resident batch.  Returns the loss as a 0-d device tensor."""
+    def _step_core(self, batch, fps_seeds):
         self.buckets.zero()                                                       # model.zero_grad()  (:184)
         cloud = batch["point_cloud"].permute(0, 2, 1)                             # :207
         pred, masks, scores, _ = self.model(cloud, fps_seeds)                     # :210
@@ -118,6 +150,39 @@ class Trainer:
                 all_reduce_mean_(self.buckets.heads, self.world_size)
         self.opt.step()                                                           # :221
         return loss.detach()
+
+    def step(self, batch, fps_seeds=None):
+        """One optimisation step on a device-resident batch.  Returns the loss as a 0-d device tensor.
+        `fps_seeds` = (seed indices for SA1 [B], for SA2 [B]); None draws them from the CPU generator exactly
+        like the reference does (models/pointnet2_utils.py:77, one randint per SA layer)."""
+        if not self.use_graph:
+            return self._step_core(batch, fps_seeds)
+        self._calls += 1
+        batch = pad_batch(batch, self.max_segments, self.max_poses)
+        B = batch["point_cloud"].shape[0]
+        if fps_seeds is None:
+            fps_seeds = (draw_fps_seed(B, batch["point_cloud"].shape[1], self.device), draw_fps_seed(B, 512, self.device))
+        else:
+            fps_seeds = tuple(s.to(self.device, dtype=torch.long) for s in fps_seeds)
+        if self._calls <= self._graph_warmup_steps:      # real eager steps: lazy initialisation + Adam state
+            return self._step_core(batch, fps_seeds)
+        if self._graph is None:
+            self._static = {k: batch[k].clone() for k in self.KEYS}
+            self._static["seeds"] = tuple(s.clone() for s in fps_seeds)
+            torch.cuda.synchronize()
+            from . import _cabi
+            n0 = _cabi.KERNEL_LAUNCHES
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self._step_core(self._static, self._static["seeds"])
+            self.kernels_per_step = _cabi.KERNEL_LAUNCHES - n0     # libmaskplanner_b200 kernels inside one replay
+        else:
+            for k in self.KEYS:
+                self._static[k].copy_(batch[k], non_blocking=True)
+            for dst, src in zip(self._static["seeds"], fps_seeds):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
 
     def step_from_host(self, host_batch, fps_seeds=None):
         """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223)."""
