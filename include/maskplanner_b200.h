@@ -141,7 +141,9 @@ MPB_API int mpb_knn_points_bwd_f32(const float *p1, const float *p2, int N, int 
  * row-wise GEMM Z[M,Cout] = A[M,Cin] * W[Cout,Cin]^T (M = B*S*K); activations travel as bf16 [M,C]
  * row-major with C a multiple of 64 (zero padded), accumulation / statistics in fp32.
  *
- * mpb_group_points_bf16 / _bwd_bf16: a5 with bf16 output (the GEMM's A operand, zero padded to ldo).
+ * mpb_group_points_bf16 / _bwd_bf16: a5 emitted as bf16 GEMM rows [B*S*K, ldo], columns in the order
+ *                      [feats (D), centred xyz (3), zero padding]; ldo % 8 == 0.  _bwd adds the feature
+ *                      columns of grad_out into grad_feats [B,N,D] (fp32, caller zero-fills).
  * mpb_gemm_bf16_tn:    C[M,N] = A[M,K] * B[N,K]^T   (tcgen05 + TMA; K % 64 == 0, N % 32 == 0;
  *                      C is bf16, or fp32 when out_fp32 != 0).  Forward (B = W) and dgrad (A = dZ, B = W^T).
  * mpb_gemm_bf16_wgrad: dW[N,K] (fp32, caller zero-fills) += dZ[M,N]^T * A[M,K]   (K % 64 == 0, N % 8 == 0).
@@ -155,8 +157,7 @@ MPB_API int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn, in
                                   const float *new_xyz, const int64_t *idx, int B, int N, int S,
                                   int K, int D, int ldo, void *out, void *stream);
 MPB_API int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const int64_t *idx, int B,
-                                      int N, int S, int K, int D, float *grad_feats,
-                                      float *grad_xyz, float *grad_new_xyz, void *stream);
+                                      int N, int S, int K, int D, float *grad_feats, void *stream);
 MPB_API int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, int N, int K,
                              int out_fp32, void *stream);
 MPB_API int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int M, int N, int K,

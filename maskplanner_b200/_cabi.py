@@ -38,7 +38,7 @@ SIGNATURES = {
     "mpb_knn_points_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     "mpb_padded_lengths_f32": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
     "mpb_group_points_bf16": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "mpb_group_points_bwd_bf16": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "mpb_group_points_bwd_bf16": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mpb_gemm_bf16_tn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mpb_gemm_bf16_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mpb_bn_stat_partials": (_I, [_L, _I]),

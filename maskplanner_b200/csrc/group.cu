@@ -150,34 +150,107 @@ extern "C" int mpb_group_points_bwd_f32(const float *grad_out, int ldo, const in
     return check_launch("group_points_bwd_kernel");
 }
 
-// bf16 variants feeding / fed by the tensor-core shared MLP (sa_gemm.cu): same gather + centre + concat,
-// rounded to bf16 on the way out, last dimension zero-padded to `ldo` (the GEMM's K padding).
+// bf16 rows for the tensor-core shared MLP (sa_gemm.cu): the GEMM's A operand, written directly.
+// Column order is FEATURES FIRST: [feats(0..D-1), centred xyz(D..D+2), zero padding up to ldo] so that the
+// D feature channels of a gathered point are 16-byte aligned vector copies (the host permutes the first
+// layer's weight columns to match).  One thread = one row x 8 columns: a single index computation and a
+// single 16-byte store per 8 outputs.
+namespace mpb {
+
+__global__ void __launch_bounds__(256)
+group_rows_bf16_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *__restrict__ feats,
+                       int64_t fsb, int64_t fsn, int64_t fsc, const float *__restrict__ new_xyz, const int64_t *__restrict__ idx,
+                       int N, int S, int K, int D, int ldo, int64_t total_vec, int vec_ok, __nv_bfloat16 *__restrict__ out)
+{
+    const int nv = ldo >> 3;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = v / nv;
+        const int c0 = (int)(v - row * nv) * 8;
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (c0 < D + 3) {
+            const int64_t i = idx[row];
+            if (i >= 0 && i < N) {
+                const int64_t bs = row / K, b = bs / S;
+                if (vec_ok && c0 + 8 <= D) {
+                    const float4 *src = reinterpret_cast<const float4 *>(feats + b * fsb + i * fsn + c0);
+                    const float4 lo = src[0], hi = src[1];
+                    f[0] = lo.x, f[1] = lo.y, f[2] = lo.z, f[3] = lo.w, f[4] = hi.x, f[5] = hi.y, f[6] = hi.z, f[7] = hi.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c0 + e;
+                        if (c < D)
+                            f[e] = feats[b * fsb + i * fsn + (int64_t)c * fsc];
+                        else if (c < D + 3)
+                            f[e] = __fsub_rn(xyz[b * xsb + i * xsn + (c - D) * xsc], new_xyz[bs * 3 + (c - D)]);
+                    }
+                }
+            }
+        }
+        uint4 pk;
+        __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        reinterpret_cast<uint4 *>(out)[v] = pk;
+    }
+}
+
+// grad_feats[b, idx[row], c] += grad_rows[row, c] for c < D: one thread = one row x 4 channels, one 16-byte
+// vector reduction (RED.128) per 4 channels when D % 4 == 0.
+__global__ void __launch_bounds__(256)
+group_rows_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ go, int ldo, const int64_t *__restrict__ idx, int N, int S, int K, int D,
+                           int64_t total_vec, float *__restrict__ gfeats)
+{
+    const int nv = (D + 3) >> 2;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = v / nv;
+        const int c0 = (int)(v - row * nv) * 4;
+        const int64_t i = idx[row];
+        if (i < 0 || i >= N) continue;
+        const int64_t b = row / ((int64_t)S * K);
+        const uint2 raw = *reinterpret_cast<const uint2 *>(go + row * ldo + c0);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.x));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.y));
+        float *dst = gfeats + (b * N + i) * D + c0;
+        if ((D & 3) == 0) {
+            atomicAdd(reinterpret_cast<float4 *>(dst), make_float4(a.x, a.y, c.x, c.y));
+        } else {
+            const float vals[4] = {a.x, a.y, c.x, c.y};
+            for (int e = 0; e < 4 && c0 + e < D; ++e) atomicAdd(dst + e, vals[e]);
+        }
+    }
+}
+
+}  // namespace mpb
+
 extern "C" int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats,
                                      int64_t fsb, int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx, int B,
                                      int N, int S, int K, int D, int ldo, void *out, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "negative size");
-    MPB_REQUIRE(ldo >= 3 + D, "ldo < 3 + D");
-    const int64_t total = (int64_t)B * S * K * ldo;
-    if (total == 0) return MPB_OK;
+    MPB_REQUIRE(ldo >= 3 + D && ldo % 8 == 0, "ldo must be a multiple of 8 and >= 3 + D");
+    const int64_t total_vec = (int64_t)B * S * K * (ldo / 8);
+    if (total_vec == 0) return MPB_OK;
     MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
     MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
-    group_points_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total, (__nv_bfloat16 *)out);
-    return check_launch("group_points_kernel<bf16>");
+    const int vec_ok = D >= 8 && fsc == 1 && (fsb % 4 == 0) && (fsn % 4 == 0) && (((uintptr_t)feats & 15) == 0);
+    group_rows_bf16_kernel<<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+        xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out);
+    return check_launch("group_rows_bf16_kernel");
 }
 
 extern "C" int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const int64_t *idx, int B, int N, int S, int K, int D,
-                                         float *grad_feats, float *grad_xyz, float *grad_new_xyz, void *stream)
+                                         float *grad_feats, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "negative size");
-    MPB_REQUIRE(ldo >= 3 + D, "ldo < 3 + D");
-    const int64_t total = (int64_t)B * S * K * (3 + D);
-    if (total == 0) return MPB_OK;
-    MPB_REQUIRE(grad_out && idx, "null pointer");
-    group_points_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total, grad_feats, grad_xyz, grad_new_xyz);
-    return check_launch("group_points_bwd_kernel<bf16>");
+    MPB_REQUIRE(ldo >= 3 + D && ldo % 8 == 0, "ldo must be a multiple of 8 and >= 3 + D");
+    const int64_t total_vec = (int64_t)B * S * K * ((D + 3) / 4);
+    if (total_vec == 0) return MPB_OK;
+    MPB_REQUIRE(grad_out && idx && grad_feats, "null pointer");
+    MPB_REQUIRE(((uintptr_t)grad_feats & 15) == 0, "grad_feats must be 16-byte aligned");
+    group_rows_bwd_bf16_kernel<<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)grad_out, ldo, idx, N, S,
+                                                                                          K, D, total_vec, grad_feats);
+    return check_launch("group_rows_bwd_bf16_kernel");
 }

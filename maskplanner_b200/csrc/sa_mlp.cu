@@ -80,23 +80,44 @@ colstats_kernel(const __nv_bfloat16 *__restrict__ Z, int64_t M, int C, float *__
     });
 }
 
-// One CTA.  Training: batch statistics -> scale/shift/mean/rstd, running stats updated in place.
+// Combine the per-CTA partial sums of 8 channels (one CTA = 8 channels x 32 partial lanes) in fp64, fixed order.
+// Returns true on the thread that holds the totals of channel `c`.
+constexpr int kFinThreads = 256;
+__device__ __forceinline__ bool reduce_partials(const float *__restrict__ partials, int nparts, int C, int &c, double &s, double &q)
+{
+    __shared__ double red[2][32][8];
+    const int pl = threadIdx.x >> 3, ci = threadIdx.x & 7;
+    c = blockIdx.x * 8 + ci;
+    s = 0.0, q = 0.0;
+    if (c < C)
+        for (int p = pl; p < nparts; p += 32) {
+            s += (double)partials[(size_t)p * 2 * C + c];
+            q += (double)partials[(size_t)p * 2 * C + C + c];
+        }
+    red[0][pl][ci] = s;
+    red[1][pl][ci] = q;
+    __syncthreads();
+    if (pl != 0 || c >= C) return false;
+    s = 0.0, q = 0.0;
+    for (int p = 0; p < 32; ++p) s += red[0][p][ci], q += red[1][p][ci];
+    return true;
+}
+
+// Training: batch statistics -> scale/shift/mean/rstd, running stats updated in place.
 // (conv bias only moves the mean: BN(z + b) == BN(z); it enters the running mean, reference :210-212.)
-__global__ void bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
+__global__ void __launch_bounds__(kFinThreads)
+bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
                                    const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta,
                                    float *__restrict__ running_mean, float *__restrict__ running_var, float momentum, float eps,
                                    float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
                                    float *__restrict__ rstd_out)
 {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int c;
+    double s, q;
+    if (reduce_partials(partials, nparts, C, c, s, q)) {
         if (c >= C_valid) {  // zero-padded channel (GEMM alignment): contributes exact zeros downstream
             scale[c] = shift[c] = mean_out[c] = rstd_out[c] = 0.f;
-            continue;
-        }
-        double s = 0.0, q = 0.0;
-        for (int p = 0; p < nparts; ++p) {
-            s += (double)partials[(size_t)p * 2 * C + c];
-            q += (double)partials[(size_t)p * 2 * C + C + c];
+            return;
         }
         const double mean = s / M;
         double var = q / M - mean * mean;
@@ -196,19 +217,17 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
 }
 
 // dgamma = sum dY*zhat, dbeta = sum dY; coef[0][c] = gamma*rstd, coef[1][c] = mean(dY), coef[2][c] = mean(dY*zhat)
-__global__ void bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
+__global__ void __launch_bounds__(kFinThreads)
+bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
                                     const float *__restrict__ gamma, const float *__restrict__ rstd, float *__restrict__ dgamma,
                                     float *__restrict__ dbeta, float *__restrict__ coef)
 {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int c;
+    double s, q;
+    if (reduce_partials(partials, nparts, C, c, s, q)) {
         if (c >= C_valid) {
             coef[c] = coef[C + c] = coef[2 * C + c] = 0.f;
-            continue;
-        }
-        double s = 0.0, q = 0.0;
-        for (int p = 0; p < nparts; ++p) {
-            s += (double)partials[(size_t)p * 2 * C + c];
-            q += (double)partials[(size_t)p * 2 * C + C + c];
+            return;
         }
         if (dbeta) dbeta[c] = (float)s;
         if (dgamma) dgamma[c] = (float)q;
@@ -247,6 +266,41 @@ bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, const float *__restrict__
             d[i] = coef[c] * (dy - coef[C + c] - zh * coef[2 * C + c]);
         }
         reinterpret_cast<uint4 *>(dZ)[v] = pack8(d);
+    }
+}
+
+// Pooled upstream gradient: one thread owns (group, 8 channels), loads arg-max / dOut once and walks the K rows.
+__global__ void __launch_bounds__(kEwThreads)
+bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, int K, const __nv_bfloat16 *__restrict__ Z,
+                        const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                        const float *__restrict__ rstd, const float *__restrict__ coef, int64_t G, int C,
+                        __nv_bfloat16 *__restrict__ dZ)
+{
+    const int cg = C >> 3;
+    for (int64_t v = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; v < G * cg; v += (int64_t)gridDim.x * kEwThreads) {
+        const int64_t g = v / cg;
+        const int c0 = (int)(v - g * cg) * 8;
+        float sc[8], sh[8], mu[8], rs[8], k0[8], k1[8], k2[8], go[8];
+        int am[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            sc[i] = scale[c], sh[i] = shift[c], mu[i] = mean[c], rs[i] = rstd[c];
+            k0[i] = coef[c], k1[i] = coef[C + c], k2[i] = coef[2 * C + c];
+            go[i] = dOut[g * C + c], am[i] = arg[g * C + c];
+        }
+        const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
+        __nv_bfloat16 *dp = dZ + (g * K) * C + c0;
+        for (int k = 0; k < K; ++k) {
+            float z[8], d[8];
+            unpack8(*reinterpret_cast<const uint4 *>(zp + (int64_t)k * C), z);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dy = (am[i] == k && fmaf(z[i], sc[i], sh[i]) > 0.f) ? go[i] : 0.f;
+                d[i] = k0[i] * (dy - k1[i] - (z[i] - mu[i]) * rs[i] * k2[i]);
+            }
+            *reinterpret_cast<uint4 *>(dp + (int64_t)k * C) = pack8(d);
+        }
     }
 }
 
@@ -290,7 +344,7 @@ extern "C" int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int
     using namespace mpb;
     MPB_REQUIRE(partials && scale && shift && mean && rstd && C > 0 && nparts > 0 && M > 0, "bad argument");
     MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
-    bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, bias, gamma, beta, running_mean,
+    bn_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, bias, gamma, beta, running_mean,
                                                             running_var, momentum, eps, scale, shift, mean, rstd);
     return check_launch("bn_finalize_kernel");
 }
@@ -346,7 +400,7 @@ extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C,
     using namespace mpb;
     MPB_REQUIRE(partials && rstd && coef && C > 0 && nparts > 0 && M > 0, "bad argument");
     MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
-    bwd_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, rstd, dgamma, dbeta, coef);
+    bwd_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, rstd, dgamma, dbeta, coef);
     return check_launch("bwd_finalize_kernel");
 }
 
@@ -365,8 +419,8 @@ extern "C" int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const in
                                                               shift, mean, rstd, coef, M, C, (__nv_bfloat16 *)dZ);
     else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0, "pooled: bad argmax/K");
-        bwd_apply_kernel<true><<<blocks, kEwThreads, 0, st>>>(nullptr, dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift, mean, rstd,
-                                                             coef, M, C, (__nv_bfloat16 *)dZ);
+        bwd_apply_pooled_kernel<<<ew_blocks((M / K) * (C >> 3)), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift,
+                                                                                     mean, rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
     }
     return check_launch("bwd_apply_kernel");
 }

@@ -218,7 +218,7 @@ class _GroupPointsBF16(torch.autograd.Function):
             return None, None, None, None, None
         go = go.contiguous()
         gf = torch.zeros(B, N, D, dtype=torch.float32, device=go.device)
-        check(_cabi.load().mpb_group_points_bwd_bf16(ptr(go), ldo, ptr(idx_c), B, N, S, K, D, ptr(gf), None, None, stream_ptr()),
+        check(_cabi.load().mpb_group_points_bwd_bf16(ptr(go), ldo, ptr(idx_c), B, N, S, K, D, ptr(gf), stream_ptr()),
               "mpb_group_points_bwd_bf16")
         return None, gf, None, None, None
 
@@ -351,6 +351,6 @@ class PointNetSetAbstraction(nn.Module):
         else:
             D = 0 if points is None else points.shape[2]
             a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))        # :133-138
-        pooled = shared_mlp_max(a0, K, self.mlp_convs, self.mlp_bns, self.training)     # :208-214
+        pooled = shared_mlp_max(a0, K, self.mlp_convs, self.mlp_bns, self.training, xyz_last=rows is None)   # :208-214
         out = pooled.view(B, S, -1).permute(0, 2, 1)
         return new_xyz.permute(0, 2, 1), (out.contiguous() if self.contiguous_output else out)

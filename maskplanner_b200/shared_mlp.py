@@ -26,25 +26,39 @@ def pad64(c):
     return (c + 63) // 64 * 64
 
 
-def _padded_weight(conv_weight, cout_p, cin_p):
-    """[Cout,Cin,1,1] fp32 -> bf16 [cout_p, cin_p] (zero padded) and its transpose [cin_p, cout_p]."""
+def _padded_weight(conv_weight, cout_p, cin_p, xyz_last):
+    """[Cout,Cin,1,1] fp32 -> bf16 [cout_p, cin_p] (zero padded) and its transpose [cin_p, cout_p].
+    xyz_last: the rows come from mpb_group_points_bf16 (features first, the 3 centred coordinates last),
+    so the reference's xyz-first input channels (:137) move to the end."""
     cout, cin = conv_weight.shape[0], conv_weight.shape[1]
     w = torch.zeros(cout_p, cin_p, dtype=torch.bfloat16, device=conv_weight.device)
-    w[:cout, :cin] = conv_weight.detach().reshape(cout, cin)
+    src = conv_weight.detach().reshape(cout, cin)
+    if xyz_last and cin > 3:
+        w[:cout, :cin - 3] = src[:, 3:]
+        w[:cout, cin - 3:cin] = src[:, :3]
+    else:
+        w[:cout, :cin] = src
     return w, w.t().contiguous()
+
+
+def _unpermute_wgrad(dw, cout, cin, xyz_last):
+    """Inverse of the column order used by _padded_weight, cropped to the real [Cout, Cin]."""
+    if xyz_last and cin > 3:
+        return torch.cat([dw[:cout, cin - 3:cin], dw[:cout, :cin - 3]], dim=1).reshape(cout, cin, 1, 1)
+    return dw[:cout, :cin].reshape(cout, cin, 1, 1)
 
 
 class SharedMLPMax(torch.autograd.Function):
     """pooled[G, C_L] = max_k relu(bn_L(... relu(bn_1(a0 @ W_1^T)) ...)) over the K rows of each group.
 
-    apply(a0, K, training, momentum_eps, *flat) with
+    apply(a0, K, training, momentum_eps, xyz_last, *flat) with
       a0    bf16 [M, pad64(Cin)], M = G*K
       flat  per layer: conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var
       momentum_eps  tuple of (momentum, eps) per layer
     """
 
     @staticmethod
-    def forward(ctx, a0, K, training, momentum_eps, *flat):
+    def forward(ctx, a0, K, training, momentum_eps, xyz_last, *flat):
         lib = _cabi.load()
         L = len(flat) // 6
         M = a0.shape[0]
@@ -58,7 +72,7 @@ class SharedMLPMax(torch.autograd.Function):
             W, bias, gamma, beta, rmean, rvar = flat[6 * l:6 * l + 6]
             cout, cin = W.shape[0], W.shape[1]
             cout_p, cin_p = pad64(cout), a.shape[1]
-            w, wt = _padded_weight(W, cout_p, cin_p)
+            w, wt = _padded_weight(W, cout_p, cin_p, xyz_last and l == 0)
             z = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
             check(lib.mpb_gemm_bf16_tn(ptr(a), ptr(w), ptr(z), M, cout_p, cin_p, 0, st), "mpb_gemm_bf16_tn")
             sc = torch.empty(4, cout_p, dtype=torch.float32, device=dev)      # rows: scale, shift, mean, rstd
@@ -93,7 +107,7 @@ class SharedMLPMax(torch.autograd.Function):
             stats.append(sc)
             wts.append(wt)
             dims.append((cout, cin, cout_p, cin_p))
-        ctx.K, ctx.L, ctx.dims, ctx.training = K, L, dims, training
+        ctx.K, ctx.L, ctx.dims, ctx.training, ctx.xyz_last = K, L, dims, training, xyz_last
         ctx.save_for_backward(argmax, *acts, *zs, *stats, *wts, *[flat[6 * l + 2] for l in range(L)])
         c_last = dims[-1][0]
         return out[:, :c_last] if c_last != out.shape[1] else out
@@ -143,7 +157,7 @@ class SharedMLPMax(torch.autograd.Function):
                                             M, cout_p, ptr(dz), st), "mpb_bn_bwd_apply_bf16")
             dw = torch.zeros(cout_p, cin_p, dtype=torch.float32, device=dev)
             check(lib.mpb_gemm_bf16_wgrad(ptr(dz), ptr(acts[l]), ptr(dw), M, cout_p, cin_p, st), "mpb_gemm_bf16_wgrad")
-            grads[6 * l] = dw[:cout, :cin].reshape(cout, cin, 1, 1)
+            grads[6 * l] = _unpermute_wgrad(dw, cout, cin, ctx.xyz_last and l == 0)
             grads[6 * l + 1] = torch.zeros(cout, dtype=torch.float32, device=dev)      # exact: BN removes the conv bias
             grads[6 * l + 2] = dgamma
             grads[6 * l + 3] = dbeta
@@ -152,16 +166,17 @@ class SharedMLPMax(torch.autograd.Function):
                 check(lib.mpb_gemm_bf16_tn(ptr(dz), ptr(wts[l]), ptr(d_a), M, cin_p, cout_p, 0, st), "mpb_gemm_bf16_tn")
             else:
                 d_a = None
-        return (d_a, None, None, None, *grads)
+        return (d_a, None, None, None, None, *grads)
 
 
-def shared_mlp_max(a0, K, convs, bns, training):
-    """Run the stack on bf16 rows `a0` [G*K, pad64(Cin)]; returns pooled fp32 [G, C_last]."""
+def shared_mlp_max(a0, K, convs, bns, training, xyz_last=False):
+    """Run the stack on bf16 rows `a0` [G*K, pad64(Cin)]; returns pooled fp32 [G, C_last].
+    xyz_last=True when `a0` comes from mpb_group_points_bf16 (features first, centred xyz last)."""
     flat, me = [], []
     for conv, bn in zip(convs, bns):
         flat += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
         me.append((bn.momentum if bn.momentum is not None else 0.1, bn.eps))
-    out = SharedMLPMax.apply(a0, K, training, tuple(me), *flat)
+    out = SharedMLPMax.apply(a0, K, training, tuple(me), bool(xyz_last), *flat)
     if training:
         for bn in bns:
             if bn.num_batches_tracked is not None:

@@ -154,3 +154,35 @@ def test_short_training_run_tracks_fp32_path():
         assert abs(b[-1] - f[-1]) < 0.25 * f[-1], (f, b)          # and end up in the same place
     finally:
         P.set_mlp_precision(old)
+
+
+@pytest.mark.parametrize("D,layout", [(0, "pm"), (6, "cm"), (128, "pm"), (128, "cm"), (10, "pm")])
+def test_bf16_group_rows_features_first(D, layout):
+    """mpb_group_points_bf16: rows [feats | centred xyz | 0-pad] rounded to bf16, and its scatter-add backward."""
+    from maskplanner_b200 import pointnet2_utils as P
+    from maskplanner_b200.shared_mlp import pad64
+    from oracle import torch_oracle as T
+    g = torch.Generator().manual_seed(D)
+    B, N, S, K = 2, 200, 16, 8
+    xyz = torch.rand(B, N, 3, generator=g)
+    idx = torch.randint(0, N, (B, S, K), generator=g)
+    new_xyz = T.index_points(xyz, torch.randint(0, N, (B, S), generator=g))
+    feats = torch.rand(B, N, D, generator=g) if D else None
+    fd = None
+    if D:
+        fd = feats.cuda() if layout == "pm" else feats.permute(0, 2, 1).contiguous().cuda().permute(0, 2, 1)   # channel-major storage
+        fd.requires_grad_(True)
+    ldo = pad64(3 + D)
+    rows = P._GroupPointsBF16.apply(xyz.cuda(), fd, new_xyz.cuda(), idx.cuda(), ldo)
+    assert rows.dtype == torch.bfloat16 and tuple(rows.shape) == (B * S * K, ldo)
+    want = torch.zeros(B, S, K, ldo)
+    if D:
+        want[..., :D] = T.index_points(feats, idx)
+    want[..., D:D + 3] = T.index_points(xyz, idx) - new_xyz[:, :, None]
+    assert torch.equal(rows.float().cpu(), want.reshape(-1, ldo).bfloat16().float())
+    if D:
+        w = torch.randn(B * S * K, ldo, generator=g).bfloat16()
+        (rows.float() * w.cuda().float()).sum().backward()
+        fo = feats.clone().requires_grad_(True)
+        (T.index_points(fo, idx).reshape(-1, D) * w[:, :D].float()).sum().backward()
+        assert torch.allclose(fd.grad.cpu(), fo.grad, rtol=1e-5, atol=1e-5)

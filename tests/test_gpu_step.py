@@ -250,7 +250,7 @@ def test_cuda_graph_step_matches_eager_step():
     from maskplanner_b200 import synthetic
     from maskplanner_b200.train_step import Trainer
     B = 4
-    batches = [synthetic.make_batch(B, "windows_v2", seed0=50 + i) for i in range(3)]
+    batches = [synthetic.make_batch(B, "windows_v2", seed0=50 + 10 * i) for i in range(3)]
     assert len({b["traj"].shape[1] for b in batches}) > 1          # different padded lengths
     curves = []
     for use_graph in (False, True):
