@@ -144,7 +144,8 @@ def workload_config(args, n, cpu=False):
             "pc_points": 5120, "parallelism": "cpu" if cpu else "dp%d" % n,
             "launch": "cpu threads" if cpu else ("eager (one launch per kernel)" if args.no_graph else "whole step captured once, one CUDA-graph replay per step"),
             "arithmetic": "fp32 (reference CPU path)" if cpu else
-                          "shared-MLP GEMMs bf16 on tcgen05 with fp32 accumulation/statistics; FPS, ball query, grouping, chamfer, heads, Adam fp32",
+                          "shared-MLP GEMMs bf16 on tcgen05 with fp32 accumulation/statistics; head GEMMs TF32 (cuBLAS); "
+                          "FPS, ball query, grouping, chamfer, mask loss, Adam fp32",
             "l2": "no flush: per-step working set (activations + 0.42 GB of parameter/optimizer state) exceeds the 126 MB L2"}
 
 

@@ -1,16 +1,20 @@
 // BatchNorm / ReLU / max-pool stages of PointNetSetAbstraction's shared MLP on bf16 activations (sm_100a).
 // Reference: models/pointnet2_utils.py:210-214 -- per layer `relu(bn(conv(x)))`, then `max` over the K
 // neighbours of each group.  The 1x1 conv runs in sa_gemm.cu and leaves Z[M,C] (bf16) in HBM; everything
-// here is HBM-bound streaming over [M,C] with 16-byte vector accesses (8 bf16 per thread per row):
+// here is HBM-bound streaming over [M,C] with 16-byte vector accesses:
 //
 //   colstats      : per-channel sum / sum of squares of Z (training-mode batch statistics)
 //   bn_finalize   : -> scale = gamma*rstd, shift = beta - mean*scale; running-stat update (momentum, unbiased var)
 //   bn_relu       : A = relu(scale*Z + shift)                                   (bf16 -> bf16)
 //   bn_relu_max   : out[g,c] = max_k relu(scale*Z[g,k,c] + shift) + arg-max     (last layer, fused max-pool)
 //   bwd_stats     : sum dY, sum dY*zhat with dY = dA * [scale*Z+shift > 0]      (dense or pooled upstream)
-//   bwd_finalize  : dgamma, dbeta and the two per-channel means BN backward needs
+//   bwd_finalize  : dgamma, dbeta and the three per-channel coefficients BN backward needs
 //   bwd_apply     : dZ = gamma*rstd*(dY - mean(dY) - zhat*mean(dY*zhat))        (bf16 out)
 //
+// Thread mapping of the streaming kernels: a thread owns ONE 8-channel group (16 bytes of a row) for its
+// whole life and walks rows with a grid stride, so all per-channel constants live in registers and the only
+// per-row work is two or three 16-byte loads, a handful of FMAs and one 16-byte store; rows are processed
+// four at a time to keep four independent loads in flight per thread.
 // Batch statistics are accumulated in fp32 per CTA and combined in fp64 by the finalize kernels
 // (deterministic: fixed partial order, no atomics across CTAs).
 #include <cuda_bf16.h>
@@ -37,29 +41,51 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
     for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return v;
 }
+__device__ __forceinline__ uint4 ld16(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void load8(const float *__restrict__ p, float (&f)[8])
+{
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+}
 
 constexpr int kEwThreads = 256;
+constexpr int kRowUnroll = 4;
 
-// Generic "two per-channel sums over all rows" skeleton: each thread owns one 8-channel group and walks
-// rows with stride; CTA-level combine through shared-memory atomics; one partial row per CTA.
+// Row walker: thread (tr, tc) of a CTA handles channel group tc (channels 8*tc .. 8*tc+7) of rows
+// blockIdx.x*rpp + tr, + gridDim.x*rpp, ...; `body(r0, nr, stride)` is called with up to kRowUnroll rows.
+struct RowWalk {
+    int cg, rpp, tr, tc;
+    bool active;
+    __device__ __forceinline__ RowWalk(int C)
+    {
+        cg = C >> 3;
+        rpp = kEwThreads / cg;
+        tr = threadIdx.x / cg;
+        tc = threadIdx.x - tr * cg;
+        active = tr < rpp;
+    }
+};
+
+// ---- training statistics ---------------------------------------------------------------------------
 template <class RowFn>
 __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict__ partials, RowFn fn)
 {
     extern __shared__ float sm_acc[];  // [2][C]
-    const int cg = C >> 3;
-    const int rows_per_pass = kEwThreads / cg;
-    const int tr = threadIdx.x / cg, tc = threadIdx.x - tr * cg;
+    const RowWalk w(C);
     for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) sm_acc[i] = 0.f;
     __syncthreads();
-    if (tr < rows_per_pass) {
+    if (w.active) {
         float s0[8], s1[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
-        for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + tr; r < M; r += (int64_t)gridDim.x * rows_per_pass) fn(r, tc * 8, s0, s1);
+        const int64_t stride = (int64_t)gridDim.x * w.rpp;
+        int64_t r = (int64_t)blockIdx.x * w.rpp + w.tr;
+        for (; r + (kRowUnroll - 1) * stride < M; r += kRowUnroll * stride) fn(r, stride, kRowUnroll, w.tc * 8, s0, s1);
+        for (; r < M; r += stride) fn(r, stride, 1, w.tc * 8, s0, s1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            atomicAdd(&sm_acc[tc * 8 + i], s0[i]);
-            atomicAdd(&sm_acc[C + tc * 8 + i], s1[i]);
+            atomicAdd(&sm_acc[w.tc * 8 + i], s0[i]);
+            atomicAdd(&sm_acc[C + w.tc * 8 + i], s1[i]);
         }
     }
     __syncthreads();
@@ -69,14 +95,22 @@ __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict_
 __global__ void __launch_bounds__(kEwThreads)
 colstats_kernel(const __nv_bfloat16 *__restrict__ Z, int64_t M, int C, float *__restrict__ partials)
 {
-    column_sums(M, C, partials, [&](int64_t r, int c0, float(&s0)[8], float(&s1)[8]) {
-        float z[8];
-        unpack8(*reinterpret_cast<const uint4 *>(Z + r * C + c0), z);
+    column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
+        uint4 raw[kRowUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s0[i] += z[i];
-            s1[i] = fmaf(z[i], z[i], s1[i]);
-        }
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (u < nr) raw[u] = ld16(Z + (r + u * stride) * C + c0);
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (u < nr) {
+                float z[8];
+                unpack8(raw[u], z);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s0[i] += z[i];
+                    s1[i] = fmaf(z[i], z[i], s1[i]);
+                }
+            }
     });
 }
 
@@ -106,11 +140,10 @@ __device__ __forceinline__ bool reduce_partials(const float *__restrict__ partia
 // Training: batch statistics -> scale/shift/mean/rstd, running stats updated in place.
 // (conv bias only moves the mean: BN(z + b) == BN(z); it enters the running mean, reference :210-212.)
 __global__ void __launch_bounds__(kFinThreads)
-bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
-                                   const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta,
-                                   float *__restrict__ running_mean, float *__restrict__ running_var, float momentum, float eps,
-                                   float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
-                                   float *__restrict__ rstd_out)
+bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M, const float *__restrict__ bias,
+                   const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean,
+                   float *__restrict__ running_var, float momentum, float eps, float *__restrict__ scale, float *__restrict__ shift,
+                   float *__restrict__ mean_out, float *__restrict__ rstd_out)
 {
     int c;
     double s, q;
@@ -134,21 +167,32 @@ bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_
     }
 }
 
+// ---- forward elementwise ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
-bn_relu_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t total_vec,
-               int cg, __nv_bfloat16 *__restrict__ A)
+bn_relu_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t M, int C,
+               __nv_bfloat16 *__restrict__ A)
 {
-    for (int64_t v = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * kEwThreads) {
-        const int c0 = (int)(v % cg) * 8;
-        float z[8];
-        unpack8(reinterpret_cast<const uint4 *>(Z)[v], z);
-        const float4 s0 = *reinterpret_cast<const float4 *>(scale + c0), s1 = *reinterpret_cast<const float4 *>(scale + c0 + 4);
-        const float4 t0 = *reinterpret_cast<const float4 *>(shift + c0), t1 = *reinterpret_cast<const float4 *>(shift + c0 + 4);
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    const RowWalk w(C);
+    if (!w.active) return;
+    const int c0 = w.tc * 8;
+    float sc[8], sh[8];
+    load8(scale + c0, sc);
+    load8(shift + c0, sh);
+    const int64_t stride = (int64_t)gridDim.x * w.rpp;
+    for (int64_t r = (int64_t)blockIdx.x * w.rpp + w.tr; r < M; r += kRowUnroll * stride) {
+        uint4 raw[kRowUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
-        reinterpret_cast<uint4 *>(A)[v] = pack8(z);
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (r + u * stride < M) raw[u] = ld16(Z + (r + u * stride) * C + c0);
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (r + u * stride < M) {
+                float z[8];
+                unpack8(raw[u], z);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
+                *reinterpret_cast<uint4 *>(A + (r + u * stride) * C + c0) = pack8(z);
+            }
     }
 }
 
@@ -157,44 +201,77 @@ __global__ void __launch_bounds__(kEwThreads)
 bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
                    int K, int C, float *__restrict__ out, int *__restrict__ arg)
 {
-    const int cg = C >> 3;
-    for (int64_t v = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; v < G * cg; v += (int64_t)gridDim.x * kEwThreads) {
-        const int64_t g = v / cg;
-        const int c0 = (int)(v - g * cg) * 8;
-        float sc[8], sh[8], best[8];
+    const RowWalk w(C);
+    if (!w.active) return;
+    const int c0 = w.tc * 8;
+    float sc[8], sh[8];
+    load8(scale + c0, sc);
+    load8(shift + c0, sh);
+    for (int64_t g = (int64_t)blockIdx.x * w.rpp + w.tr; g < G; g += (int64_t)gridDim.x * w.rpp) {
+        float best[8];
         int bi[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sc[i] = scale[c0 + i], sh[i] = shift[c0 + i], best[i] = -INFINITY, bi[i] = 0;
+        for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0;
         const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
-        for (int k = 0; k < K; ++k) {
-            float z[8];
-            unpack8(*reinterpret_cast<const uint4 *>(zp + (int64_t)k * C), z);
+        for (int k = 0; k < K; k += kRowUnroll) {
+            uint4 raw[kRowUnroll];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
-                if (a > best[i]) best[i] = a, bi[i] = k;
-            }
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (k + u < K) raw[u] = ld16(zp + (int64_t)(k + u) * C);
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (k + u < K) {
+                    float z[8];
+                    unpack8(raw[u], z);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
+                        if (a > best[i]) best[i] = a, bi[i] = k + u;
+                    }
+                }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) out[g * C + c0 + i] = best[i], arg[g * C + c0 + i] = bi[i];
+        float4 *op = reinterpret_cast<float4 *>(out + g * C + c0);
+        op[0] = make_float4(best[0], best[1], best[2], best[3]);
+        op[1] = make_float4(best[4], best[5], best[6], best[7]);
+        int4 *ap = reinterpret_cast<int4 *>(arg + g * C + c0);
+        ap[0] = make_int4(bi[0], bi[1], bi[2], bi[3]);
+        ap[1] = make_int4(bi[4], bi[5], bi[6], bi[7]);
     }
 }
 
+// ---- backward --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
 bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale,
                        const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd, int64_t M,
                        int C, float *__restrict__ partials)
 {
-    column_sums(M, C, partials, [&](int64_t r, int c0, float(&s0)[8], float(&s1)[8]) {
-        float z[8], d[8];
-        unpack8(*reinterpret_cast<const uint4 *>(Z + r * C + c0), z);
-        unpack8(*reinterpret_cast<const uint4 *>(dA + r * C + c0), d);
+    const int c00 = (threadIdx.x % (C >> 3)) * 8;
+    float sc[8], sh[8], mu[8], rs[8];
+    load8(scale + c00, sc);
+    load8(shift + c00, sh);
+    load8(mean + c00, mu);
+    load8(rstd + c00, rs);
+    column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
+        uint4 rz[kRowUnroll], rd[kRowUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float dy = fmaf(z[i], scale[c0 + i], shift[c0 + i]) > 0.f ? d[i] : 0.f;
-            s0[i] += dy;
-            s1[i] = fmaf(dy, (z[i] - mean[c0 + i]) * rstd[c0 + i], s1[i]);
-        }
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (u < nr) {
+                rz[u] = ld16(Z + (r + u * stride) * C + c0);
+                rd[u] = ld16(dA + (r + u * stride) * C + c0);
+            }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (u < nr) {
+                float z[8], d[8];
+                unpack8(rz[u], z);
+                unpack8(rd[u], d);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float dy = fmaf(z[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
+                    s0[i] += dy;
+                    s1[i] = fmaf(dy, (z[i] - mu[i]) * rs[i], s1[i]);
+                }
+            }
     });
 }
 
@@ -204,23 +281,25 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                         const float *__restrict__ rstd, int64_t G, int K, int C, float *__restrict__ partials)
 {
-    column_sums(G, C, partials, [&](int64_t g, int c0, float(&s0)[8], float(&s1)[8]) {
+    column_sums(G, C, partials, [&](int64_t g0, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
+        for (int u = 0; u < nr; ++u) {
+            const int64_t g = g0 + u * stride;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            const float z = __bfloat162float(Z[(g * K + arg[g * C + c]) * C + c]);
-            const float dy = fmaf(z, scale[c], shift[c]) > 0.f ? dOut[g * C + c] : 0.f;
-            s0[i] += dy;
-            s1[i] = fmaf(dy, (z - mean[c]) * rstd[c], s1[i]);
+            for (int i = 0; i < 8; ++i) {
+                const int c = c0 + i;
+                const float z = __bfloat162float(Z[(g * K + arg[g * C + c]) * C + c]);
+                const float dy = fmaf(z, scale[c], shift[c]) > 0.f ? dOut[g * C + c] : 0.f;
+                s0[i] += dy;
+                s1[i] = fmaf(dy, (z - mean[c]) * rstd[c], s1[i]);
+            }
         }
     });
 }
 
 // dgamma = sum dY*zhat, dbeta = sum dY; coef[0][c] = gamma*rstd, coef[1][c] = mean(dY), coef[2][c] = mean(dY*zhat)
 __global__ void __launch_bounds__(kFinThreads)
-bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M,
-                                    const float *__restrict__ gamma, const float *__restrict__ rstd, float *__restrict__ dgamma,
-                                    float *__restrict__ dbeta, float *__restrict__ coef)
+bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M, const float *__restrict__ gamma,
+                    const float *__restrict__ rstd, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef)
 {
     int c;
     double s, q;
@@ -237,86 +316,115 @@ bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C
     }
 }
 
-template <bool POOLED>
-__global__ void __launch_bounds__(kEwThreads)
-bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, const float *__restrict__ dOut, const int *__restrict__ arg, int K,
-                 const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift,
-                 const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ coef, int64_t M, int C,
-                 __nv_bfloat16 *__restrict__ dZ)
-{
-    const int cg = C >> 3;
-    for (int64_t v = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; v < M * cg; v += (int64_t)gridDim.x * kEwThreads) {
-        const int64_t r = v / cg;
-        const int c0 = (int)(v - r * cg) * 8;
-        float z[8], d[8];
-        unpack8(reinterpret_cast<const uint4 *>(Z)[v], z);
-        if (POOLED) {
-            const int64_t g = r / K;
-            const int k = (int)(r - g * K);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] = arg[g * C + c0 + i] == k ? dOut[g * C + c0 + i] : 0.f;
-        } else {
-            unpack8(reinterpret_cast<const uint4 *>(dA)[v], d);
-        }
+// Per-thread constants of dZ = k0*(dY - k1 - zhat*k2) rewritten as dZ = p*dY - w*z + e:
+//   p = k0, w = k0*k2*rstd, e = mean*w - k0*k1
+struct ApplyConst {
+    float sc[8], sh[8], p[8], w[8], e[8];
+    __device__ __forceinline__ void load(const float *scale, const float *shift, const float *mean, const float *rstd, const float *coef,
+                                         int C, int c0)
+    {
+        float mu[8], rs[8], k1[8], k2[8];
+        load8(scale + c0, sc);
+        load8(shift + c0, sh);
+        load8(mean + c0, mu);
+        load8(rstd + c0, rs);
+        load8(coef + c0, p);
+        load8(coef + C + c0, k1);
+        load8(coef + 2 * C + c0, k2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            const float dy = fmaf(z[i], scale[c], shift[c]) > 0.f ? d[i] : 0.f;
-            const float zh = (z[i] - mean[c]) * rstd[c];
-            d[i] = coef[c] * (dy - coef[C + c] - zh * coef[2 * C + c]);
+            w[i] = p[i] * k2[i] * rs[i];
+            e[i] = fmaf(mu[i], w[i], -p[i] * k1[i]);
         }
-        reinterpret_cast<uint4 *>(dZ)[v] = pack8(d);
+    }
+};
+
+__global__ void __launch_bounds__(kEwThreads)
+bwd_apply_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale,
+                       const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
+                       const float *__restrict__ coef, int64_t M, int C, __nv_bfloat16 *__restrict__ dZ)
+{
+    const RowWalk w(C);
+    if (!w.active) return;
+    const int c0 = w.tc * 8;
+    ApplyConst k;
+    k.load(scale, shift, mean, rstd, coef, C, c0);
+    const int64_t stride = (int64_t)gridDim.x * w.rpp;
+    for (int64_t r = (int64_t)blockIdx.x * w.rpp + w.tr; r < M; r += kRowUnroll * stride) {
+        uint4 rz[kRowUnroll], rd[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (r + u * stride < M) {
+                rz[u] = ld16(Z + (r + u * stride) * C + c0);
+                rd[u] = ld16(dA + (r + u * stride) * C + c0);
+            }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (r + u * stride < M) {
+                float z[8], d[8];
+                unpack8(rz[u], z);
+                unpack8(rd[u], d);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float dy = fmaf(z[i], k.sc[i], k.sh[i]) > 0.f ? d[i] : 0.f;
+                    d[i] = fmaf(k.p[i], dy, fmaf(-k.w[i], z[i], k.e[i]));
+                }
+                *reinterpret_cast<uint4 *>(dZ + (r + u * stride) * C + c0) = pack8(d);
+            }
     }
 }
 
-// Pooled upstream gradient: one thread owns (group, 8 channels), loads arg-max / dOut once and walks the K rows.
+// Pooled upstream gradient: a thread owns (group, 8 channels), loads arg-max / dOut once and walks the K rows.
 __global__ void __launch_bounds__(kEwThreads)
 bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, int K, const __nv_bfloat16 *__restrict__ Z,
                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                         const float *__restrict__ rstd, const float *__restrict__ coef, int64_t G, int C,
                         __nv_bfloat16 *__restrict__ dZ)
 {
-    const int cg = C >> 3;
-    for (int64_t v = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; v < G * cg; v += (int64_t)gridDim.x * kEwThreads) {
-        const int64_t g = v / cg;
-        const int c0 = (int)(v - g * cg) * 8;
-        float sc[8], sh[8], mu[8], rs[8], k0[8], k1[8], k2[8], go[8];
+    const RowWalk w(C);
+    if (!w.active) return;
+    const int c0 = w.tc * 8;
+    ApplyConst k;
+    k.load(scale, shift, mean, rstd, coef, C, c0);
+    for (int64_t g = (int64_t)blockIdx.x * w.rpp + w.tr; g < G; g += (int64_t)gridDim.x * w.rpp) {
+        float go[8];
         int am[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            sc[i] = scale[c], sh[i] = shift[c], mu[i] = mean[c], rs[i] = rstd[c];
-            k0[i] = coef[c], k1[i] = coef[C + c], k2[i] = coef[2 * C + c];
-            go[i] = dOut[g * C + c], am[i] = arg[g * C + c];
+        load8(dOut + g * C + c0, go);
+        {
+            const int4 a = *reinterpret_cast<const int4 *>(arg + g * C + c0), b = *reinterpret_cast<const int4 *>(arg + g * C + c0 + 4);
+            am[0] = a.x, am[1] = a.y, am[2] = a.z, am[3] = a.w, am[4] = b.x, am[5] = b.y, am[6] = b.z, am[7] = b.w;
         }
         const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
         __nv_bfloat16 *dp = dZ + (g * K) * C + c0;
-        for (int k = 0; k < K; ++k) {
-            float z[8], d[8];
-            unpack8(*reinterpret_cast<const uint4 *>(zp + (int64_t)k * C), z);
+        for (int kk = 0; kk < K; kk += kRowUnroll) {
+            uint4 raw[kRowUnroll];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float dy = (am[i] == k && fmaf(z[i], sc[i], sh[i]) > 0.f) ? go[i] : 0.f;
-                d[i] = k0[i] * (dy - k1[i] - (z[i] - mu[i]) * rs[i] * k2[i]);
-            }
-            *reinterpret_cast<uint4 *>(dp + (int64_t)k * C) = pack8(d);
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (kk + u < K) raw[u] = ld16(zp + (int64_t)(kk + u) * C);
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (kk + u < K) {
+                    float z[8], d[8];
+                    unpack8(raw[u], z);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float dy = (am[i] == kk + u && fmaf(z[i], k.sc[i], k.sh[i]) > 0.f) ? go[i] : 0.f;
+                        d[i] = fmaf(k.p[i], dy, fmaf(-k.w[i], z[i], k.e[i]));
+                    }
+                    *reinterpret_cast<uint4 *>(dp + (int64_t)(kk + u) * C) = pack8(d);
+                }
         }
     }
 }
 
-static inline int stat_parts(int64_t rows, int C)
+static inline int row_blocks(int64_t rows, int C, int per_sm)
 {
-    const int rows_per_pass = kEwThreads / (C >> 3);
-    int64_t want = (rows + rows_per_pass - 1) / rows_per_pass;
-    const int cap = 2 * sm_count();
+    const int rpp = kEwThreads / (C >> 3);
+    int64_t want = (rows + rpp - 1) / rpp;
+    const int cap = per_sm * sm_count();
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
-static inline unsigned ew_blocks(int64_t total)
-{
-    int64_t b = (total + kEwThreads - 1) / kEwThreads;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
-}
+static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, 4); }
 
 }  // namespace mpb
 
@@ -344,8 +452,9 @@ extern "C" int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int
     using namespace mpb;
     MPB_REQUIRE(partials && scale && shift && mean && rstd && C > 0 && nparts > 0 && M > 0, "bad argument");
     MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
-    bn_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, bias, gamma, beta, running_mean,
-                                                            running_var, momentum, eps, scale, shift, mean, rstd);
+    bn_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, bias, gamma, beta,
+                                                                              running_mean, running_var, momentum, eps, scale, shift, mean,
+                                                                              rstd);
     return check_launch("bn_finalize_kernel");
 }
 
@@ -355,9 +464,8 @@ extern "C" int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *
     MPB_CHECK_C(C);
     MPB_REQUIRE(M >= 0 && Z && scale && shift && A, "bad argument");
     if (M == 0) return MPB_OK;
-    const int64_t total = M * (C >> 3);
-    bn_relu_kernel<<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, total, C >> 3,
-                                                                              (__nv_bfloat16 *)A);
+    bn_relu_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, 8), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)Z, scale, shift, M, C, (__nv_bfloat16 *)A);
     return check_launch("bn_relu_kernel");
 }
 
@@ -368,8 +476,8 @@ extern "C" int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const flo
     MPB_CHECK_C(C);
     MPB_REQUIRE(G >= 0 && K > 0 && Z && scale && shift && out && argmax, "bad argument");
     if (G == 0) return MPB_OK;
-    bn_relu_max_kernel<<<ew_blocks(G * (C >> 3)), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C,
-                                                                                        out, argmax);
+    bn_relu_max_kernel<<<row_blocks(G, C, 8), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
+                                                                                    argmax);
     return check_launch("bn_relu_max_kernel");
 }
 
@@ -400,7 +508,8 @@ extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C,
     using namespace mpb;
     MPB_REQUIRE(partials && rstd && coef && C > 0 && nparts > 0 && M > 0, "bad argument");
     MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
-    bwd_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, rstd, dgamma, dbeta, coef);
+    bwd_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, rstd, dgamma,
+                                                                               dbeta, coef);
     return check_launch("bwd_finalize_kernel");
 }
 
@@ -413,14 +522,13 @@ extern "C" int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const in
     MPB_REQUIRE(M > 0 && Z && scale && shift && mean && rstd && coef && dZ, "bad argument");
     MPB_REQUIRE((dA != nullptr) != (dOut != nullptr), "exactly one of dA (dense) / dOut (pooled) must be given");
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned blocks = ew_blocks(M * (C >> 3));
-    if (dA)
-        bwd_apply_kernel<false><<<blocks, kEwThreads, 0, st>>>((const __nv_bfloat16 *)dA, nullptr, nullptr, 1, (const __nv_bfloat16 *)Z, scale,
-                                                              shift, mean, rstd, coef, M, C, (__nv_bfloat16 *)dZ);
-    else {
+    if (dA) {
+        bwd_apply_dense_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, 8), kEwThreads, 0, st>>>(
+            (const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale, shift, mean, rstd, coef, M, C, (__nv_bfloat16 *)dZ);
+    } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0, "pooled: bad argmax/K");
-        bwd_apply_pooled_kernel<<<ew_blocks((M / K) * (C >> 3)), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift,
-                                                                                     mean, rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
+        bwd_apply_pooled_kernel<<<row_blocks(M / K, C, 8), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift, mean,
+                                                                               rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
     }
-    return check_launch("bwd_apply_kernel");
+    return check_launch("bwd_apply kernel");
 }

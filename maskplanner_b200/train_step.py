@@ -89,7 +89,7 @@ class Trainer:
     KEYS = ("point_cloud", "traj", "traj_as_pc", "stroke_ids")
 
     def __init__(self, category="windows_v2", device=None, lr=1e-3, seed=0, loss_cfg=None, world_size=1, fused_loss=True,
-                 use_graph=False, graph_warmup_steps=2):
+                 use_graph=False, graph_warmup_steps=2, heads_tf32=None):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         torch.manual_seed(seed)                       # identical initial weights on every rank
         self.model = regressor.maskplanner_model(category).to(self.device)
@@ -97,6 +97,11 @@ class Trainer:
         self.loss_cfg = loss_cfg or L.LossConfig()
         self.world_size = world_size
         self.fused_loss = fused_loss
+        # Heads (nn.Linear with M = batch size) stay library GEMMs.  With the bf16 tensor-core
+        # encoder they run on TF32 tensor cores (10-bit mantissa, finer than the encoder's bf16 activations);
+        # with the strict-fp32 encoder they stay strict fp32 so that mode keeps the reference's arithmetic.
+        from .pointnet2_utils import get_mlp_precision
+        self.heads_tf32 = get_mlp_precision() == "bf16" if heads_tf32 is None else bool(heads_tf32)
         cfg = synthetic.CATEGORIES[category]
         self.max_segments = synthetic.out_vectors(cfg["n_pred_traj_points"])   # GT segments never exceed the prediction budget
         self.max_poses = cfg["n_pred_traj_points"]
@@ -134,6 +139,16 @@ class Trainer:
         return {k: host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True) for k in self.KEYS}
 
     def _step_core(self, batch, fps_seeds):
+        if not self.heads_tf32:
+            return self._step_body(batch, fps_seeds)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True      # head GEMMs (M = batch, library cuBLAS) on TF32 tensor cores
+        try:
+            return self._step_body(batch, fps_seeds)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    def _step_body(self, batch, fps_seeds):
         self.buckets.zero()                                                       # model.zero_grad()  (:184)
         cloud = batch["point_cloud"].permute(0, 2, 1)                             # :207
         pred, masks, scores, _ = self.model(cloud, fps_seeds)                     # :210

