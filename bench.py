@@ -271,14 +271,44 @@ def run_ours(args, ws, rank, local):
     h2d = sum(v.numel() * 4 for k, v in host[0].items() if torch.is_tensor(v) and k in ("point_cloud", "traj", "traj_as_pc", "stroke_ids"))
     h2d += 2 * B * 8  # the two FPS seed vectors (int64), drawn on the host like the reference (:77)
 
+    # roofline leg: the same step, eager, with CUDA events around every launch of the two GEMM kernels
+    # (they are the largest share of the step, profiles/); events are recorded on the launching stream
+    from maskplanner_b200 import shared_mlp
+    shared_mlp.GEMM_TIMELINE = []
+    gen = torch.Generator().manual_seed(1)
+    for i in range(3):
+        seeds = (torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen))
+        trainer._step_core(resident[i % 3], tuple(s.to(dev) for s in seeds))
+    torch.cuda.synchronize()
+    timeline, shared_mlp.GEMM_TIMELINE = shared_mlp.GEMM_TIMELINE, None
+    per_kernel = {}
+    for name, nbytes, flops, e0, e1 in timeline:
+        d = per_kernel.setdefault(name, {"launches": 0, "bytes": 0, "flops": 0, "ms": 0.0})
+        d["launches"] += 1
+        d["bytes"] += nbytes
+        d["flops"] += flops
+        d["ms"] += e0.elapsed_time(e1)
+
     if rank == 0:
         ktab, fps_bytes = kernel_table(args, dev, peak)
-        fps_ms = ktab["fps_sa1"]["ms"]
-        roof = {"bound": "hbm", "kernel": "fps_resident_kernel (SA1: 5120 -> 512, B=%d)" % B, "achieved": fps_bytes / fps_ms / 1e6,
-                "peak": peak, "unit": "GB/s", "frac": fps_bytes / fps_ms / 1e6 / peak, "traffic": None,
-                "note": "achieved = algorithmic stream bytes npoint*N*20 B per cloud (SURVEY.md 8d) / CUDA-event duration; "
-                        "the kernel keeps the cloud in registers, so DRAM traffic is only the compulsory 12N+8*npoint B per cloud; "
-                        "peak = " + peak_src}
+        for name, d in per_kernel.items():
+            ktab[name] = {"launches_per_step": d["launches"] // 3, "ms_per_step": d["ms"] / 3, "avg_launch_us": d["ms"] / d["launches"] * 1e3,
+                          "algorithmic_GBps": d["bytes"] / d["ms"] / 1e6, "frac_of_hbm_peak": d["bytes"] / d["ms"] / 1e6 / peak,
+                          "tflops": d["flops"] / d["ms"] / 1e9}
+        top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+        d = per_kernel[top]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": "%s (tcgen05/TMA shared-MLP GEMM, %d launches per step)" % (top, d["launches"] // 3),
+                "achieved": d["bytes"] / d["ms"] / 1e6, "peak": peak, "unit": "GB/s", "frac": d["bytes"] / d["ms"] / 1e6 / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+                "avg_launch_us": d["ms"] / d["launches"] * 1e3,
+                "note": "achieved = algorithmic bytes (bf16 operands read once + output written once, DESIGN.md) summed over the "
+                        "kernel's launches of one step / summed CUDA-event durations of those launches, eager replay of the timed step; "
+                        "arithmetic intensity 21-85 flop/B < machine balance 258 flop/B, so HBM is the binding roof; "
+                        "traffic = ncu dram bytes per launch (profiles/traffic.json); peak = " + peak_src}
         line = {"metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, ws), "clocks": clocks,

@@ -62,7 +62,8 @@ static int make_map_bf16(CUtensorMap *map, const void *ptr, int64_t rows, int64_
     return MPB_OK;
 }
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 256;     // wgrad: producer, MMA, allocator, spare + one epilogue warpgroup
+constexpr int kGemmTnThreads = 384;   // gemm_tn: the same + a second epilogue warpgroup
 constexpr int kTileM = 128;
 constexpr int kTileK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int kABytes = kTileM * 128; // 16 KB per A stage
@@ -83,7 +84,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 }
 
 template <bool OUT_F32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void *__restrict__ Cout,
                int M, int N, int K, int BN, int ldc, int stages)
 {
@@ -159,10 +160,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
-        int acc = 0;
+        // Two epilogue warpgroups: warps 4-7 drain accumulator 0 (even tiles of this CTA), warps 8-11 accumulator 1
+        // (odd tiles), so TMEM->register->global of one tile overlaps the next tile's drain as well as its MMAs.
+        const int ew = warp & 3;           // the TMEM lane quarter this warp may read (warp % 4)
+        const int acc = (warp - 4) >> 2;   // accumulator buffer owned by this warpgroup
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int t = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+            if ((t & 1) != acc) continue;
             const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tail->tfull[acc], acc_phase);
             tc_fence_after();
@@ -192,7 +197,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tail->tempty[acc]);
-            if ((acc ^= 1) == 0) acc_phase ^= 1;
+            acc_phase ^= 1;
         }
     }
     tc_fence_before();
@@ -202,7 +207,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // dW[n0 + i, k0 + j] += sum_{m in this CTA's row range} dZ[m, n0 + i] * A[m, k0 + j]
 // blockIdx.x = ((n_tile * k_tiles) + k_tile) * m_splits + m_split
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmA, float *__restrict__ dW, int M,
              int N, int K, int ldw, int k_tiles, int m_splits, int rows_per_split, int stages)
 {
@@ -288,7 +293,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
                 if (row < N) {
                     float *dst = dW + (size_t)row * ldw + k0 + c0;
 #pragma unroll
-                    for (int v = 0; v < 32; ++v) atomicAdd(dst + v, __uint_as_float(r[v]));
+                    for (int v = 0; v < 32; v += 4)   // 16-byte vector reductions (RED.E.ADD.F32x4)
+                        atomicAdd(reinterpret_cast<float4 *>(dst + v),
+                                  make_float4(__uint_as_float(r[v]), __uint_as_float(r[v + 1]), __uint_as_float(r[v + 2]),
+                                              __uint_as_float(r[v + 3])));
                 }
             }
         }
@@ -332,11 +340,11 @@ extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, in
     if (out_fp32) {
         auto kern = gemm_tn_kernel<true>;
         MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
+        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
     } else {
         auto kern = gemm_tn_kernel<false>;
         MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
+        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
     }
     return check_launch("gemm_tn_kernel");
 }
@@ -360,8 +368,11 @@ extern "C" int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int
     m_splits = m_splits < 1 ? 1 : (m_splits > row_blocks ? row_blocks : m_splits);
     const int rows_per_split = ((row_blocks + m_splits - 1) / m_splits) * 64;
     m_splits = (M + rows_per_split - 1) / rows_per_split;
-    const int stage_bytes = (2 + 4) * 64 * 128;  // worst case NU = 256
-    const int stages = 4;
+    // stage = 64 contraction rows x (128 dZ channels + up to 256 A channels); sized so that two CTAs share an SM
+    // (one CTA's TMEM drain + reductions overlap the other's loads)
+    const int stage_bytes = (2 + (K < 256 ? K : 256) / 64) * 64 * 128;
+    int stages = (100 * 1024) / stage_bytes;
+    stages = stages < 2 ? 2 : (stages > 4 ? 4 : stages);
     const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmSmemTail) + 1024;
     MPB_ENSURE_DYN_SMEM(wgrad_kernel, 227 * 1024);
     wgrad_kernel<<<n_tiles * k_tiles * m_splits, kGemmThreads, smem, (cudaStream_t)stream>>>(tmZ, tmA, dW, M, N, K, K, k_tiles, m_splits,

@@ -15,15 +15,58 @@ Activations are bf16 [M, C] row-major (M = B*S*K neighbourhood rows), channel co
 multiples of 64; statistics, pooled outputs and all parameter gradients are fp32.  In training mode the
 conv bias cannot influence the output (BatchNorm removes it); it only enters the running mean, and its
 gradient is exactly zero (the reference's value there is rounding noise).
+
+L2-resident chunking.  Every [M, C] tensor of SA1/SA2 (134-268 MB at B = 64) is larger than the 126 MB
+L2, and training-mode BatchNorm puts a full-batch barrier between layers, so producer and consumer
+kernels of one tensor cannot be fused across the whole batch.  They CAN be run back to back on a row
+chunk small enough to stay in L2: forward, per chunk `bn_relu(l-1) -> GEMM(l) -> colstats(l)`; backward,
+per chunk `apply(l) -> wgrad(l) -> dgrad(l) -> bwd_stats(l-1)`.  The consumer of each intermediate then
+hits L2 instead of HBM (two of five forward passes and three of nine backward passes per layer), with the
+kernels unchanged -- only launch order and pointer offsets differ.
 """
+import ctypes
+
 import torch
 
 from . import _cabi
 from ._cabi import check, ptr, stream_ptr
 
+# Rows per L2-resident chunk are chosen so that the widest producer/consumer pair of the stack
+# (A chunk + Z chunk, bf16) stays below this many bytes.
+L2_CHUNK_BYTES = 48 << 20
+
 
 def pad64(c):
     return (c + 63) // 64 * 64
+
+
+# Optional per-launch timing of the two GEMM kernels (bench.py's roofline leg): set to a list and every GEMM
+# launch appends (kernel name, algorithmic bytes, flops, start event, end event), recorded on the launching stream.
+GEMM_TIMELINE = None
+
+
+def _gemm_tn(lib, a_ptr, b_ptr, c_ptr, M, N, K, st):
+    """C[M,N] (bf16) = A[M,K] @ B[N,K]^T.  Algorithmic bytes: A and B read once, C written once, all bf16."""
+    ev = None
+    if GEMM_TIMELINE is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(lib.mpb_gemm_bf16_tn(a_ptr, b_ptr, c_ptr, M, N, K, 0, st), "mpb_gemm_bf16_tn")
+    if ev is not None:
+        ev[1].record()
+        GEMM_TIMELINE.append(("gemm_tn_kernel", 2 * (M * K + N * K + M * N), 2 * M * N * K, ev[0], ev[1]))
+
+
+def _gemm_wgrad(lib, dz_ptr, a_ptr, dw_ptr, M, N, K, st):
+    """dW[N,K] (fp32) += dZ[M,N]^T @ A[M,K].  Algorithmic bytes: dZ and A read once (bf16), dW written once (fp32)."""
+    ev = None
+    if GEMM_TIMELINE is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(lib.mpb_gemm_bf16_wgrad(dz_ptr, a_ptr, dw_ptr, M, N, K, st), "mpb_gemm_bf16_wgrad")
+    if ev is not None:
+        ev[1].record()
+        GEMM_TIMELINE.append(("wgrad_kernel", 2 * M * (N + K) + 4 * N * K, 2 * M * N * K, ev[0], ev[1]))
 
 
 def _padded_weight(conv_weight, cout_p, cin_p, xyz_last):
@@ -48,6 +91,25 @@ def _unpermute_wgrad(dw, cout, cin, xyz_last):
     return dw[:cout, :cin].reshape(cout, cin, 1, 1)
 
 
+def _row_chunks(M, K, widest_pair_bytes_per_row):
+    """Row ranges [(r0, r1), ...]: whole groups of K rows, a multiple of 128 rows (GEMM tile) where possible."""
+    rows = max(K, L2_CHUNK_BYTES // max(widest_pair_bytes_per_row, 1))
+    unit = K * 128 // _gcd(K, 128)               # lcm(K, 128)
+    rows = max(unit, rows // unit * unit) if rows >= unit else max(K, rows // K * K)
+    return [(r0, min(M, r0 + rows)) for r0 in range(0, M, rows)]
+
+
+def _gcd(a, b):
+    while b:
+        a, b = b, a % b
+    return a
+
+
+def _off(t, row):
+    """Device pointer of row `row` of a contiguous 2-D tensor."""
+    return ctypes.c_void_p(t.data_ptr() + row * t.shape[1] * t.element_size())
+
+
 class SharedMLPMax(torch.autograd.Function):
     """pooled[G, C_L] = max_k relu(bn_L(... relu(bn_1(a0 @ W_1^T)) ...)) over the K rows of each group.
 
@@ -65,23 +127,41 @@ class SharedMLPMax(torch.autograd.Function):
         G = M // K
         dev = a0.device
         st = stream_ptr()
-        acts, zs, stats, wts, dims = [a0], [], [], [], []
+        dims = []
+        c_in_p = a0.shape[1]
+        for l in range(L):
+            cout, cin = flat[6 * l].shape[0], flat[6 * l].shape[1]
+            dims.append((cout, cin, pad64(cout), c_in_p))
+            c_in_p = pad64(cout)
+        chunks = _row_chunks(M, K, max(2 * (d[2] + d[3]) for d in dims))
+        acts, zs, stats, wts = [a0], [], [], []
         a = a0
         out = argmax = None
         for l in range(L):
             W, bias, gamma, beta, rmean, rvar = flat[6 * l:6 * l + 6]
-            cout, cin = W.shape[0], W.shape[1]
-            cout_p, cin_p = pad64(cout), a.shape[1]
+            cout, cin, cout_p, cin_p = dims[l]
             w, wt = _padded_weight(W, cout_p, cin_p, xyz_last and l == 0)
             z = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
-            check(lib.mpb_gemm_bf16_tn(ptr(a), ptr(w), ptr(z), M, cout_p, cin_p, 0, st), "mpb_gemm_bf16_tn")
             sc = torch.empty(4, cout_p, dtype=torch.float32, device=dev)      # rows: scale, shift, mean, rstd
             mom, eps = momentum_eps[l]
+            np_c = [lib.mpb_bn_stat_partials(r1 - r0, cout_p) for r0, r1 in chunks]
+            part = torch.empty(sum(np_c), 2, cout_p, dtype=torch.float32, device=dev) if training else None
+            if l > 0:
+                a = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev)
+                acts.append(a)
+            p0 = 0
+            for ci, (r0, r1) in enumerate(chunks):
+                if l > 0:   # previous layer's normalise + ReLU for this chunk, consumed from L2 by the GEMM below
+                    ps = stats[l - 1]
+                    check(lib.mpb_bn_relu_bf16(_off(zs[l - 1], r0), ptr(ps[0]), ptr(ps[1]), r1 - r0, cin_p, _off(a, r0), st),
+                          "mpb_bn_relu_bf16")
+                _gemm_tn(lib, _off(a, r0), ptr(w), _off(z, r0), r1 - r0, cout_p, cin_p, st)
+                if training:
+                    check(lib.mpb_bn_colstats_bf16(_off(z, r0), r1 - r0, cout_p, _off(part.view(-1, 2 * cout_p), p0), np_c[ci], st),
+                          "mpb_bn_colstats_bf16")
+                    p0 += np_c[ci]
             if training:
-                nparts = lib.mpb_bn_stat_partials(M, cout_p)
-                part = torch.empty(nparts, 2, cout_p, dtype=torch.float32, device=dev)
-                check(lib.mpb_bn_colstats_bf16(ptr(z), M, cout_p, ptr(part), nparts, st), "mpb_bn_colstats_bf16")
-                check(lib.mpb_bn_finalize_f32(ptr(part), nparts, cout_p, cout, M, ptr(bias), ptr(gamma), ptr(beta), ptr(rmean),
+                check(lib.mpb_bn_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(bias), ptr(gamma), ptr(beta), ptr(rmean),
                                               ptr(rvar), mom, eps, ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), st),
                       "mpb_bn_finalize_f32")
             else:
@@ -94,20 +174,16 @@ class SharedMLPMax(torch.autograd.Function):
                 sc[1, :cout] = (beta if beta is not None else 0.0) + (b0 - rmean) * s
                 sc[2, :cout] = rmean - b0
                 sc[3, :cout] = rstd
-            if l < L - 1:
-                a = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
-                check(lib.mpb_bn_relu_bf16(ptr(z), ptr(sc[0]), ptr(sc[1]), M, cout_p, ptr(a), st), "mpb_bn_relu_bf16")
-                acts.append(a)
-            else:
-                out = torch.empty(G, cout_p, dtype=torch.float32, device=dev)
-                argmax = torch.empty(G, cout_p, dtype=torch.int32, device=dev)
-                check(lib.mpb_bn_relu_max_bf16(ptr(z), ptr(sc[0]), ptr(sc[1]), G, K, cout_p, ptr(out), ptr(argmax), st),
-                      "mpb_bn_relu_max_bf16")
             zs.append(z)
             stats.append(sc)
             wts.append(wt)
-            dims.append((cout, cin, cout_p, cin_p))
-        ctx.K, ctx.L, ctx.dims, ctx.training, ctx.xyz_last = K, L, dims, training, xyz_last
+        cl_p = dims[-1][2]
+        out = torch.empty(G, cl_p, dtype=torch.float32, device=dev)
+        argmax = torch.empty(G, cl_p, dtype=torch.int32, device=dev)
+        sc = stats[-1]
+        check(lib.mpb_bn_relu_max_bf16(ptr(zs[-1]), ptr(sc[0]), ptr(sc[1]), G, K, cl_p, ptr(out), ptr(argmax), st),
+              "mpb_bn_relu_max_bf16")
+        ctx.K, ctx.L, ctx.dims, ctx.training, ctx.xyz_last, ctx.chunks = K, L, dims, training, xyz_last, chunks
         ctx.save_for_backward(argmax, *acts, *zs, *stats, *wts, *[flat[6 * l + 2] for l in range(L)])
         c_last = dims[-1][0]
         return out[:, :c_last] if c_last != out.shape[1] else out
@@ -118,7 +194,7 @@ class SharedMLPMax(torch.autograd.Function):
             raise RuntimeError("SharedMLPMax: backward through eval-mode BatchNorm is not implemented on the tensor-core path; "
                                "use precision='fp32' for that")
         lib = _cabi.load()
-        K, L, dims = ctx.K, ctx.L, ctx.dims
+        K, L, dims, chunks = ctx.K, ctx.L, ctx.dims, ctx.chunks
         saved = ctx.saved_tensors
         argmax = saved[0]
         acts, zs = saved[1:1 + L], saved[1 + L:1 + 2 * L]
@@ -134,38 +210,63 @@ class SharedMLPMax(torch.autograd.Function):
         else:
             d_pool = d_out.contiguous().float()
         grads = [None] * (6 * L)
+
+        def alloc_partials(l, pooled):
+            cp = dims[l][2]
+            np_c = [lib.mpb_bn_stat_partials((r1 - r0) // K if pooled else r1 - r0, cp) for r0, r1 in chunks]
+            return np_c, torch.empty(sum(np_c), 2 * cp, dtype=torch.float32, device=dev)
+
+        # statistics of the last layer: the pooled upstream gradient touches one row per (group, channel)
+        np_c, part = alloc_partials(L - 1, True)
+        sc = stats[L - 1]
+        p0 = 0
+        for ci, (r0, r1) in enumerate(chunks):
+            check(lib.mpb_bn_bwd_stats_bf16(None, _off(d_pool, r0 // K), _off(argmax, r0 // K), K, _off(zs[L - 1], r0), ptr(sc[0]),
+                                            ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), r1 - r0, cl_p, _off(part, p0), np_c[ci], st),
+                  "mpb_bn_bwd_stats_bf16")
+            p0 += np_c[ci]
         d_a = None
         for l in range(L - 1, -1, -1):
             cout, cin, cout_p, cin_p = dims[l]
             z, sc, gamma = zs[l], stats[l], gammas[l]
             pooled = l == L - 1
-            rows = G if pooled else M
-            nparts = lib.mpb_bn_stat_partials(rows, cout_p)
-            part = torch.empty(nparts, 2, cout_p, dtype=torch.float32, device=dev)
             coef = torch.empty(3, cout_p, dtype=torch.float32, device=dev)
             dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
             dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
-            up_dense = None if pooled else ptr(d_a)
-            up_pool = ptr(d_pool) if pooled else None
-            am = ptr(argmax) if pooled else None
-            check(lib.mpb_bn_bwd_stats_bf16(up_dense, up_pool, am, K, ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), M, cout_p,
-                                            ptr(part), nparts, st), "mpb_bn_bwd_stats_bf16")
-            check(lib.mpb_bn_bwd_finalize_f32(ptr(part), nparts, cout_p, cout, M, ptr(gamma), ptr(sc[3]), ptr(dgamma), ptr(dbeta),
+            check(lib.mpb_bn_bwd_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(gamma), ptr(sc[3]), ptr(dgamma), ptr(dbeta),
                                               ptr(coef), st), "mpb_bn_bwd_finalize_f32")
             dz = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
-            check(lib.mpb_bn_bwd_apply_bf16(up_dense, up_pool, am, K, ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), ptr(coef),
-                                            M, cout_p, ptr(dz), st), "mpb_bn_bwd_apply_bf16")
             dw = torch.zeros(cout_p, cin_p, dtype=torch.float32, device=dev)
-            check(lib.mpb_gemm_bf16_wgrad(ptr(dz), ptr(acts[l]), ptr(dw), M, cout_p, cin_p, st), "mpb_gemm_bf16_wgrad")
+            need_da = l > 0 or ctx.needs_input_grad[0]
+            d_prev = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev) if need_da else None
+            if l > 0:
+                np_n, part_n = alloc_partials(l - 1, False)
+                ps = stats[l - 1]
+            p0 = 0
+            for ci, (r0, r1) in enumerate(chunks):   # apply -> wgrad -> dgrad -> next layer's statistics, chunk by chunk (L2)
+                rows = r1 - r0
+                if pooled:
+                    check(lib.mpb_bn_bwd_apply_bf16(None, _off(d_pool, r0 // K), _off(argmax, r0 // K), K, _off(z, r0), ptr(sc[0]),
+                                                    ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), ptr(coef), rows, cout_p, _off(dz, r0), st),
+                          "mpb_bn_bwd_apply_bf16")
+                else:
+                    check(lib.mpb_bn_bwd_apply_bf16(_off(d_a, r0), None, None, K, _off(z, r0), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]),
+                                                    ptr(sc[3]), ptr(coef), rows, cout_p, _off(dz, r0), st), "mpb_bn_bwd_apply_bf16")
+                _gemm_wgrad(lib, _off(dz, r0), _off(acts[l], r0), ptr(dw), rows, cout_p, cin_p, st)
+                if need_da:
+                    _gemm_tn(lib, _off(dz, r0), ptr(wts[l]), _off(d_prev, r0), rows, cin_p, cout_p, st)
+                if l > 0:
+                    check(lib.mpb_bn_bwd_stats_bf16(_off(d_prev, r0), None, None, K, _off(zs[l - 1], r0), ptr(ps[0]), ptr(ps[1]),
+                                                    ptr(ps[2]), ptr(ps[3]), rows, cin_p, _off(part_n, p0), np_n[ci], st),
+                          "mpb_bn_bwd_stats_bf16")
+                    p0 += np_n[ci]
             grads[6 * l] = _unpermute_wgrad(dw, cout, cin, ctx.xyz_last and l == 0)
             grads[6 * l + 1] = torch.zeros(cout, dtype=torch.float32, device=dev)      # exact: BN removes the conv bias
             grads[6 * l + 2] = dgamma
             grads[6 * l + 3] = dbeta
-            if l > 0 or ctx.needs_input_grad[0]:
-                d_a = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev)
-                check(lib.mpb_gemm_bf16_tn(ptr(dz), ptr(wts[l]), ptr(d_a), M, cin_p, cout_p, 0, st), "mpb_gemm_bf16_tn")
-            else:
-                d_a = None
+            d_a = d_prev
+            if l > 0:
+                np_c, part = np_n, part_n
         return (d_a, None, None, None, None, *grads)
 
 
