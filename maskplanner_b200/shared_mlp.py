@@ -16,15 +16,16 @@ multiples of 64; statistics, pooled outputs and all parameter gradients are fp32
 conv bias cannot influence the output (BatchNorm removes it); it only enters the running mean, and its
 gradient is exactly zero (the reference's value there is rounding noise).
 
-L2-resident chunking.  Every [M, C] tensor of SA1/SA2 (134-268 MB at B = 64) is larger than the 126 MB
-L2, and training-mode BatchNorm puts a full-batch barrier between layers, so producer and consumer
-kernels of one tensor cannot be fused across the whole batch.  They CAN be run back to back on a row
-chunk small enough to stay in L2: forward, per chunk `bn_relu(l-1) -> GEMM(l) -> colstats(l)`; backward,
-per chunk `apply(l) -> wgrad(l) -> dgrad(l) -> bwd_stats(l-1)`.  The consumer of each intermediate then
-hits L2 instead of HBM (two of five forward passes and three of nine backward passes per layer), with the
-kernels unchanged -- only launch order and pointer offsets differ.
+Optional L2-resident chunking (off by default, see L2_CHUNK_BYTES).  Every [M, C] tensor of SA1/SA2
+(134-268 MB at B = 64) is larger than the 126 MB L2, and training-mode BatchNorm puts a full-batch barrier
+between layers, so producer and consumer kernels of one tensor cannot be fused across the whole batch.
+They CAN be run back to back on a row chunk small enough to stay in L2: forward, per chunk
+`bn_relu(l-1) -> GEMM(l) -> colstats(l)`; backward, per chunk `apply(l) -> wgrad(l) -> dgrad(l) ->
+bwd_stats(l-1)`; only launch order and pointer offsets differ.  Measured on B200 this is a net loss at
+B = 64, so the schedule below degenerates to one chunk unless MPB_L2_CHUNK_MB is set.
 """
 import ctypes
+import os
 
 import torch
 
@@ -32,8 +33,10 @@ from . import _cabi
 from ._cabi import check, ptr, stream_ptr
 
 # Rows per L2-resident chunk are chosen so that the widest producer/consumer pair of the stack
-# (A chunk + Z chunk, bf16) stays below this many bytes.
-L2_CHUNK_BYTES = 48 << 20
+# (A chunk + Z chunk, bf16) stays below this many bytes; 0 disables chunking (one launch per stage).
+# Measured on B200 at B = 64 (profiles/r01_notes.md): with 8 chunks the per-launch fixed cost of the two
+# GEMM kernels (barrier/TMEM set-up, split-M reductions) outweighs the L2 hits, so the default is off.
+L2_CHUNK_BYTES = int(os.environ.get("MPB_L2_CHUNK_MB", "0")) << 20
 
 
 def pad64(c):
@@ -93,6 +96,8 @@ def _unpermute_wgrad(dw, cout, cin, xyz_last):
 
 def _row_chunks(M, K, widest_pair_bytes_per_row):
     """Row ranges [(r0, r1), ...]: whole groups of K rows, a multiple of 128 rows (GEMM tile) where possible."""
+    if L2_CHUNK_BYTES <= 0:
+        return [(0, M)]
     rows = max(K, L2_CHUNK_BYTES // max(widest_pair_bytes_per_row, 1))
     unit = K * 128 // _gcd(K, 128)               # lcm(K, 128)
     rows = max(unit, rows // unit * unit) if rows >= unit else max(K, rows // K * K)
