@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--workload", default="train", choices=["train", "sa_micro", "chamfer"])
     ap.add_argument("--category", default="windows_v2")
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU (weak scaling)")
-    ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU-reference step (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=None,
+                    help="samples per CPU-reference step (default: --batch for --impl reference, 16 for the inline cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured step")
     return ap.parse_args()
@@ -124,6 +125,7 @@ def reference_step_time(category, ref_batch, steps, warmup):
 def run_reference(args, ws, rank):
     if rank != 0:
         return
+    args.ref_batch = args.ref_batch or args.batch      # the arm's own config: B = 64 per step (~3-4 s of CPU work each)
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
     dt = reference_step_time(args.category, args.ref_batch, steps, warm)
@@ -219,6 +221,9 @@ def run_ours(args, ws, rank, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if ws > 1:
+        # NCCL collectives are captured inside the step's CUDA graph: the watchdog thread must not poll CUDA
+        # events while a capture is open (PyTorch's documented requirement for whole-network capture)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     _cabi.load()
     peak, peak_src = peaks()
@@ -316,13 +321,20 @@ def run_ours(args, ws, rank, local):
                         "ms_per_step": e2e_step * 1e3},
                 "gpu_launches": launches, "roofline": roof, "kernels": ktab, "final_loss": float(lv)}
         if not args.no_cpu_baseline:
+            args.ref_batch = args.ref_batch or 16
             dt = reference_step_time(args.category, args.ref_batch, 1, 1)
             line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "1 timed + 1 warm-up optimisation step of the oracle port at B=%d on the host cores" % args.ref_batch}
         print(json.dumps(line), flush=True)
     if ws > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        trainer._graph = None          # drop the captured NCCL work before the communicator goes away
+        sys.stdout.flush()
+        try:
+            dist.destroy_process_group()
+        except Exception as e:        # teardown only; the measurement is already printed
+            print("destroy_process_group: %s" % e, file=sys.stderr)
 
 
 def main():

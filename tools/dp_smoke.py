@@ -1,0 +1,33 @@
+"""2-rank DP smoke test with progress markers (run under torchrun + timeout)."""
+import os, sys, time
+os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", os.environ.get("ASYNC_EH", "0"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from maskplanner_b200 import synthetic
+from maskplanner_b200.train_step import Trainer
+rank, ws, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+def log(*a):
+    print("[r%d %.1f]" % (rank, time.time() % 1000), *a, file=sys.stderr, flush=True)
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+log("pg up")
+use_graph = os.environ.get("GRAPH", "1") == "1"
+B = 16
+tr = Trainer("windows_v2", dev, world_size=ws, use_graph=use_graph)
+tr.model.dropout.p = 0.0
+batch = tr.to_device(synthetic.make_batch(B, "windows_v2", seed0=100 * rank))
+gen = torch.Generator().manual_seed(5)
+for i in range(6):
+    seeds = (torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen))
+    loss = tr.step(batch, seeds)
+    torch.cuda.synchronize()
+    log("step", i, float(loss))
+# parameters must stay identical across ranks
+flat = torch.cat([p.detach().flatten() for p in tr.model.parameters()])
+other = flat.clone()
+dist.broadcast(other, src=0)
+log("param max diff vs rank0", float((flat - other).abs().max()))
+dist.barrier()
+dist.destroy_process_group()
+log("done")
