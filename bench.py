@@ -224,6 +224,8 @@ def run_ours(args, ws, rank, local):
         # NCCL collectives are captured inside the step's CUDA graph: the watchdog thread must not poll CUDA
         # events while a capture is open (PyTorch's documented requirement for whole-network capture)
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _cabi.load()
     peak, peak_src = peaks()

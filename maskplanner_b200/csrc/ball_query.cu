@@ -3,10 +3,10 @@
 //
 // The reference materialises a [B,S,N] fp32 distance tensor plus a [B,S,N] int64 index tensor and
 // fully sorts the latter; only the first `nsample` in-ball indices in ascending order survive.
-// Here one THREAD owns one query and walks the cloud in index order through a shared-memory tile
-// of (x, y, z, |p|^2) float4s (one broadcast LDS.128 per point per warp), appending hits to its
-// output row until `nsample` are found -- O(S*N) fp32 work, O(S*nsample) bytes written, nothing
-// else touches HBM.  A block stops as soon as all of its queries are full.
+// Here one WARP owns one query and walks the cloud in index order through a shared-memory tile
+// of (x, y, z, |p|^2) float4s, 32 points per step, appending hits (ballot + popc keep them in index
+// order) until `nsample` are found -- O(S*N) fp32 work, O(S*nsample) bytes written, nothing else
+// touches HBM.  A block stops as soon as all of its queries are full.
 //
 // Bit-exactness contract: d = ((-2*dot) + |q|^2) + |p|^2, dot = fma(qz,pz, fma(qy,py, qx*px)),
 // |v|^2 = ((vx*vx)+(vy*vy))+(vz*vz) with every op rounded; in-ball iff !(d > r2) (NaN counts as
@@ -27,15 +27,20 @@ __device__ __forceinline__ float sqdist_expanded(float qx, float qy, float qz, f
 
 constexpr int kBqTile = 1024;  // points per shared-memory tile (16 KB)
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// One WARP per query: the 32 lanes test 32 consecutive points per step (conflict-free LDS.128), a ballot
+// gives the in-ball mask and each hit lane stores its index at `cnt + popc(mask below me)`, which keeps
+// the output in ascending index order.  B*S warps (32 768 at the micro-benchmark shape) fill the machine;
+// a thread-per-query mapping has the same instruction count but only B*S/32 warps and is latency-bound.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 ball_query_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc,
                   const float *__restrict__ q, int64_t qsb, int64_t qsn, int64_t qsc, int N, int S, float r2,
                   int nsample, int64_t *__restrict__ out)
 {
     __shared__ float4 tile[kBqTile];
     const int b = blockIdx.y;
-    const int s = blockIdx.x * THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * WARPS + (threadIdx.x >> 5);
     const bool live = s < S;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (live) {
@@ -46,35 +51,42 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64
     }
     const float qn = norm3_rn(qx, qy, qz);
     int64_t *o = out + ((int64_t)b * S + (live ? s : 0)) * nsample;
-    int cnt = live ? 0 : nsample;
-    long long first = N;
+    int cnt = live ? 0 : nsample;   // warp-uniform
+    int first = N;
+    const unsigned below = (1u << lane) - 1u;
     const float *pb = xyz + (int64_t)b * xsb;
     for (int t0 = 0; t0 < N; t0 += kBqTile) {
         const int tn = min(kBqTile, N - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < tn; i += THREADS) {
+        for (int i = threadIdx.x; i < tn; i += WARPS * 32) {
             const float *p = pb + (int64_t)(t0 + i) * xsn;
             const float x = p[0], y = p[xsc], z = p[2 * xsc];
             tile[i] = make_float4(x, y, z, norm3_rn(x, y, z));
         }
         __syncthreads();
-        if (cnt < nsample) {
-#pragma unroll 4
-            for (int i = 0; i < tn; ++i) {
-                const float d = sqdist_expanded(qx, qy, qz, qn, tile[i]);
-                if (!(d > r2)) {
-                    if (cnt < nsample) {
-                        if (cnt == 0) first = t0 + i;
-                        o[cnt] = t0 + i;
-                        ++cnt;
-                    }
-                }
+        for (int i0 = 0; i0 < tn && cnt < nsample; i0 += 64) {
+            // two independent 32-point groups per iteration (two LDS + FMA chains in flight)
+            const int ia = i0 + lane, ib = i0 + 32 + lane;
+            const bool in_a = ia < tn && !(sqdist_expanded(qx, qy, qz, qn, tile[ia < tn ? ia : 0]) > r2);
+            const bool in_b = ib < tn && !(sqdist_expanded(qx, qy, qz, qn, tile[ib < tn ? ib : 0]) > r2);
+            const unsigned ma = __ballot_sync(0xffffffffu, in_a), mb = __ballot_sync(0xffffffffu, in_b);
+            if (ma) {
+                if (cnt == 0) first = t0 + i0 + __ffs(ma) - 1;
+                const int pos = cnt + __popc(ma & below);
+                if (in_a && pos < nsample) o[pos] = t0 + ia;
+                cnt += __popc(ma);
+            }
+            if (mb && cnt < nsample) {
+                if (cnt == 0) first = t0 + i0 + 32 + __ffs(mb) - 1;
+                const int pos = cnt + __popc(mb & below);
+                if (in_b && pos < nsample) o[pos] = t0 + ib;
+                cnt += __popc(mb);
             }
         }
         if (__syncthreads_and(cnt >= nsample)) break;
     }
     if (live)
-        for (int k = cnt; k < nsample; ++k) o[k] = first;  // pad with the first hit (N if the ball is empty)
+        for (int k = (cnt < nsample ? cnt : nsample) + lane; k < nsample; k += 32) o[k] = first;  // pad with the first hit (N if empty)
 }
 
 // kNN grouping: thread per query, the K smallest expanded-form distances kept sorted (ascending) in
@@ -180,16 +192,13 @@ extern "C" int mpb_ball_query_f32(const float *xyz, int64_t xsb, int64_t xsn, in
     MPB_REQUIRE(xyz && new_xyz && out_idx, "null pointer");
     MPB_REQUIRE(B <= 65535, "B exceeds grid.y");
     cudaStream_t st = (cudaStream_t)stream;
-    // 64-thread blocks keep the grid >= 2 waves at the model shapes (S=512,B=64 -> 512 blocks)
-    if ((int64_t)B * ((S + 127) / 128) >= 4 * sm_count()) {
-        dim3 grid((S + 127) / 128, B);
-        ball_query_kernel<128><<<grid, 128, 0, st>>>(xyz, xsb, xsn, xsc, new_xyz, qsb, qsn, qsc, N, S, r2, nsample, out_idx);
-    } else if ((int64_t)B * ((S + 63) / 64) >= 2 * sm_count()) {
-        dim3 grid((S + 63) / 64, B);
-        ball_query_kernel<64><<<grid, 64, 0, st>>>(xyz, xsb, xsn, xsc, new_xyz, qsb, qsn, qsc, N, S, r2, nsample, out_idx);
+    // 16 queries (warps) per block share one point tile; fall back to 4 when that would leave SMs idle
+    if ((int64_t)B * ((S + 15) / 16) >= 2 * sm_count()) {
+        dim3 grid((S + 15) / 16, B);
+        ball_query_kernel<16><<<grid, 512, 0, st>>>(xyz, xsb, xsn, xsc, new_xyz, qsb, qsn, qsc, N, S, r2, nsample, out_idx);
     } else {
-        dim3 grid((S + 31) / 32, B);
-        ball_query_kernel<32><<<grid, 32, 0, st>>>(xyz, xsb, xsn, xsc, new_xyz, qsb, qsn, qsc, N, S, r2, nsample, out_idx);
+        dim3 grid((S + 3) / 4, B);
+        ball_query_kernel<4><<<grid, 128, 0, st>>>(xyz, xsb, xsn, xsc, new_xyz, qsb, qsn, qsc, N, S, r2, nsample, out_idx);
     }
     return check_launch("ball_query_kernel");
 }

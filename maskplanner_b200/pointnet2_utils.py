@@ -354,3 +354,103 @@ class PointNetSetAbstraction(nn.Module):
         pooled = shared_mlp_max(a0, K, self.mlp_convs, self.mlp_bns, self.training, xyz_last=rows is None)   # :208-214
         out = pooled.view(B, S, -1).permute(0, 2, 1)
         return new_xyz.permute(0, 2, 1), (out.contiguous() if self.contiguous_output else out)
+
+
+# ---------------------------------------------------------------------------------------------
+# Remaining surface of the reference file: multi-scale grouping and feature propagation.
+# Neither is on the MaskPlanner path (Msg is unused, FP only appears in a NotImplementedError class), but
+# other backbones of the reference import them; they reuse the same kernels.
+# ---------------------------------------------------------------------------------------------
+def _torch_mlp_max(rows, convs, bns):
+    """rows [B,S,K,C] -> [B,C',S] with strict-fp32 library GEMMs (reference :267-271)."""
+    x = rows
+    for conv, bn in zip(convs, bns):
+        x = F.linear(x, conv.weight.view(conv.out_channels, -1), conv.bias)
+        x = F.relu(bn(x.permute(0, 3, 1, 2))).permute(0, 2, 3, 1)
+    return torch.max(x, 2)[0].permute(0, 2, 1).contiguous()
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """Reference :219-276: one FPS, then per radius ball query -> [feats | centred xyz] -> MLP -> max, concatenated.
+    Same constructor, attributes and parameter names (``conv_blocks.{i}.{j}``, ``bn_blocks.{i}.{j}``)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint = npoint
+        self.radius_list = radius_list
+        self.nsample_list = nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for mlp in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last_channel = in_channel + 3
+            for out_channel in mlp:
+                convs.append(nn.Conv2d(last_channel, out_channel, 1))
+                bns.append(nn.BatchNorm2d(out_channel))
+                last_channel = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self.precision = None
+
+    def forward(self, xyz, points, seed_idx=None):
+        from .shared_mlp import pad64, shared_mlp_max
+        xyz = xyz.permute(0, 2, 1)
+        if points is not None:
+            points = points.permute(0, 2, 1)
+        B, N, C = xyz.shape
+        S = self.npoint
+        new_xyz = index_points(xyz, farthest_point_sample(xyz, S, seed_idx))          # :253
+        tensor_core = (self.precision or _MLP_PRECISION) == "bf16" and (self.training or not torch.is_grad_enabled())
+        D = 0 if points is None else points.shape[2]
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            idx = query_ball_point(radius, K, xyz, new_xyz)                           # :257
+            if tensor_core:
+                # the reference concatenates [feats, centred xyz] here (:262-263): exactly the bf16 row layout
+                a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))
+                pooled = shared_mlp_max(a0, K, self.conv_blocks[i], self.bn_blocks[i], self.training, xyz_last=False)
+                outs.append(pooled.view(B, S, -1).permute(0, 2, 1))
+            else:
+                centred = group_points(xyz, None, new_xyz, idx)                       # :258-259
+                rows = centred if points is None else torch.cat([index_points(points, idx), centred], dim=-1)
+                outs.append(_torch_mlp_max(rows, self.conv_blocks[i], self.bn_blocks[i]))
+        return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=1)                       # :274-276
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """Reference :279-329: inverse-distance interpolation from the 3 nearest sampled points, concat, Conv1d MLP.
+    The 3-NN search is the kNN kernel (expanded-form distances, ascending); the MLP over [B,C,N] stays a library op."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv1d(last_channel, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last_channel = out_channel
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        xyz1 = xyz1.permute(0, 2, 1)
+        xyz2 = xyz2.permute(0, 2, 1)
+        points2 = points2.permute(0, 2, 1)
+        B, N, C = xyz1.shape
+        S = xyz2.shape[1]
+        if S == 1:
+            interpolated = points2.repeat(1, N, 1)                                     # :307-308
+        else:
+            k = min(3, S)
+            idx, dists = knn_group(k, xyz2, xyz1, return_dist=True)                     # :310-312 (sort + first 3)
+            recip = 1.0 / (dists + 1e-8)                                                # :314
+            weight = recip / torch.sum(recip, dim=2, keepdim=True)                      # :315-316
+            interpolated = torch.sum(index_points(points2, idx) * weight.view(B, N, k, 1), dim=2)   # :317
+        if points1 is not None:
+            new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)    # :319-321
+        else:
+            new_points = interpolated
+        new_points = new_points.permute(0, 2, 1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            new_points = F.relu(bn(conv(new_points)))                                   # :326-328
+        return new_points

@@ -222,6 +222,41 @@ def chamfer_fixtures(RC):
     print("chamfer_small.npz:", len(cases), "arrays")
 
 
+def msg_fp_fixture(R):
+    """PointNetSetAbstractionMsg and PointNetFeaturePropagation (off the MaskPlanner path): frozen straight
+    from the reference modules (no oracle restatement; the GPU tests compare the drop-in modules with these files)."""
+    torch.manual_seed(321)
+    B, N = 2, 400
+    xyz = synthetic.make_clouds(B, N, seed0=61, kind="cube").permute(0, 2, 1).contiguous()
+    feats = torch.randn(B, 5, N)
+    cases = {"xyz": xyz.numpy(), "feats": feats.numpy()}
+    msg = R.PointNetSetAbstractionMsg(48, [0.3, 0.6], [8, 16], 5, [[16, 32], [24, 40]])
+    fp = R.PointNetFeaturePropagation(72 + 5, [32, 16])
+    for k, v in msg.state_dict().items():
+        cases["msg/" + k] = v.numpy().copy()
+    for k, v in fp.state_dict().items():
+        cases["fp/" + k] = v.numpy().copy()
+    seed = torch.randint(0, N, (B,))
+    cases["seed"] = seed.numpy()
+    msg.train(), fp.train()
+    f1 = feats.clone().requires_grad_(True)
+    orig = torch.randint
+    try:
+        torch.randint = lambda *a, **kw: seed.clone()
+        nx, nf = msg(xyz, f1)
+    finally:
+        torch.randint = orig
+    up = fp(xyz, nx, f1, nf)                       # propagate the 72 multi-scale channels back to all N points
+    loss = (up ** 2).sum()
+    g = torch.autograd.grad(loss, [f1] + list(msg.parameters()))
+    cases["msg_new_xyz"], cases["msg_new_points"], cases["fp_out"] = nx.detach().numpy(), nf.detach().numpy(), up.detach().numpy()
+    cases["grad_feats"] = g[0].numpy()
+    for (n, _), gr in zip(msg.named_parameters(), g[1:]):
+        cases["grad/msg." + n] = gr.numpy()
+    np.savez_compressed(os.path.join(OUT, "msg_fp_small.npz"), **cases)
+    print("msg_fp_small.npz:", len(cases), "arrays")
+
+
 class _Cfg(dict):
     __getattr__ = dict.__getitem__
 
@@ -317,6 +352,7 @@ def main():
     encoder_model_shapes(R)
     sa_module_fixture(R)
     chamfer_fixtures(RC)
+    msg_fp_fixture(R)
     step_fixture()
 
 

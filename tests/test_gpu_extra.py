@@ -1,0 +1,77 @@
+"""GPU parity for the remaining surface of models/pointnet2_utils.py and small extensions:
+PointNetSetAbstractionMsg / PointNetFeaturePropagation against fixtures frozen from the reference modules
+(oracle/make_golden.py::msg_fp_fixture), the `full_points` argument, bf16 chamfer inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_msg_and_feature_propagation_golden(golden, precision, tol):
+    from maskplanner_b200 import pointnet2_utils as P
+    g = golden("msg_fp_small.npz")
+    msg = P.PointNetSetAbstractionMsg(48, [0.3, 0.6], [8, 16], 5, [[16, 32], [24, 40]])
+    fp = P.PointNetFeaturePropagation(72 + 5, [32, 16])
+    msg.load_state_dict(_sd(g, "msg/"))            # same parameter names as the reference
+    fp.load_state_dict(_sd(g, "fp/"))
+    msg.precision = precision
+    msg.cuda().train(), fp.cuda().train()
+    xyz = torch.from_numpy(g["xyz"]).cuda()
+    feats = torch.from_numpy(g["feats"]).cuda().requires_grad_(True)
+    nx, nf = msg(xyz, feats, seed_idx=torch.from_numpy(g["seed"]))
+    assert np.array_equal(nx.detach().cpu().numpy(), g["msg_new_xyz"])
+    assert tuple(nf.shape) == g["msg_new_points"].shape
+    assert _rel(nf.detach().cpu().numpy(), g["msg_new_points"]) < tol
+    up = fp(xyz, nx, feats, nf)
+    assert tuple(up.shape) == g["fp_out"].shape
+    assert _rel(up.detach().cpu().numpy(), g["fp_out"]) < max(tol, 1e-4) * 3
+    if precision == "fp32":
+        grads = torch.autograd.grad((up ** 2).sum(), [feats] + list(msg.parameters()))
+        assert _rel(grads[0].cpu().numpy(), g["grad_feats"]) < 2e-3
+        gmax = max(np.abs(g["grad/msg." + n]).max() for n, _ in msg.named_parameters())
+        for (n, _), gr in zip(msg.named_parameters(), grads[1:]):
+            want = g["grad/msg." + n]
+            assert np.allclose(gr.cpu().numpy(), want, rtol=2e-3, atol=2e-5 * gmax), n
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_full_points_argument(precision, tol):
+    """pointnet2_seg.py:67 passes full_points=[B,C+D,N] with points=None: the grouped tensor is the gathered full rows."""
+    from maskplanner_b200 import pointnet2_utils as P
+    from oracle import torch_oracle as T
+    torch.manual_seed(0)
+    B, N = 2, 300
+    xyz = torch.rand(B, 3, N) * 2 - 1
+    full = torch.cat([xyz, torch.randn(B, 4, N)], dim=1)
+    sa = P.PointNetSetAbstraction(32, 0.5, 8, 7, [16, 32], False)
+    ref = T.PointNetSetAbstraction(32, 0.5, 8, 7, [16, 32], False)
+    ref.load_state_dict(sa.state_dict())
+    sa.precision = precision
+    sa.cuda()
+    seed = torch.tensor([3, 77])
+    nx, nf = sa(xyz.cuda(), None, full_points=full.cuda(), seed_idx=seed)
+    rx, rf = ref(xyz, None, full_points=full, seed_idx=seed)
+    assert torch.equal(nx.cpu(), rx)
+    assert _rel(nf.detach().cpu().numpy(), rf.detach().numpy()) < tol
+
+
+def test_bf16_chamfer_inputs_accumulate_in_fp32():
+    """BASELINE configs[2] lists bf16 inputs: a builder extension (pytorch3d is fp32/fp64 only) -- inputs are widened
+    to fp32, so the result equals the fp32 kernel on the bf16-rounded points (tolerance 1e-2 vs the unrounded ones)."""
+    from maskplanner_b200 import pytorch3d_chamfer as CH
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(4, 500, 3, generator=g).cuda(), torch.randn(4, 600, 3, generator=g).cuda()
+    a = CH.chamfer_distance(x.bfloat16(), y.bfloat16())[0]
+    b = CH.chamfer_distance(x.bfloat16().float(), y.bfloat16().float())[0]
+    c = CH.chamfer_distance(x, y)[0]
+    assert torch.equal(a, b) and abs(float(a) - float(c)) / float(c) < 1e-2
