@@ -66,6 +66,19 @@ struct RowWalk {
     }
 };
 
+// Contiguous slab of rows owned by this CTA: [slab_begin, slab_end), slab size a multiple of rpp.
+__device__ __forceinline__ int64_t slab_rows(int64_t M, int rpp)
+{
+    const int64_t per = (M + gridDim.x - 1) / gridDim.x;
+    return (per + rpp - 1) / rpp * rpp;
+}
+__device__ __forceinline__ int64_t slab_begin(int64_t M, int rpp) { return (int64_t)blockIdx.x * slab_rows(M, rpp); }
+__device__ __forceinline__ int64_t slab_end(int64_t M, int rpp)
+{
+    const int64_t e = slab_begin(M, rpp) + slab_rows(M, rpp);
+    return e < M ? e : M;
+}
+
 // ---- training statistics ---------------------------------------------------------------------------
 template <class RowFn>
 __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict__ partials, RowFn fn)
@@ -78,10 +91,12 @@ __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict_
         float s0[8], s1[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
-        const int64_t stride = (int64_t)gridDim.x * w.rpp;
-        int64_t r = (int64_t)blockIdx.x * w.rpp + w.tr;
-        for (; r + (kRowUnroll - 1) * stride < M; r += kRowUnroll * stride) fn(r, stride, kRowUnroll, w.tc * 8, s0, s1);
-        for (; r < M; r += stride) fn(r, stride, 1, w.tc * 8, s0, s1);
+        // each CTA streams one contiguous slab of rows (consecutive 16-byte x cg x rpp blocks: DRAM-page friendly)
+        const int64_t r_end = slab_end(M, w.rpp);
+        const int64_t stride = w.rpp;
+        int64_t r = slab_begin(M, w.rpp) + w.tr;
+        for (; r + (kRowUnroll - 1) * stride < r_end; r += kRowUnroll * stride) fn(r, stride, kRowUnroll, w.tc * 8, s0, s1);
+        for (; r < r_end; r += stride) fn(r, stride, 1, w.tc * 8, s0, s1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             atomicAdd(&sm_acc[w.tc * 8 + i], s0[i]);
@@ -178,15 +193,15 @@ bn_relu_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ sc
     float sc[8], sh[8];
     load8(scale + c0, sc);
     load8(shift + c0, sh);
-    const int64_t stride = (int64_t)gridDim.x * w.rpp;
-    for (int64_t r = (int64_t)blockIdx.x * w.rpp + w.tr; r < M; r += kRowUnroll * stride) {
+    const int64_t stride = w.rpp, r_end = slab_end(M, w.rpp);
+    for (int64_t r = slab_begin(M, w.rpp) + w.tr; r < r_end; r += kRowUnroll * stride) {
         uint4 raw[kRowUnroll];
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
-            if (r + u * stride < M) raw[u] = ld16(Z + (r + u * stride) * C + c0);
+            if (r + u * stride < r_end) raw[u] = ld16(Z + (r + u * stride) * C + c0);
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
-            if (r + u * stride < M) {
+            if (r + u * stride < r_end) {
                 float z[8];
                 unpack8(raw[u], z);
 #pragma unroll
@@ -349,18 +364,18 @@ bwd_apply_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
     const int c0 = w.tc * 8;
     ApplyConst k;
     k.load(scale, shift, mean, rstd, coef, C, c0);
-    const int64_t stride = (int64_t)gridDim.x * w.rpp;
-    for (int64_t r = (int64_t)blockIdx.x * w.rpp + w.tr; r < M; r += kRowUnroll * stride) {
+    const int64_t stride = w.rpp, r_end = slab_end(M, w.rpp);
+    for (int64_t r = slab_begin(M, w.rpp) + w.tr; r < r_end; r += kRowUnroll * stride) {
         uint4 rz[kRowUnroll], rd[kRowUnroll];
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
-            if (r + u * stride < M) {
+            if (r + u * stride < r_end) {
                 rz[u] = ld16(Z + (r + u * stride) * C + c0);
                 rd[u] = ld16(dA + (r + u * stride) * C + c0);
             }
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
-            if (r + u * stride < M) {
+            if (r + u * stride < r_end) {
                 float z[8], d[8];
                 unpack8(rz[u], z);
                 unpack8(rd[u], d);
@@ -424,7 +439,7 @@ static inline int row_blocks(int64_t rows, int C, int per_sm)
     const int cap = per_sm * sm_count();
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
-static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, 4); }
+static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, 8); }
 
 }  // namespace mpb
 

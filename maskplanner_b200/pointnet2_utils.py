@@ -450,7 +450,8 @@ class PointNetFeaturePropagation(nn.Module):
             new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)    # :319-321
         else:
             new_points = interpolated
-        new_points = new_points.permute(0, 2, 1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            new_points = F.relu(bn(conv(new_points)))                                   # :326-328
-        return new_points
+        x = new_points                                                                  # [B,N,C] rows
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):                              # :326-328
+            x = F.linear(x, conv.weight.squeeze(-1), conv.bias)                         # Conv1d(k=1) as a strict-fp32 row GEMM
+            x = F.relu(bn(x.permute(0, 2, 1))).permute(0, 2, 1)
+        return x.permute(0, 2, 1).contiguous()
