@@ -85,14 +85,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 
 template <bool OUT_F32>
 __global__ void __launch_bounds__(kGemmTnThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void *__restrict__ Cout,
-               int M, int N, int K, int BN, int ldc, int stages)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, void *__restrict__ Cout, int M, int N, int K, int BN, int ldc, int stages)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
-    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(smem + (size_t)stages * stage_bytes);
+    // [stages x (A | B)] [bf16 path: 2 warpgroups x 2 output staging tiles of 128 rows x 128 B] [barriers]
+    uint8_t *staging = smem + (size_t)stages * stage_bytes;
+    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(staging + (OUT_F32 ? 0 : 4 * kABytes));
     const int num_kb = K / kTileK;
     const int tiles_m = (M + kTileM - 1) / kTileM, tiles_n = N / BN;
     const int total = tiles_m * tiles_n;
@@ -166,39 +168,71 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int acc = (warp - 4) >> 2;   // accumulator buffer owned by this warpgroup
         uint32_t acc_phase = 0;
         int t = 0;
+        int nstore = 0;                                 // 64-column blocks stored so far by this warpgroup (staging ring of 2)
+        const bool issuer = ew == 0 && lane == 0;       // the one thread of the warpgroup that owns its bulk-store groups
+        const int r_in_tile = ew * 32 + lane;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
             if ((t & 1) != acc) continue;
             const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tail->tfull[acc], acc_phase);
             tc_fence_after();
-            const int row = m0 + ew * 32 + lane;
+            const int row = m0 + r_in_tile;
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(ew * 32) << 16);
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                if (row < M) {
-                    if (OUT_F32) {
+            if (OUT_F32) {
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                    if (row < M) {
                         float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(Cout) + (size_t)row * ldc + n0 + c0);
 #pragma unroll
                         for (int v = 0; v < 8; ++v)
                             dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                                                  __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-                    } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(Cout) + (size_t)row * ldc + n0 + c0);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+            } else {
+                // bf16: TMEM -> registers -> swizzled staging tile in shared memory -> ONE TMA store per 128 x 64 block
+                // (full 128-byte lines to L2 instead of 32 half-sector writes per warp instruction)
+                for (int c0 = 0; c0 < BN; c0 += 64, ++nstore) {
+                    uint8_t *buf = staging + (size_t)(acc * 2 + (nstore & 1)) * kABytes;
+                    if (issuer) bulk_wait_read<1>();                 // the store that used this buffer two blocks ago has drained
+                    named_bar_sync(1 + acc, 128);
+                    uint8_t *rowp = buf + r_in_tile * 128;
 #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            dst[v] = make_uint4(pack_bf16(__uint_as_float(r[8 * v]), __uint_as_float(r[8 * v + 1])),
-                                                pack_bf16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
-                                                pack_bf16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
-                                                pack_bf16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
+                    for (int h = 0; h < 2; ++h) {
+                        if (c0 + 32 * h < BN) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(taddr + (uint32_t)(c0 + 32 * h), r);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const int chunk = (4 * h + v) ^ (r_in_tile & 7);   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+                                *reinterpret_cast<uint4 *>(rowp + chunk * 16) =
+                                    make_uint4(pack_bf16(__uint_as_float(r[8 * v]), __uint_as_float(r[8 * v + 1])),
+                                               pack_bf16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
+                                               pack_bf16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
+                                               pack_bf16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
+                            }
+                        }
+                    }
+                    if (c0 + 64 >= BN) {                               // accumulator fully drained: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + acc, 128);
+                    if (issuer) {
+                        tma_store_2d(&tmC, buf, n0 + c0, m0);
+                        bulk_commit();
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tail->tempty[acc]);
             acc_phase ^= 1;
         }
+        if (!OUT_F32 && issuer) bulk_wait<0>();          // all stores complete before the CTA (and its shared memory) goes away
     }
     tc_fence_before();
     __syncthreads();
@@ -306,9 +340,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
     if (warp == 2) tmem_dealloc<256>(tmem_base);
 }
 
+// Columns per tile: the whole N when it fits one UMMA (N <= 256, multiple of 32); otherwise the largest multiple of
+// 64 dividing N (the bf16 epilogue stores whole 64-column blocks, which must not straddle two tiles).
 static int pick_bn(int N)
 {
-    for (int bn = 256; bn >= 32; bn -= 32)
+    if (N <= 256) return N % 32 == 0 ? N : 0;
+    for (int bn = 256; bn >= 64; bn -= 64)
         if (N % bn == 0) return bn;
     return 0;
 }
@@ -325,26 +362,30 @@ extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, in
     const int BN = pick_bn(N);
     MPB_REQUIRE(BN > 0, "N must be a multiple of 32");
     MPB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
-    CUtensorMap tmA, tmB;
+    MPB_REQUIRE(BN == N || BN % 64 == 0, "N > 256 must be a multiple of 64");
+    CUtensorMap tmA, tmB, tmC;
     int rc = make_map_bf16(&tmA, A, M, K, K, kTileM);
     if (rc) return rc;
     rc = make_map_bf16(&tmB, B, N, K, K, BN);
     if (rc) return rc;
     const int stage_bytes = kABytes + BN * 128;
-    int stages = (200 * 1024) / stage_bytes;
+    const int staging_bytes = out_fp32 ? 0 : 4 * kABytes;    // bf16 output: 2 warpgroups x 2 staging tiles for the TMA stores
+    int stages = (224 * 1024 - staging_bytes) / stage_bytes;
     stages = stages > 8 ? 8 : stages;
-    const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmSmemTail) + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + staging_bytes + sizeof(GemmSmemTail) + 1024;
     const int tiles = ((M + kTileM - 1) / kTileM) * (N / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
     cudaStream_t st = (cudaStream_t)stream;
     if (out_fp32) {
         auto kern = gemm_tn_kernel<true>;
         MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
+        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmA, C, M, N, K, BN, N, stages);
     } else {
+        rc = make_map_bf16(&tmC, C, M, N, N, kTileM);          // output tiles: 128 rows x 64 columns, SWIZZLE_128B
+        if (rc) return rc;
         auto kern = gemm_tn_kernel<false>;
         MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, C, M, N, K, BN, N, stages);
+        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmC, C, M, N, K, BN, N, stages);
     }
     return check_launch("gemm_tn_kernel");
 }
