@@ -189,16 +189,17 @@ def kernel_table(args, dev, peak):
     t = time_kernel(lambda: P.query_ball_point(0.2, 32, xyz, new_xyz), flush=flush)
     out["ball_query_sa1"] = {"ms": t, "gpairs_per_s": B * 512 * 5120 / t / 1e6}
     ball = P.query_ball_point(0.2, 32, xyz, new_xyz)
-    t = time_kernel(lambda: P.group_points(xyz, None, new_xyz, ball), flush=flush)
-    gb = 2 * B * 512 * 32 * 3 * 4
+    # grouping as the step runs it: bf16 GEMM rows [B*S*K, pad64(3+D)] (gathered fp32 reads + bf16 row writes)
+    t = time_kernel(lambda: P._GroupPointsBF16.apply(xyz, None, new_xyz, ball, 64), flush=flush)
+    gb = B * 512 * 32 * (3 * 4 + 64 * 2)
     out["group_sa1"] = {"ms": t, "algorithmic_GBps": gb / t / 1e6, "frac_of_hbm_peak": gb / t / 1e6 / peak}
     f2 = torch.randn(B, 512, 128, device=dev)
     x2 = new_xyz
     idx2 = P.farthest_point_sample(x2, 128, seed_idx=seed)
     nx2 = P.index_points(x2, idx2)
     ball2 = P.query_ball_point(0.4, 64, x2, nx2)
-    t = time_kernel(lambda: P.group_points(x2, f2, nx2, ball2), flush=flush)
-    gb = 2 * B * 128 * 64 * 131 * 4
+    t = time_kernel(lambda: P._GroupPointsBF16.apply(x2, f2, nx2, ball2, 192), flush=flush)
+    gb = B * 128 * 64 * (131 * 4 + 192 * 2)
     out["group_sa2"] = {"ms": t, "algorithmic_GBps": gb / t / 1e6, "frac_of_hbm_peak": gb / t / 1e6 / peak}
     cfg = synthetic.CATEGORIES[args.category]
     ov = synthetic.out_vectors(cfg["n_pred_traj_points"])

@@ -162,6 +162,13 @@ MPB_API int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, int N
                              int out_fp32, void *stream);
 MPB_API int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int M, int N, int K,
                                 void *stream);
+/* Forward GEMM with the layer's BatchNorm statistics fused into the epilogue: besides C (bf16) it writes
+ * `nparts` partial rows [2][N] (sum, sum of squares of the stored bf16 values over disjoint row sets) that
+ * mpb_bn_finalize_f32 combines.  nparts = mpb_gemm_tn_stat_partials(M,N,K); 0 means the shape cannot be
+ * fused (N > 256) and the caller uses mpb_gemm_bf16_tn + mpb_bn_colstats_bf16. */
+MPB_API int mpb_gemm_tn_stat_partials(int M, int N, int K);
+MPB_API int mpb_gemm_bf16_tn_stats(const void *A, const void *B, void *C, int M, int N, int K,
+                                   float *partials, int nparts, void *stream);
 MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
 MPB_API int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *partials, int nparts,
                                  void *stream);

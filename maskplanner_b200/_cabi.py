@@ -41,6 +41,8 @@ SIGNATURES = {
     "mpb_group_points_bwd_bf16": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mpb_gemm_bf16_tn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mpb_gemm_bf16_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "mpb_gemm_tn_stat_partials": (_I, [_I, _I, _I]),
+    "mpb_gemm_bf16_tn_stats": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _P]),
     "mpb_bn_stat_partials": (_I, [_L, _I]),
     "mpb_bn_colstats_bf16": (_I, [_P, _L, _I, _P, _I, _P]),
     "mpb_bn_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),

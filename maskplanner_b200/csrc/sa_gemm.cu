@@ -83,10 +83,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <bool OUT_F32>
+// Column sums of a 32 x 32 block held one ROW per lane (v[c] = this lane's value in column c): a transpose-reduce
+// butterfly.  Each step halves the live registers -- a lane keeps the half of the columns selected by one bit of its
+// lane index and receives the other lanes' contributions for that half -- so after 16+8+4+2+1 = 31 shuffles lane L
+// holds the sum over all 32 rows of column L.  No shared memory, no atomics.
+__device__ __forceinline__ float warp_column_sum_32x32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// STATS: additionally accumulate per-column sum / sum of squares of the (bf16-rounded) outputs -- the training-mode
+// BatchNorm statistics of the layer (reference :210-212) -- in the epilogue, so Z is not read again for them.
+// Each epilogue warp keeps its own [2][BN] accumulator in shared memory (lane L owns column 32j+L: no conflicts, no
+// atomics) and writes it as one partial row at the end: partials[(blockIdx.x*8 + epilogue warp)][2][N].
+template <bool OUT_F32, bool STATS>
 __global__ void __launch_bounds__(kGemmTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, void *__restrict__ Cout, int M, int N, int K, int BN, int ldc, int stages)
+               const __grid_constant__ CUtensorMap tmC, void *__restrict__ Cout, int M, int N, int K, int BN, int ldc, int stages,
+               float *__restrict__ stat_partials)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
@@ -94,7 +118,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
     // [stages x (A | B)] [bf16 path: 2 warpgroups x 2 output staging tiles of 128 rows x 128 B] [barriers]
     uint8_t *staging = smem + (size_t)stages * stage_bytes;
-    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(staging + (OUT_F32 ? 0 : 4 * kABytes));
+    float *stat_acc = reinterpret_cast<float *>(staging + (OUT_F32 ? 0 : 4 * kABytes));          // STATS: [8 warps][2][BN]
+    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(reinterpret_cast<uint8_t *>(stat_acc) + (STATS ? 8 * 2 * 256 * 4 : 0));
     const int num_kb = K / kTileK;
     const int tiles_m = (M + kTileM - 1) / kTileM, tiles_n = N / BN;
     const int total = tiles_m * tiles_n;
@@ -171,6 +196,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int nstore = 0;                                 // 64-column blocks stored so far by this warpgroup (staging ring of 2)
         const bool issuer = ew == 0 && lane == 0;       // the one thread of the warpgroup that owns its bulk-store groups
         const int r_in_tile = ew * 32 + lane;
+        float *my_stat = stat_acc + (size_t)(warp - 4) * 2 * BN;
+        if (STATS)
+            for (int c = lane; c < 2 * BN; c += 32) my_stat[c] = 0.f;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
             if ((t & 1) != acc) continue;
             const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
@@ -206,14 +234,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (c0 + 32 * h < BN) {
                             uint32_t r[32];
                             tmem_ld_32x32(taddr + (uint32_t)(c0 + 32 * h), r);
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int v = 0; v < 16; ++v) pk[v] = pack_bf16(__uint_as_float(r[2 * v]), __uint_as_float(r[2 * v + 1]));
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
                                 const int chunk = (4 * h + v) ^ (r_in_tile & 7);   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
-                                *reinterpret_cast<uint4 *>(rowp + chunk * 16) =
-                                    make_uint4(pack_bf16(__uint_as_float(r[8 * v]), __uint_as_float(r[8 * v + 1])),
-                                               pack_bf16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
-                                               pack_bf16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
-                                               pack_bf16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
+                                *reinterpret_cast<uint4 *>(rowp + chunk * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                            }
+                            if (STATS) {   // statistics of exactly what was stored (rows past M are zero: TMA zero-fills A)
+                                float zv[32], zq[32];
+#pragma unroll
+                                for (int v = 0; v < 16; ++v) {
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk[v]));
+                                    zv[2 * v] = f.x, zv[2 * v + 1] = f.y;
+                                    zq[2 * v] = f.x * f.x, zq[2 * v + 1] = f.y * f.y;
+                                }
+                                const float cs = warp_column_sum_32x32(zv, lane), cq = warp_column_sum_32x32(zq, lane);
+                                my_stat[c0 + 32 * h + lane] += cs;
+                                my_stat[BN + c0 + 32 * h + lane] += cq;
                             }
                         }
                     }
@@ -233,6 +272,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             acc_phase ^= 1;
         }
         if (!OUT_F32 && issuer) bulk_wait<0>();          // all stores complete before the CTA (and its shared memory) goes away
+        if (STATS) {
+            float *dst = stat_partials + ((size_t)blockIdx.x * 8 + (warp - 4)) * 2 * N;      // tiles_n == 1 here: BN == N
+            for (int c = lane; c < 2 * BN; c += 32) dst[c] = my_stat[c];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -352,7 +395,34 @@ static int pick_bn(int N)
 
 }  // namespace mpb
 
+namespace mpb {
+static int gemm_tn_launch(const void *A, const void *B, void *C, int M, int N, int K, int out_fp32, float *stat_partials, int nparts,
+                          void *stream);
+}
+
 extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, int N, int K, int out_fp32, void *stream)
+{
+    return mpb::gemm_tn_launch(A, B, C, M, N, K, out_fp32, nullptr, 0, stream);
+}
+
+// Number of [2][N] partial rows mpb_gemm_bf16_tn_stats writes (0: this shape cannot fuse the statistics).
+extern "C" int mpb_gemm_tn_stat_partials(int M, int N, int K)
+{
+    if (M <= 0 || N <= 0 || N > 256 || N % 32 || K % 64) return 0;
+    const int tiles = (M + mpb::kTileM - 1) / mpb::kTileM;
+    return 8 * (tiles < mpb::sm_count() ? tiles : mpb::sm_count());
+}
+
+extern "C" int mpb_gemm_bf16_tn_stats(const void *A, const void *B, void *C, int M, int N, int K, float *partials, int nparts,
+                                      void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(partials && nparts > 0 && nparts == mpb_gemm_tn_stat_partials(M, N, K), "partials / nparts mismatch");
+    return gemm_tn_launch(A, B, C, M, N, K, 0, partials, nparts, stream);
+}
+
+static int mpb::gemm_tn_launch(const void *A, const void *B, void *C, int M, int N, int K, int out_fp32, float *stat_partials,
+                               int nparts, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad size");
@@ -369,7 +439,8 @@ extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, in
     rc = make_map_bf16(&tmB, B, N, K, K, BN);
     if (rc) return rc;
     const int stage_bytes = kABytes + BN * 128;
-    const int staging_bytes = out_fp32 ? 0 : 4 * kABytes;    // bf16 output: 2 warpgroups x 2 staging tiles for the TMA stores
+    const int staging_bytes = (out_fp32 ? 0 : 4 * kABytes)    // bf16 output: 2 warpgroups x 2 staging tiles for the TMA stores
+                              + (stat_partials ? 8 * 2 * 256 * 4 : 0);   // fused statistics: 8 warps x [2][256] floats
     int stages = (224 * 1024 - staging_bytes) / stage_bytes;
     stages = stages > 8 ? 8 : stages;
     const size_t smem = (size_t)stages * stage_bytes + staging_bytes + sizeof(GemmSmemTail) + 1024;
@@ -377,15 +448,22 @@ extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, in
     const int grid = tiles < sm_count() ? tiles : sm_count();
     cudaStream_t st = (cudaStream_t)stream;
     if (out_fp32) {
-        auto kern = gemm_tn_kernel<true>;
+        auto kern = gemm_tn_kernel<true, false>;
         MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmA, C, M, N, K, BN, N, stages);
+        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmA, C, M, N, K, BN, N, stages, nullptr);
     } else {
         rc = make_map_bf16(&tmC, C, M, N, N, kTileM);          // output tiles: 128 rows x 64 columns, SWIZZLE_128B
         if (rc) return rc;
-        auto kern = gemm_tn_kernel<false>;
-        MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmC, C, M, N, K, BN, N, stages);
+        if (stat_partials) {
+            MPB_REQUIRE(BN == N && nparts == 8 * grid, "fused statistics need a single column tile");
+            auto kern = gemm_tn_kernel<false, true>;
+            MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
+            kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmC, C, M, N, K, BN, N, stages, stat_partials);
+        } else {
+            auto kern = gemm_tn_kernel<false, false>;
+            MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
+            kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmC, C, M, N, K, BN, N, stages, nullptr);
+        }
     }
     return check_launch("gemm_tn_kernel");
 }

@@ -48,13 +48,20 @@ def pad64(c):
 GEMM_TIMELINE = None
 
 
-def _gemm_tn(lib, a_ptr, b_ptr, c_ptr, M, N, K, st):
-    """C[M,N] (bf16) = A[M,K] @ B[N,K]^T.  Algorithmic bytes: A and B read once, C written once, all bf16."""
+FUSE_STATS = os.environ.get("MPB_FUSE_STATS", "1") == "1"   # BatchNorm statistics in the GEMM epilogue (N <= 256)
+
+
+def _gemm_tn(lib, a_ptr, b_ptr, c_ptr, M, N, K, st, stats=None):
+    """C[M,N] (bf16) = A[M,K] @ B[N,K]^T.  Algorithmic bytes: A and B read once, C written once, all bf16.
+    stats = (partials pointer, nparts): also emit the per-column sum / sum-of-squares partials of C."""
     ev = None
     if GEMM_TIMELINE is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    check(lib.mpb_gemm_bf16_tn(a_ptr, b_ptr, c_ptr, M, N, K, 0, st), "mpb_gemm_bf16_tn")
+    if stats is not None:
+        check(lib.mpb_gemm_bf16_tn_stats(a_ptr, b_ptr, c_ptr, M, N, K, stats[0], stats[1], st), "mpb_gemm_bf16_tn_stats")
+    else:
+        check(lib.mpb_gemm_bf16_tn(a_ptr, b_ptr, c_ptr, M, N, K, 0, st), "mpb_gemm_bf16_tn")
     if ev is not None:
         ev[1].record()
         GEMM_TIMELINE.append(("gemm_tn_kernel", 2 * (M * K + N * K + M * N), 2 * M * N * K, ev[0], ev[1]))
@@ -149,7 +156,9 @@ class SharedMLPMax(torch.autograd.Function):
             z = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
             sc = torch.empty(4, cout_p, dtype=torch.float32, device=dev)      # rows: scale, shift, mean, rstd
             mom, eps = momentum_eps[l]
-            np_c = [lib.mpb_bn_stat_partials(r1 - r0, cout_p) for r0, r1 in chunks]
+            # statistics fused into the GEMM epilogue when the layer fits one column tile (N <= 256), else a separate pass
+            fuse = [lib.mpb_gemm_tn_stat_partials(r1 - r0, cout_p, cin_p) if (training and FUSE_STATS) else 0 for r0, r1 in chunks]
+            np_c = [f or lib.mpb_bn_stat_partials(r1 - r0, cout_p) for f, (r0, r1) in zip(fuse, chunks)]
             part = torch.empty(sum(np_c), 2, cout_p, dtype=torch.float32, device=dev) if training else None
             if l > 0:
                 a = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev)
@@ -160,10 +169,11 @@ class SharedMLPMax(torch.autograd.Function):
                     ps = stats[l - 1]
                     check(lib.mpb_bn_relu_bf16(_off(zs[l - 1], r0), ptr(ps[0]), ptr(ps[1]), r1 - r0, cin_p, _off(a, r0), st),
                           "mpb_bn_relu_bf16")
-                _gemm_tn(lib, _off(a, r0), ptr(w), _off(z, r0), r1 - r0, cout_p, cin_p, st)
+                pptr = _off(part.view(-1, 2 * cout_p), p0) if training else None
+                _gemm_tn(lib, _off(a, r0), ptr(w), _off(z, r0), r1 - r0, cout_p, cin_p, st, stats=(pptr, fuse[ci]) if fuse[ci] else None)
                 if training:
-                    check(lib.mpb_bn_colstats_bf16(_off(z, r0), r1 - r0, cout_p, _off(part.view(-1, 2 * cout_p), p0), np_c[ci], st),
-                          "mpb_bn_colstats_bf16")
+                    if not fuse[ci]:
+                        check(lib.mpb_bn_colstats_bf16(_off(z, r0), r1 - r0, cout_p, pptr, np_c[ci], st), "mpb_bn_colstats_bf16")
                     p0 += np_c[ci]
             if training:
                 check(lib.mpb_bn_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(bias), ptr(gamma), ptr(beta), ptr(rmean),
