@@ -105,8 +105,10 @@ def dist_setup(args):
 # --------------------------------------------------------------------------------------------------
 def reference_step_time(category, ref_batch, steps, warmup):
     from maskplanner_b200 import synthetic
+    from oracle import c_oracle
     from oracle import step_oracle as SO
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(os.cpu_count())          # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    c_oracle.set_threads(os.cpu_count())
     torch.manual_seed(0)
     cfg = synthetic.CATEGORIES[category]
     model = SO.Regressor(synthetic.out_vectors(cfg["n_pred_traj_points"]), n_stroke_masks=cfg["max_n_strokes"])
@@ -323,7 +325,7 @@ def run_ours(args, ws, rank, local):
                 "e2e": {"value": B * ws / e2e_step, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_step * 1e3},
                 "gpu_launches": launches, "roofline": roof, "kernels": ktab, "final_loss": float(lv)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and ws == 1:       # reported at N = 1 only
             args.ref_batch = args.ref_batch or 16
             dt = reference_step_time(args.category, args.ref_batch, 1, 1)
             line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",

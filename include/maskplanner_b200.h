@@ -179,12 +179,15 @@ MPB_API int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int C_
                                 float *scale, float *shift, float *mean, float *rstd, void *stream);
 MPB_API int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *shift, int64_t M,
                              int C, void *A, void *stream);
+/* zmax (optional, fp32 [G,C]): the pre-activation Z at the arg-max row, consumed by _bwd_stats (pooled). */
 MPB_API int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const float *shift, int64_t G,
-                                 int K, int C, float *out, int32_t *argmax, void *stream);
+                                 int K, int C, float *out, int32_t *argmax, float *zmax,
+                                 void *stream);
 /* Backward: exactly one of dA (dense upstream gradient, bf16 [M,C]) and dOut (pooled upstream gradient,
  * fp32 [M/K, C], with argmax and K) is non-NULL. */
-MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,
-                                  const void *Z, const float *scale, const float *shift,
+MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax,
+                                  const float *zmax, int K, const void *Z, const float *scale,
+                                  const float *shift,
                                   const float *mean, const float *rstd, int64_t M, int C,
                                   float *partials, int nparts, void *stream);
 MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,

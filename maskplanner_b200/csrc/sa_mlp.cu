@@ -214,7 +214,7 @@ bn_relu_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ sc
 // out[g, c] = max_k relu(scale*Z[g*K + k, c] + shift); arg[g, c] = first k attaining it (torch.max semantics).
 __global__ void __launch_bounds__(kEwThreads)
 bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
-                   int K, int C, float *__restrict__ out, int *__restrict__ arg)
+                   int K, int C, float *__restrict__ out, int *__restrict__ arg, float *__restrict__ zmax)
 {
     const RowWalk w(C);
     if (!w.active) return;
@@ -223,10 +223,10 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
     load8(scale + c0, sc);
     load8(shift + c0, sh);
     for (int64_t g = (int64_t)blockIdx.x * w.rpp + w.tr; g < G; g += (int64_t)gridDim.x * w.rpp) {
-        float best[8];
+        float best[8], bz[8];
         int bi[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0;
+        for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0, bz[i] = 0.f;
         const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
         for (int k = 0; k < K; k += kRowUnroll) {
             uint4 raw[kRowUnroll];
@@ -241,7 +241,7 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
-                        if (a > best[i]) best[i] = a, bi[i] = k + u;
+                        if (a > best[i]) best[i] = a, bi[i] = k + u, bz[i] = z[i];
                     }
                 }
         }
@@ -251,6 +251,11 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
         int4 *ap = reinterpret_cast<int4 *>(arg + g * C + c0);
         ap[0] = make_int4(bi[0], bi[1], bi[2], bi[3]);
         ap[1] = make_int4(bi[4], bi[5], bi[6], bi[7]);
+        if (zmax) {   // pre-activation at the arg-max row: lets the backward statistics skip a 2-byte gather per (g, c)
+            float4 *zp4 = reinterpret_cast<float4 *>(zmax + g * C + c0);
+            zp4[0] = make_float4(bz[0], bz[1], bz[2], bz[3]);
+            zp4[1] = make_float4(bz[4], bz[5], bz[6], bz[7]);
+        }
     }
 }
 
@@ -293,8 +298,9 @@ bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
 // Upstream gradient is the pooled one: only the arg-max row of each (group, channel) carries dOut.
 __global__ void __launch_bounds__(kEwThreads)
 bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, const __nv_bfloat16 *__restrict__ Z,
-                        const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
-                        const float *__restrict__ rstd, int64_t G, int K, int C, float *__restrict__ partials)
+                        const float *__restrict__ zmax, const float *__restrict__ scale, const float *__restrict__ shift,
+                        const float *__restrict__ mean, const float *__restrict__ rstd, int64_t G, int K, int C,
+                        float *__restrict__ partials)
 {
     column_sums(G, C, partials, [&](int64_t g0, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
         for (int u = 0; u < nr; ++u) {
@@ -302,7 +308,7 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = c0 + i;
-                const float z = __bfloat162float(Z[(g * K + arg[g * C + c]) * C + c]);
+                const float z = zmax ? zmax[g * C + c] : __bfloat162float(Z[(g * K + arg[g * C + c]) * C + c]);
                 const float dy = fmaf(z, scale[c], shift[c]) > 0.f ? dOut[g * C + c] : 0.f;
                 s0[i] += dy;
                 s1[i] = fmaf(dy, (z - mean[c]) * rstd[c], s1[i]);
@@ -485,18 +491,19 @@ extern "C" int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *
 }
 
 extern "C" int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const float *shift, int64_t G, int K, int C, float *out,
-                                    int32_t *argmax, void *stream)
+                                    int32_t *argmax, float *zmax, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
     MPB_REQUIRE(G >= 0 && K > 0 && Z && scale && shift && out && argmax, "bad argument");
     if (G == 0) return MPB_OK;
     bn_relu_max_kernel<<<row_blocks(G, C, 8), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
-                                                                                    argmax);
+                                                                                    argmax, zmax);
     return check_launch("bn_relu_max_kernel");
 }
 
-extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K, const void *Z, const float *scale,
+extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax, const float *zmax, int K, const void *Z,
+                                     const float *scale,
                                      const float *shift, const float *mean, const float *rstd, int64_t M, int C, float *partials,
                                      int nparts, void *stream)
 {
@@ -511,7 +518,7 @@ extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const in
                                                                                  shift, mean, rstd, M, C, partials);
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0 && nparts == stat_parts(M / K, C), "pooled: bad argmax/K/nparts");
-        bwd_stats_pooled_kernel<<<nparts, kEwThreads, 2 * C * sizeof(float), st>>>(dOut, argmax, (const __nv_bfloat16 *)Z, scale, shift, mean,
+        bwd_stats_pooled_kernel<<<nparts, kEwThreads, 2 * C * sizeof(float), st>>>(dOut, argmax, (const __nv_bfloat16 *)Z, zmax, scale, shift, mean,
                                                                                   rstd, M / K, K, C, partials);
     }
     return check_launch("bwd_stats kernel");

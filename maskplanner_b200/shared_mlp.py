@@ -195,11 +195,12 @@ class SharedMLPMax(torch.autograd.Function):
         cl_p = dims[-1][2]
         out = torch.empty(G, cl_p, dtype=torch.float32, device=dev)
         argmax = torch.empty(G, cl_p, dtype=torch.int32, device=dev)
+        zmax = torch.empty(G, cl_p, dtype=torch.float32, device=dev) if training else None
         sc = stats[-1]
-        check(lib.mpb_bn_relu_max_bf16(ptr(zs[-1]), ptr(sc[0]), ptr(sc[1]), G, K, cl_p, ptr(out), ptr(argmax), st),
+        check(lib.mpb_bn_relu_max_bf16(ptr(zs[-1]), ptr(sc[0]), ptr(sc[1]), G, K, cl_p, ptr(out), ptr(argmax), ptr(zmax), st),
               "mpb_bn_relu_max_bf16")
         ctx.K, ctx.L, ctx.dims, ctx.training, ctx.xyz_last, ctx.chunks = K, L, dims, training, xyz_last, chunks
-        ctx.save_for_backward(argmax, *acts, *zs, *stats, *wts, *[flat[6 * l + 2] for l in range(L)])
+        ctx.save_for_backward(argmax, *acts, *zs, *stats, *wts, *[flat[6 * l + 2] for l in range(L)], zmax)
         c_last = dims[-1][0]
         return out[:, :c_last] if c_last != out.shape[1] else out
 
@@ -214,6 +215,7 @@ class SharedMLPMax(torch.autograd.Function):
         argmax = saved[0]
         acts, zs = saved[1:1 + L], saved[1 + L:1 + 2 * L]
         stats, wts, gammas = saved[1 + 2 * L:1 + 3 * L], saved[1 + 3 * L:1 + 4 * L], saved[1 + 4 * L:1 + 5 * L]
+        zmax = saved[1 + 5 * L]
         M = acts[0].shape[0]
         G = M // K
         dev = d_out.device
@@ -236,7 +238,7 @@ class SharedMLPMax(torch.autograd.Function):
         sc = stats[L - 1]
         p0 = 0
         for ci, (r0, r1) in enumerate(chunks):
-            check(lib.mpb_bn_bwd_stats_bf16(None, _off(d_pool, r0 // K), _off(argmax, r0 // K), K, _off(zs[L - 1], r0), ptr(sc[0]),
+            check(lib.mpb_bn_bwd_stats_bf16(None, _off(d_pool, r0 // K), _off(argmax, r0 // K), _off(zmax, r0 // K), K, _off(zs[L - 1], r0), ptr(sc[0]),
                                             ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), r1 - r0, cl_p, _off(part, p0), np_c[ci], st),
                   "mpb_bn_bwd_stats_bf16")
             p0 += np_c[ci]
@@ -271,7 +273,7 @@ class SharedMLPMax(torch.autograd.Function):
                 if need_da:
                     _gemm_tn(lib, _off(dz, r0), ptr(wts[l]), _off(d_prev, r0), rows, cin_p, cout_p, st)
                 if l > 0:
-                    check(lib.mpb_bn_bwd_stats_bf16(_off(d_prev, r0), None, None, K, _off(zs[l - 1], r0), ptr(ps[0]), ptr(ps[1]),
+                    check(lib.mpb_bn_bwd_stats_bf16(_off(d_prev, r0), None, None, None, K, _off(zs[l - 1], r0), ptr(ps[0]), ptr(ps[1]),
                                                     ptr(ps[2]), ptr(ps[3]), rows, cin_p, _off(part_n, p0), np_n[ci], st),
                           "mpb_bn_bwd_stats_bf16")
                     p0 += np_n[ci]

@@ -194,3 +194,15 @@ ORC_API void orc_knn_group_f32(const float *xyz, const float *new_xyz, int B, in
 }
 
 ORC_API int orc_version(void) { return 1; }
+
+/* Thread count of the OpenMP loops above (torchrun exports OMP_NUM_THREADS=1; the timed CPU arm asks for all cores). */
+#ifdef _OPENMP
+#include <omp.h>
+ORC_API int orc_set_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+ORC_API int orc_set_threads(int n) { (void)n; return 1; }
+#endif

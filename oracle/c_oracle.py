@@ -30,6 +30,11 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads used by the C loops (returns the value in effect)."""
+    return int(lib().orc_set_threads(ctypes.c_int(int(n))))
+
+
 def _np(a, dtype):
     if hasattr(a, "detach"):
         a = a.detach().cpu().numpy()
