@@ -191,8 +191,8 @@ MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32
                                   const float *mean, const float *rstd, int64_t M, int C,
                                   float *partials, int nparts, void *stream);
 MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
-                                    const float *gamma, const float *rstd, float *dgamma,
-                                    float *dbeta, float *coef, void *stream);
+                                    const float *gamma, const float *mean, const float *rstd,
+                                    float *dgamma, float *dbeta, float *coef, void *stream);
 MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,
                                   const void *Z, const float *scale, const float *shift,
                                   const float *mean, const float *rstd, const float *coef,

@@ -16,6 +16,8 @@
 //   :82) -> __fmul_rn/__fadd_rn so ptxas cannot contract to FMA;  running distance starts at
 //   1e10 and is replaced only when dist < it (:76, :83-84);  argmax = lowest index among equal
 //   maxima (:85).  Distances are >= +0, so their bit patterns order like signed integers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpb {
@@ -23,8 +25,8 @@ namespace mpb {
 constexpr int kFpsMaxPPT = 8;
 constexpr int kFpsMaxThreads = 1024;
 
-template <int PPT>
-__global__ void __launch_bounds__(kFpsMaxThreads, 1)
+template <int PPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_resident_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sn, int64_t sc, int N,
                     const int64_t *__restrict__ seed, int npoint, int64_t *__restrict__ out)
 {
@@ -184,7 +186,15 @@ struct FpsPlan {
 static FpsPlan fps_plan(int N)
 {
     FpsPlan p;
-    if (N <= kFpsMaxPPT * kFpsMaxThreads) {
+    static const int forced = [] {   // tuning hook: MPB_FPS_THREADS=512 forces 512-thread CTAs (up to 12 points per thread)
+        const char *e = getenv("MPB_FPS_THREADS");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 512 && N <= 512 * 12) {
+        p.cluster = 1;
+        p.threads = 512;
+        p.ppt = (N + 511) / 512;
+    } else if (N <= kFpsMaxPPT * kFpsMaxThreads) {
         p.cluster = 1;
         int t = ((N + 3) / 4 + 127) / 128 * 128;  // aim for ~4 points per thread
         p.threads = t < 128 ? 128 : (t > kFpsMaxThreads ? kFpsMaxThreads : t);
@@ -203,11 +213,11 @@ static FpsPlan fps_plan(int N)
     return p;
 }
 
-template <int PPT>
+template <int PPT, int MAXT>
 static int launch_resident(const FpsPlan &p, const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                            const int64_t *seed, int npoint, int64_t *out, cudaStream_t st)
 {
-    auto kern = fps_resident_kernel<PPT>;
+    auto kern = fps_resident_kernel<PPT, MAXT>;
     const size_t smem = (size_t)3 * p.threads * PPT * sizeof(float);
     MPB_ENSURE_DYN_SMEM(kern, smem);
     static bool nonportable_ok = false;
@@ -260,7 +270,7 @@ extern "C" int mpb_fps_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc,
     switch (p.ppt) {
 #define MPB_CASE(P) \
     case P:         \
-        return launch_resident<P>(p, xyz, sb, sn, sc, B, N, seed_idx, npoint, out_idx, st);
+        return launch_resident<P, (P <= 8 ? 1024 : 512)>(p, xyz, sb, sn, sc, B, N, seed_idx, npoint, out_idx, st);
         MPB_CASE(1)
         MPB_CASE(2)
         MPB_CASE(3)
@@ -269,6 +279,10 @@ extern "C" int mpb_fps_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc,
         MPB_CASE(6)
         MPB_CASE(7)
         MPB_CASE(8)
+        MPB_CASE(9)
+        MPB_CASE(10)
+        MPB_CASE(11)
+        MPB_CASE(12)
 #undef MPB_CASE
     }
     set_error("mpb_fps_f32: internal plan error (ppt=%d)", p.ppt);

@@ -266,11 +266,10 @@ bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
                        int C, float *__restrict__ partials)
 {
     const int c00 = (threadIdx.x % (C >> 3)) * 8;
-    float sc[8], sh[8], mu[8], rs[8];
+    float sc[8], sh[8];
     load8(scale + c00, sc);
     load8(shift + c00, sh);
-    load8(mean + c00, mu);
-    load8(rstd + c00, rs);
+    (void)mean, (void)rstd;
     column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
         uint4 rz[kRowUnroll], rd[kRowUnroll];
 #pragma unroll
@@ -286,10 +285,10 @@ bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
                 unpack8(rz[u], z);
                 unpack8(rd[u], d);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 8; ++i) {   // raw moments sum dY, sum dY*z; the finalize kernel turns them into sum dY*zhat in fp64
                     const float dy = fmaf(z[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
                     s0[i] += dy;
-                    s1[i] = fmaf(dy, (z[i] - mu[i]) * rs[i], s1[i]);
+                    s1[i] = fmaf(dy, z[i], s1[i]);
                 }
             }
     });
@@ -311,16 +310,18 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
                 const float z = zmax ? zmax[g * C + c] : __bfloat162float(Z[(g * K + arg[g * C + c]) * C + c]);
                 const float dy = fmaf(z, scale[c], shift[c]) > 0.f ? dOut[g * C + c] : 0.f;
                 s0[i] += dy;
-                s1[i] = fmaf(dy, (z - mean[c]) * rstd[c], s1[i]);
+                s1[i] = fmaf(dy, z, s1[i]);
             }
         }
     });
 }
 
+// Partials hold the raw moments (sum dY, sum dY*z); sum dY*zhat = rstd*(sum dY*z - mean*sum dY), formed in fp64.
 // dgamma = sum dY*zhat, dbeta = sum dY; coef[0][c] = gamma*rstd, coef[1][c] = mean(dY), coef[2][c] = mean(dY*zhat)
 __global__ void __launch_bounds__(kFinThreads)
 bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M, const float *__restrict__ gamma,
-                    const float *__restrict__ rstd, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef)
+                    const float *__restrict__ mean, const float *__restrict__ rstd, float *__restrict__ dgamma,
+                    float *__restrict__ dbeta, float *__restrict__ coef)
 {
     int c;
     double s, q;
@@ -329,6 +330,7 @@ bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C
             coef[c] = coef[C + c] = coef[2 * C + c] = 0.f;
             return;
         }
+        q = (double)rstd[c] * (q - (double)mean[c] * s);
         if (dbeta) dbeta[c] = (float)s;
         if (dgamma) dgamma[c] = (float)q;
         coef[c] = (gamma ? gamma[c] : 1.f) * rstd[c];
@@ -525,13 +527,14 @@ extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const in
 }
 
 extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M, const float *gamma,
-                                       const float *rstd, float *dgamma, float *dbeta, float *coef, void *stream)
+                                       const float *mean, const float *rstd, float *dgamma, float *dbeta, float *coef,
+                                       void *stream)
 {
     using namespace mpb;
-    MPB_REQUIRE(partials && rstd && coef && C > 0 && nparts > 0 && M > 0, "bad argument");
+    MPB_REQUIRE(partials && mean && rstd && coef && C > 0 && nparts > 0 && M > 0, "bad argument");
     MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
-    bwd_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, rstd, dgamma,
-                                                                               dbeta, coef);
+    bwd_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, mean, rstd,
+                                                                               dgamma, dbeta, coef);
     return check_launch("bwd_finalize_kernel");
 }
 

@@ -250,8 +250,8 @@ class SharedMLPMax(torch.autograd.Function):
             coef = torch.empty(3, cout_p, dtype=torch.float32, device=dev)
             dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
             dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
-            check(lib.mpb_bn_bwd_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(gamma), ptr(sc[3]), ptr(dgamma), ptr(dbeta),
-                                              ptr(coef), st), "mpb_bn_bwd_finalize_f32")
+            check(lib.mpb_bn_bwd_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(gamma), ptr(sc[2]), ptr(sc[3]), ptr(dgamma),
+                                              ptr(dbeta), ptr(coef), st), "mpb_bn_bwd_finalize_f32")
             dz = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
             dw = torch.zeros(cout_p, cin_p, dtype=torch.float32, device=dev)
             need_da = l > 0 or ctx.needs_input_grad[0]
