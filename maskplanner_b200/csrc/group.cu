@@ -12,15 +12,23 @@
 
 namespace mpb {
 
+// Forward gathers: `lpr` (a power of two, <= 32) consecutive lanes share one output row -- the row's index
+// arithmetic is done once per lane, the lanes then stride over the row's columns, so both the gathered read and
+// the write are coalesced and no per-element 64-bit division is left.
 __global__ void index_points_kernel(const float *__restrict__ pts, int64_t sb, int64_t sn, int64_t sc, int N, int C,
-                                    const int64_t *__restrict__ idx, int64_t M, int64_t total, float *__restrict__ out)
+                                    const int64_t *__restrict__ idx, int64_t M, int64_t rows, int lpr_shift,
+                                    float *__restrict__ out)
 {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(e % C);
-        const int64_t row = e / C;  // b*M + m
+    const int lpr = 1 << lpr_shift;
+    const int sub = threadIdx.x & (lpr - 1);
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> lpr_shift;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift; row < rows; row += stride) {
         const int64_t b = row / M;
         const int64_t i = idx[row];
-        out[e] = (i >= 0 && i < N) ? pts[b * sb + i * sn + c * sc] : 0.f;
+        const bool ok = i >= 0 && i < N;
+        const float *src = pts + b * sb + (ok ? i : 0) * sn;
+        float *dst = out + row * C;
+        for (int c = sub; c < C; c += lpr) dst[c] = ok ? src[(int64_t)c * sc] : 0.f;
     }
 }
 
@@ -45,22 +53,29 @@ template <typename OutT>
 __global__ void group_points_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc,
                                     const float *__restrict__ feats, int64_t fsb, int64_t fsn, int64_t fsc,
                                     const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int S,
-                                    int K, int D, int ldo, int64_t total, OutT *__restrict__ out)
+                                    int K, int D, int ldo, int64_t rows, int lpr_shift, OutT *__restrict__ out)
 {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(e % ldo);
-        const int64_t row = e / ldo;   // (b*S + s)*K + k
-        const int64_t bs = row / K;    // b*S + s
+    const int lpr = 1 << lpr_shift;
+    const int sub = threadIdx.x & (lpr - 1);
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> lpr_shift;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift; row < rows; row += stride) {
+        const int64_t bs = row / K;    // b*S + s ; row = (b*S + s)*K + k
         const int64_t b = bs / S;
         const int64_t i = idx[row];
         const bool ok = i >= 0 && i < N;
-        float v = 0.f;
-        if (c < 3) {
-            if (ok) v = __fsub_rn(xyz[b * xsb + i * xsn + c * xsc], new_xyz[bs * 3 + c]);  // :134
-        } else if (c < 3 + D) {
-            if (ok) v = feats[b * fsb + i * fsn + (int64_t)(c - 3) * fsc];               // :137-138
+        const float *px = xyz + b * xsb + (ok ? i : 0) * xsn;
+        const float *pf = feats ? feats + b * fsb + (ok ? i : 0) * fsn : nullptr;
+        OutT *dst = out + row * ldo;
+        for (int c = sub; c < ldo; c += lpr) {
+            float v = 0.f;
+            if (ok) {
+                if (c < 3)
+                    v = __fsub_rn(px[c * xsc], new_xyz[bs * 3 + c]);      // :134
+                else if (c < 3 + D)
+                    v = pf[(int64_t)(c - 3) * fsc];                       // :137-138
+            }
+            store_as(dst + c, v);
         }
-        store_as(out + e, v);
     }
 }
 
@@ -87,6 +102,14 @@ __global__ void group_points_bwd_kernel(const InT *__restrict__ go, int ldo, con
     }
 }
 
+// smallest power of two >= min(width, 32), as a shift
+static inline int lanes_per_row_shift(int width)
+{
+    int s = 0;
+    while ((1 << s) < width && s < 5) ++s;
+    return s;
+}
+
 static inline unsigned grid_for(int64_t total, int threads)
 {
     int64_t blocks = (total + threads - 1) / threads;
@@ -104,7 +127,9 @@ extern "C" int mpb_index_points_f32(const float *points, int64_t sb, int64_t sn,
     const int64_t total = (int64_t)B * M * C;
     if (total == 0) return MPB_OK;
     MPB_REQUIRE(points && idx && out, "null pointer");
-    index_points_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(points, sb, sn, sc, N, C, idx, M, total, out);
+    const int shift = lanes_per_row_shift(C);
+    index_points_kernel<<<grid_for(((int64_t)B * M) << shift, 256), 256, 0, (cudaStream_t)stream>>>(points, sb, sn, sc, N, C, idx, M,
+                                                                                                  (int64_t)B * M, shift, out);
     return check_launch("index_points_kernel");
 }
 
@@ -131,8 +156,10 @@ extern "C" int mpb_group_points_f32(const float *xyz, int64_t xsb, int64_t xsn, 
     if (total == 0) return MPB_OK;
     MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
     MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
-    group_points_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc,
-                                                                               new_xyz, idx, N, S, K, D, ldo, total, out);
+    const int shift = lanes_per_row_shift(ldo);
+    const int64_t rows = (int64_t)B * S * K;
+    group_points_kernel<float><<<grid_for(rows << shift, 256), 256, 0, (cudaStream_t)stream>>>(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc,
+                                                                                             new_xyz, idx, N, S, K, D, ldo, rows, shift, out);
     return check_launch("group_points_kernel");
 }
 
