@@ -7,7 +7,8 @@
 // shared-memory tile (every thread reads the same target row => broadcast LDS.128, reused by the
 // R register-resident queries) and keeps a running (min, arg-min) per query.  Both chamfer
 // directions run in ONE launch (blockIdx.z), and either can be skipped.  HBM traffic is the
-// compulsory (4D+12)*N*(P1+P2) bytes; the kernel is bound by fp32 issue rate (2D+3 instr / pair).
+// compulsory (4D+12)*N*(P1+P2) bytes; the kernel is bound by the fma pipe: D packed fp32x2
+// instruction pairs (FADD2 + FFMA2) per TWO (query, target) pairs plus one FMNMX3.
 //
 // Arithmetic contract: d = sum_k (q_k - t_k)^2 accumulated with FMA over k = 0..D-1 in order
 // (what nvcc emits for pytorch3d's CUDA loop); strict '<' while scanning targets in index order
@@ -18,21 +19,70 @@
 namespace mpb {
 
 constexpr int kChThreads = 128;
+constexpr int kChChunkPairs = 4;  // index bookkeeping granularity: 4 target pairs = 8 targets
 
+// Shared-memory tile of NEGATED targets, two targets per row so that one 64-bit register pair holds
+// (-t[2p][d], -t[2p+1][d]): row p = { d0.lo d0.hi d1.lo d1.hi ... } padded to a float4 multiple.
 template <int D>
 struct ChTile {
-    static constexpr int DP = (D + 3) / 4 * 4;                 // padded row (float4 granules)
-    static constexpr int TILE = (4096 / DP) / 32 * 32;         // targets per tile (~16 KB)
+    static constexpr int ROW = (2 * D + 3) / 4 * 4;                                  // floats per target pair
+    static constexpr int PAIRS = (4096 / ROW) / kChChunkPairs * kChChunkPairs;       // ~16 KB tile
+    static constexpr int TILE = 2 * PAIRS;                                           // targets per tile
+    // Coordinates whose differences are taken with two scalar FADDs instead of one FADD2.  Measured on
+    // B200: every split other than 0 is slower (29.8 vs 27.8 ms at 64k x 64k x 32, D = 3), i.e. FADD shares
+    // the fma pipe's issue budget, so everything stays packed.
+    static constexpr int SCALAR_DIMS = 0;
 };
 
+// VW consecutive floats of a target row, negated (targets at infinity when the row does not exist).
+template <int VW>
+__device__ __forceinline__ void load_neg_row(const float *__restrict__ src, bool exists, bool vec_ok, float (&o)[VW])
+{
+    if (!exists) {
+#pragma unroll
+        for (int k = 0; k < VW; ++k) o[k] = INFINITY;
+    } else if (VW == 4 && vec_ok) {
+        const float4 v = *reinterpret_cast<const float4 *>(src);
+        o[0] = -v.x, o[1 % VW] = -v.y, o[2 % VW] = -v.z, o[3 % VW] = -v.w;
+    } else if (VW == 2 && vec_ok) {
+        const float2 v = *reinterpret_cast<const float2 *>(src);
+        o[0] = -v.x, o[1 % VW] = -v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < VW; ++k) o[k] = -src[k];
+    }
+}
+
+// One squared distance with the contract's rounding: df = q - t, acc = fma(df, df, acc), k ascending.
+template <int D>
+__device__ __forceinline__ float chamfer_dist_scalar(const float (&q)[D], const float *__restrict__ t)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float df = q[d] - t[d];
+        acc = __fmaf_rn(df, df, acc);
+    }
+    return acc;
+}
+
+// The pair loop runs on packed fp32x2 math (FADD2 / FFMA2: two targets per instruction, each lane
+// IEEE-identical to the scalar form above since q + (-t) == q - t) and tracks only the running
+// MINIMUM (one FMNMX per pair on the alu pipe instead of compare + two selects); the arg-min is kept
+// at chunk granularity ("the first chunk of 8 targets in which the minimum strictly dropped to its
+// final value") and resolved after the scan by recomputing that one chunk: the first target whose
+// distance equals the minimum, i.e. exactly what a strict '<' scan in index order selects.
 template <int D, int R>
 __global__ void __launch_bounds__(kChThreads)
 chamfer_nn_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
                   const int64_t *__restrict__ x_len, const int64_t *__restrict__ y_len, float *__restrict__ dist_x,
                   int64_t *__restrict__ idx_x, float *__restrict__ dist_y, int64_t *__restrict__ idx_y, int dir0)
 {
-    constexpr int DP = ChTile<D>::DP, TILE = ChTile<D>::TILE;
-    __shared__ __align__(16) float tile[TILE * DP];
+    constexpr int ROW = ChTile<D>::ROW, PAIRS = ChTile<D>::PAIRS, TILE = ChTile<D>::TILE;
+    constexpr int CH = kChChunkPairs;
+    constexpr int VW = (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1, G = D / VW;
+    constexpr int NS = ChTile<D>::SCALAR_DIMS;
+    __shared__ __align__(16) float tile[PAIRS * ROW];
     const int dir = dir0 + blockIdx.z;
     const int n = blockIdx.y;
     const float *Q = dir == 0 ? x : y;
@@ -47,59 +97,71 @@ chamfer_nn_kernel(const float *__restrict__ x, const float *__restrict__ y, int 
     lq = lq < 0 ? 0 : (lq > Pq ? Pq : lq);
     lt = lt < 0 ? 0 : (lt > Pt ? Pt : lt);
 
-    float q[R][D], best[R];
-    int bi[R];
+    float q[R][D], best[R], prev[R];
+    int bc[R];  // chunk (of 2*CH targets, counted from target 0) holding the arg-min
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int i = q0 + r * kChThreads + threadIdx.x;
-        best[r] = INFINITY;
-        bi[r] = 0;
+        best[r] = prev[r] = INFINITY;
+        bc[r] = 0;
         const float *qp = Q + ((int64_t)n * Pq + (i < Pq ? i : 0)) * D;
 #pragma unroll
         for (int d = 0; d < D; ++d) q[r][d] = qp[d];
     }
     const float *Tn = T + (int64_t)n * Pt * D;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(Tn) & (VW * 4 - 1)) == 0;  // row pitch D*4 keeps it
     if (q0 < lq) {
         for (int t0 = 0; t0 < (int)lt; t0 += TILE) {
             const int tn = min(TILE, (int)lt - t0);
+            const int nchunks = (tn + 2 * CH - 1) / (2 * CH);
             __syncthreads();
-            if (D == DP) {  // rows already float4-granular: straight coalesced copy
-                const float4 *src = reinterpret_cast<const float4 *>(Tn + (int64_t)t0 * D);
-                float4 *dst = reinterpret_cast<float4 *>(tile);
-                const bool al = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-                if (al) {
-                    for (int e = threadIdx.x; e < tn * (D / 4); e += kChThreads) dst[e] = src[e];
-                } else {
-                    for (int e = threadIdx.x; e < tn * D; e += kChThreads) tile[e] = Tn[(int64_t)t0 * D + e];
-                }
-            } else {
-                for (int e = threadIdx.x; e < tn * D; e += kChThreads) {
-                    const int row = e / D, col = e - row * D;
-                    tile[row * DP + col] = Tn[(int64_t)t0 * D + e];
-                }
+            // one (target pair, column group) per thread: VW columns of rows 2p and 2p+1, negated and
+            // interleaved; rows past the end become targets at infinity (distance +inf, never the minimum)
+            for (int e = threadIdx.x; e < nchunks * CH * G; e += kChThreads) {
+                const int p = e / G, g = e - p * G;
+                float a[VW], b[VW];
+                load_neg_row<VW>(Tn + ((int64_t)t0 + 2 * p) * D + g * VW, 2 * p < tn, vec_ok, a);
+                load_neg_row<VW>(Tn + ((int64_t)t0 + 2 * p + 1) * D + g * VW, 2 * p + 1 < tn, vec_ok, b);
+                float2 *dst = reinterpret_cast<float2 *>(tile + p * ROW + 2 * g * VW);
+#pragma unroll
+                for (int k = 0; k < VW; ++k) dst[k] = make_float2(a[k], b[k]);
             }
             __syncthreads();
-#pragma unroll 2
-            for (int j = 0; j < tn; ++j) {
-                float t[DP];
+            const int chunk0 = t0 / (2 * CH);
+            for (int c = 0; c < nchunks; ++c) {
 #pragma unroll
-                for (int v = 0; v < DP / 4; ++v) {
-                    const float4 f = reinterpret_cast<const float4 *>(tile + j * DP)[v];
-                    t[4 * v] = f.x, t[4 * v + 1] = f.y, t[4 * v + 2] = f.z, t[4 * v + 3] = f.w;
+                for (int p = 0; p < CH; ++p) {
+                    float2 t2[ROW / 2];
+                    const float4 *rowp = reinterpret_cast<const float4 *>(tile + (c * CH + p) * ROW);
+#pragma unroll
+                    for (int v = 0; v < ROW / 4; ++v) {
+                        const float4 f = rowp[v];
+                        t2[2 * v] = make_float2(f.x, f.y);
+                        t2[2 * v + 1] = make_float2(f.z, f.w);
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float2 acc;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            float2 df;
+                            if (d < D - NS) {
+                                df = __fadd2_rn(make_float2(q[r][d], q[r][d]), t2[d]);
+                            } else {
+                                df.x = __fadd_rn(q[r][d], t2[d].x);
+                                df.y = __fadd_rn(q[r][d], t2[d].y);
+                            }
+                            acc = d == 0 ? __fmul2_rn(df, df) : __ffma2_rn(df, df, acc);
+                        }
+                        best[r] = fminf(fminf(best[r], acc.x), acc.y);
+                    }
                 }
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const float df = q[r][d] - t[d];
-                        acc = __fmaf_rn(df, df, acc);
+                for (int r = 0; r < R; ++r)
+                    if (best[r] < prev[r]) {
+                        prev[r] = best[r];
+                        bc[r] = chunk0 + c;
                     }
-                    if (acc < best[r]) {
-                        best[r] = acc;
-                        bi[r] = t0 + j;
-                    }
-                }
             }
         }
     }
@@ -108,8 +170,15 @@ chamfer_nn_kernel(const float *__restrict__ x, const float *__restrict__ y, int 
         const int i = q0 + r * kChThreads + threadIdx.x;
         if (i < Pq) {
             const bool valid = i < lq && lt > 0;
+            int bi = 0;
+            if (valid && best[r] < INFINITY) {
+                const int js = bc[r] * (2 * CH), je = min(js + 2 * CH, (int)lt);
+                bi = js;
+                for (int j = je - 1; j >= js; --j)  // descending: the last hit kept is the lowest index
+                    if (chamfer_dist_scalar<D>(q[r], Tn + (int64_t)j * D) == best[r]) bi = j;
+            }
             od[(int64_t)n * Pq + i] = valid ? best[r] : 0.f;
-            oi[(int64_t)n * Pq + i] = valid ? bi[r] : 0;
+            oi[(int64_t)n * Pq + i] = valid ? bi : 0;
         }
     }
 }
