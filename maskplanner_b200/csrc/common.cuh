@@ -55,6 +55,17 @@ __device__ __forceinline__ int redux_max_s32(int v) { return __reduce_max_sync(0
 __device__ __forceinline__ int redux_min_s32(int v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ unsigned redux_min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
 
+// ---- packed fp32x2 arithmetic and contraction ----------------------------------------------------
+// ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry an explicit .rn
+// (seen in SASS with the intrinsics, with inline PTX, with fma(1, a, b) as the sum and with
+// -fmad=false alike).  Kernels with a bit-exact "every product and every sum individually rounded"
+// contract (FPS) therefore keep packed ops for differences and products only and add the products
+// with SCALAR __fadd_rn, which ptxas never contracts.
+__device__ __forceinline__ float2 add2_products_rn(float2 a, float2 b)
+{
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+
 // ---- thread-block-cluster primitives (raw PTX, no cooperative_groups dependency) --------------
 __device__ __forceinline__ unsigned cluster_ctarank()
 {

@@ -81,11 +81,27 @@ fps_resident_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sn, int64
         const int buf = s & 1;
         float best = -2.0f;
         int bi = 0x7fffffff;
+        // Packed fp32x2 update, two points per instruction: FADD2 differences (p + (-c) == p - c), FMUL2
+        // products, scalar FADD sums (common.cuh: ptxas would contract packed sums of products), so every
+        // lane carries the bits of the scalar form.  The odd point of an odd PPT goes scalar.
+        const float ncx = -cx, ncy = -cy, ncz = -cz;
+#pragma unroll
+        for (int j = 0; j + 1 < PPT; j += 2) {
+            const float2 dx = __fadd2_rn(make_float2(px[j], px[j + 1]), make_float2(ncx, ncx));
+            const float2 dy = __fadd2_rn(make_float2(py[j], py[j + 1]), make_float2(ncy, ncy));
+            const float2 dz = __fadd2_rn(make_float2(pz[j], pz[j + 1]), make_float2(ncz, ncz));
+            const float2 d = add2_products_rn(add2_products_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+            md[j] = fminf(d.x, md[j]);          // == (d < md) ? d : md  (d is never -0, NaN keeps md)
+            md[j + 1] = fminf(d.y, md[j + 1]);
+        }
+        if (PPT & 1) {
+            constexpr int j = PPT - 1;
+            const float dx = __fadd_rn(px[j], ncx), dy = __fadd_rn(py[j], ncy), dz = __fadd_rn(pz[j], ncz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            md[j] = fminf(d, md[j]);
+        }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
-            const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            md[j] = (d < md[j]) ? d : md[j];
             if (md[j] > best) {  // strict: the thread's points are visited in ascending index order
                 best = md[j];
                 bi = j * stride_j + first;
