@@ -136,6 +136,13 @@ MPB_API int mpb_knn_points_bwd_f32(const float *p1, const float *p2, int N, int 
                                    int K, const float *grad_dists, float *grad_p1, float *grad_p2,
                                    void *stream);
 
+/* Conv2d/Conv1d 1x1 weight (fp32 [cout, cin], models/pointnet2_utils.py:166-169) -> the two bf16 GEMM
+ * operands of the tensor-core path in ONE launch: Wp [cout_p, cin_p] (zero padded) and its transpose
+ * Wt [cin_p, cout_p].  xyz_last != 0: the three leading (centred xyz) input channels of the reference's
+ * concatenation order (:137) move behind the feature channels, matching mpb_group_points_bf16 rows. */
+MPB_API int mpb_pack_weight_bf16(const float *W, int cout, int cin, int cout_p, int cin_p, int xyz_last,
+                                 void *Wp, void *Wt, void *stream);
+
 /* ---- a7: PointNetSetAbstraction's shared MLP        models/pointnet2_utils.py:208-214 -------------
  * relu(bn(conv1x1(x))) per layer then max over the K neighbours.  The 1x1 conv over [B,C,K,S] is the
  * row-wise GEMM Z[M,Cout] = A[M,Cin] * W[Cout,Cin]^T (M = B*S*K); activations travel as bf16 [M,C]
@@ -190,9 +197,13 @@ MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32
                                   const float *shift,
                                   const float *mean, const float *rstd, int64_t M, int C,
                                   float *partials, int nparts, void *stream);
+/* clear / clear_count (optional, count a multiple of 4 floats, 16-byte aligned): a buffer this launch
+ * also zero-fills -- the fp32 accumulator of the mpb_gemm_bf16_wgrad call that follows, plus any
+ * exactly-zero gradients (conv bias under training-mode BatchNorm). */
 MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                     const float *gamma, const float *mean, const float *rstd,
-                                    float *dgamma, float *dbeta, float *coef, void *stream);
+                                    float *dgamma, float *dbeta, float *coef, float *clear,
+                                    int64_t clear_count, void *stream);
 MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,
                                   const void *Z, const float *scale, const float *shift,
                                   const float *mean, const float *rstd, const float *coef,

@@ -84,14 +84,15 @@ def _padded_weight(conv_weight, cout_p, cin_p, xyz_last):
     xyz_last: the rows come from mpb_group_points_bf16 (features first, the 3 centred coordinates last),
     so the reference's xyz-first input channels (:137) move to the end."""
     cout, cin = conv_weight.shape[0], conv_weight.shape[1]
-    w = torch.zeros(cout_p, cin_p, dtype=torch.bfloat16, device=conv_weight.device)
-    src = conv_weight.detach().reshape(cout, cin)
-    if xyz_last and cin > 3:
-        w[:cout, :cin - 3] = src[:, 3:]
-        w[:cout, cin - 3:cin] = src[:, :3]
-    else:
-        w[:cout, :cin] = src
-    return w, w.t().contiguous()
+    dev = conv_weight.device
+    w = torch.empty(cout_p, cin_p, dtype=torch.bfloat16, device=dev)
+    wt = torch.empty(cin_p, cout_p, dtype=torch.bfloat16, device=dev)
+    src = conv_weight.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    check(_cabi.load().mpb_pack_weight_bf16(ptr(src), cout, cin, cout_p, cin_p, 1 if xyz_last else 0, ptr(w), ptr(wt),
+                                            stream_ptr()), "mpb_pack_weight_bf16")
+    return w, wt
 
 
 def _unpermute_wgrad(dw, cout, cin, xyz_last):
@@ -250,10 +251,13 @@ class SharedMLPMax(torch.autograd.Function):
             coef = torch.empty(3, cout_p, dtype=torch.float32, device=dev)
             dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
             dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+            # weight-gradient accumulator + the (exactly zero) conv-bias gradient: one buffer, zero-filled by the finalize launch
+            nw = cout_p * cin_p
+            wbuf = torch.empty(nw + (cout + 3) // 4 * 4, dtype=torch.float32, device=dev)
+            dw, dbias = wbuf[:nw].view(cout_p, cin_p), wbuf[nw:nw + cout]
             check(lib.mpb_bn_bwd_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(gamma), ptr(sc[2]), ptr(sc[3]), ptr(dgamma),
-                                              ptr(dbeta), ptr(coef), st), "mpb_bn_bwd_finalize_f32")
+                                              ptr(dbeta), ptr(coef), ptr(wbuf), wbuf.numel(), st), "mpb_bn_bwd_finalize_f32")
             dz = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
-            dw = torch.zeros(cout_p, cin_p, dtype=torch.float32, device=dev)
             need_da = l > 0 or ctx.needs_input_grad[0]
             d_prev = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev) if need_da else None
             if l > 0:
@@ -278,7 +282,7 @@ class SharedMLPMax(torch.autograd.Function):
                           "mpb_bn_bwd_stats_bf16")
                     p0 += np_n[ci]
             grads[6 * l] = _unpermute_wgrad(dw, cout, cin, ctx.xyz_last and l == 0)
-            grads[6 * l + 1] = torch.zeros(cout, dtype=torch.float32, device=dev)      # exact: BN removes the conv bias
+            grads[6 * l + 1] = dbias                                                   # exact zeros: BN removes the conv bias
             grads[6 * l + 2] = dgamma
             grads[6 * l + 3] = dbeta
             d_a = d_prev
