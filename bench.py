@@ -138,7 +138,7 @@ def run_reference(args, ws, rank):
             "data": "synthetic", "config": workload_config(args, args.gpus, cpu=True),
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n, cpu=False):
@@ -330,7 +330,7 @@ def run_ours(args, ws, rank, local):
             dt = reference_step_time(args.category, args.ref_batch, 1, 1)
             line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "1 timed + 1 warm-up optimisation step of the oracle port at B=%d on the host cores" % args.ref_batch}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if ws > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -342,8 +342,23 @@ def run_ours(args, ws, rank, local):
             print("destroy_process_group: %s" % e, file=sys.stderr)
 
 
+def _claim_stdout():
+    """Reserve the process's stdout for the ONE JSON line: fd 1 is pointed at stderr for everything else
+    (NCCL's version banner, library chatter), and print() of the result goes to the saved descriptor."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
     args = parse()
+    _claim_stdout()
     ws, rank, local = dist_setup(args)
     if args.impl == "reference":
         run_reference(args, ws, rank)
