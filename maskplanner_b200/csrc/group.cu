@@ -184,20 +184,24 @@ extern "C" int mpb_group_points_bwd_f32(const float *grad_out, int ldo, const in
 // single 16-byte store per 8 outputs.
 namespace mpb {
 
+// IT = uint32_t whenever the element count fits (always, in practice): the per-item row / batch decomposition is three
+// integer divisions, and 64-bit ones (~100 instructions each) made the kernel instruction-bound at 1.2-1.6 TB/s.
+template <typename IT>
 __global__ void __launch_bounds__(256)
 group_rows_bf16_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *__restrict__ feats,
                        int64_t fsb, int64_t fsn, int64_t fsc, const float *__restrict__ new_xyz, const int64_t *__restrict__ idx,
                        int N, int S, int K, int D, int ldo, int64_t total_vec, int vec_ok, __nv_bfloat16 *__restrict__ out)
 {
-    const int nv = ldo >> 3;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = v / nv;
+    const IT nv = (IT)(ldo >> 3), total = (IT)total_vec, step = (IT)gridDim.x * blockDim.x;
+    for (IT v = (IT)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += step) {
+        const IT row = v / nv;
         const int c0 = (int)(v - row * nv) * 8;
         float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (c0 < D + 3) {
             const int64_t i = idx[row];
             if (i >= 0 && i < N) {
-                const int64_t bs = row / K, b = bs / S;
+                const IT bs = row / (IT)K;
+                const int64_t b = (int64_t)(bs / (IT)S);
                 if (vec_ok && c0 + 8 <= D) {
                     const float4 *src = reinterpret_cast<const float4 *>(feats + b * fsb + i * fsn + c0);
                     const float4 lo = src[0], hi = src[1];
@@ -224,18 +228,19 @@ group_rows_bf16_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, 
 
 // grad_feats[b, idx[row], c] += grad_rows[row, c] for c < D: one thread = one row x 4 channels, one 16-byte
 // vector reduction (RED.128) per 4 channels when D % 4 == 0.
+template <typename IT>
 __global__ void __launch_bounds__(256)
 group_rows_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ go, int ldo, const int64_t *__restrict__ idx, int N, int S, int K, int D,
                            int64_t total_vec, float *__restrict__ gfeats)
 {
-    const int nv = (D + 3) >> 2;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = v / nv;
+    const IT nv = (IT)((D + 3) >> 2), total = (IT)total_vec, step = (IT)gridDim.x * blockDim.x, sk = (IT)S * (IT)K;
+    for (IT v = (IT)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += step) {
+        const IT row = v / nv;
         const int c0 = (int)(v - row * nv) * 4;
         const int64_t i = idx[row];
         if (i < 0 || i >= N) continue;
-        const int64_t b = row / ((int64_t)S * K);
-        const uint2 raw = *reinterpret_cast<const uint2 *>(go + row * ldo + c0);
+        const int64_t b = (int64_t)(row / sk);
+        const uint2 raw = *reinterpret_cast<const uint2 *>(go + (int64_t)row * ldo + c0);
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.x));
         const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.y));
         float *dst = gfeats + (b * N + i) * D + c0;
@@ -262,8 +267,13 @@ extern "C" int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn,
     MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
     MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
     const int vec_ok = D >= 8 && fsc == 1 && (fsb % 4 == 0) && (fsn % 4 == 0) && (((uintptr_t)feats & 15) == 0);
-    group_rows_bf16_kernel<<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
-        xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out);
+    // 32-bit item arithmetic needs total + one grid stride to stay below 2^32
+    if (total_vec < (int64_t)3 << 30)
+        group_rows_bf16_kernel<uint32_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+            xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out);
+    else
+        group_rows_bf16_kernel<int64_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+            xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out);
     return check_launch("group_rows_bf16_kernel");
 }
 
@@ -277,7 +287,11 @@ extern "C" int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const in
     if (total_vec == 0) return MPB_OK;
     MPB_REQUIRE(grad_out && idx && grad_feats, "null pointer");
     MPB_REQUIRE(((uintptr_t)grad_feats & 15) == 0, "grad_feats must be 16-byte aligned");
-    group_rows_bwd_bf16_kernel<<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)grad_out, ldo, idx, N, S,
-                                                                                          K, D, total_vec, grad_feats);
+    if (total_vec < (int64_t)3 << 30)
+        group_rows_bwd_bf16_kernel<uint32_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total_vec, grad_feats);
+    else
+        group_rows_bwd_bf16_kernel<int64_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total_vec, grad_feats);
     return check_launch("group_rows_bwd_bf16_kernel");
 }

@@ -50,6 +50,10 @@ __device__ __forceinline__ void load8(const float *__restrict__ p, float (&f)[8]
 
 constexpr int kEwThreads = 256;
 constexpr int kRowUnroll = 4;
+// Grids are ONE wave of resident CTAs (each streams a contiguous slab of rows): the statistics kernels are
+// compiled for 4 CTAs/SM (<= 64 registers) and launched 4 per SM; the elementwise kernels ask the occupancy
+// calculator.  (Before: 8 CTAs per SM requested with 3 resident => 2.67 waves, an 11 % tail.)
+constexpr int kStatCtasPerSm = 4;
 
 // Row walker: thread (tr, tc) of a CTA handles channel group tc (channels 8*tc .. 8*tc+7) of rows
 // blockIdx.x*rpp + tr, + gridDim.x*rpp, ...; `body(r0, nr, stride)` is called with up to kRowUnroll rows.
@@ -107,7 +111,7 @@ __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict_
     for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) partials[(size_t)blockIdx.x * 2 * C + i] = sm_acc[i];
 }
 
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
 colstats_kernel(const __nv_bfloat16 *__restrict__ Z, int64_t M, int C, float *__restrict__ partials)
 {
     column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
@@ -280,7 +284,7 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
 bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale,
                        const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd, int64_t M,
                        int C, float *__restrict__ partials)
@@ -315,7 +319,7 @@ bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
 }
 
 // Upstream gradient is the pooled one: only the arg-max row of each (group, channel) carries dOut.
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
 bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, const __nv_bfloat16 *__restrict__ Z,
                         const float *__restrict__ zmax, const float *__restrict__ scale, const float *__restrict__ shift,
                         const float *__restrict__ mean, const float *__restrict__ rstd, int64_t G, int K, int C,
@@ -470,7 +474,19 @@ static inline int row_blocks(int64_t rows, int C, int per_sm)
     const int cap = per_sm * sm_count();
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
-static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, 8); }
+static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, kStatCtasPerSm); }
+
+// Resident CTAs per SM of an elementwise kernel (cached per call site; a host-side query, legal during graph capture).
+#define MPB_RESIDENT_PER_SM(kernel)                                                       \
+    ([&]() -> int {                                                                       \
+        static int n_ = 0;                                                                \
+        if (!n_) {                                                                        \
+            int q_ = 0;                                                                   \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q_, kernel, kEwThreads, 0) != cudaSuccess) q_ = 1; \
+            n_ = q_ < 1 ? 1 : q_;                                                         \
+        }                                                                                 \
+        return n_;                                                                        \
+    }())
 
 }  // namespace mpb
 
@@ -545,7 +561,7 @@ extern "C" int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *
     MPB_CHECK_C(C);
     MPB_REQUIRE(M >= 0 && Z && scale && shift && A, "bad argument");
     if (M == 0) return MPB_OK;
-    bn_relu_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, 8), kEwThreads, 0, (cudaStream_t)stream>>>(
+    bn_relu_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, MPB_RESIDENT_PER_SM(bn_relu_kernel)), kEwThreads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16 *)Z, scale, shift, M, C, (__nv_bfloat16 *)A);
     return check_launch("bn_relu_kernel");
 }
@@ -557,7 +573,7 @@ extern "C" int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const flo
     MPB_CHECK_C(C);
     MPB_REQUIRE(G >= 0 && K > 0 && Z && scale && shift && out && argmax, "bad argument");
     if (G == 0) return MPB_OK;
-    bn_relu_max_kernel<<<row_blocks(G, C, 8), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
+    bn_relu_max_kernel<<<row_blocks(G, C, MPB_RESIDENT_PER_SM(bn_relu_max_kernel)), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
                                                                                     argmax, zmax);
     return check_launch("bn_relu_max_kernel");
 }
@@ -609,11 +625,11 @@ extern "C" int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const in
     MPB_REQUIRE((dA != nullptr) != (dOut != nullptr), "exactly one of dA (dense) / dOut (pooled) must be given");
     cudaStream_t st = (cudaStream_t)stream;
     if (dA) {
-        bwd_apply_dense_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, 8), kEwThreads, 0, st>>>(
+        bwd_apply_dense_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, MPB_RESIDENT_PER_SM(bwd_apply_dense_kernel)), kEwThreads, 0, st>>>(
             (const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale, shift, mean, rstd, coef, M, C, (__nv_bfloat16 *)dZ);
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0, "pooled: bad argmax/K");
-        bwd_apply_pooled_kernel<<<row_blocks(M / K, C, 8), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift, mean,
+        bwd_apply_pooled_kernel<<<row_blocks(M / K, C, MPB_RESIDENT_PER_SM(bwd_apply_pooled_kernel)), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift, mean,
                                                                                rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
     }
     return check_launch("bwd_apply kernel");
