@@ -283,6 +283,83 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
     }
 }
 
+// Few groups, many rows per group (SA3: G = batch size, K = 128): one 1024-thread CTA per group, the K rows are
+// interleaved over 1024/(C/8) segments and the per-segment (max, arg, z) triples meet in shared memory.
+constexpr int kWideThreads = 1024;
+__global__ void __launch_bounds__(kWideThreads)
+bn_relu_max_wide_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
+                        int K, int C, float *__restrict__ out, int *__restrict__ arg, float *__restrict__ zmax)
+{
+    extern __shared__ float sm_wide[];           // [3][segments][C]: best, arg (as int bits), z
+    const int cg = C >> 3, nseg = kWideThreads / cg;
+    const int seg = threadIdx.x / cg, tc = threadIdx.x - seg * cg;
+    const bool active = seg < nseg;
+    const int c0 = tc * 8;
+    float *s_best = sm_wide, *s_z = sm_wide + 2 * nseg * C;
+    int *s_arg = reinterpret_cast<int *>(sm_wide + nseg * C);
+    float sc[8], sh[8];
+    if (active) {
+        load8(scale + c0, sc);
+        load8(shift + c0, sh);
+    }
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
+        float best[8], bz[8];
+        int bi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0, bz[i] = 0.f;
+        if (active) {
+            const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
+            for (int k = seg; k < K; k += kRowUnroll * nseg) {
+                uint4 raw[kRowUnroll];
+#pragma unroll
+                for (int u = 0; u < kRowUnroll; ++u)
+                    if (k + u * nseg < K) raw[u] = ld16(zp + (int64_t)(k + u * nseg) * C);
+#pragma unroll
+                for (int u = 0; u < kRowUnroll; ++u)
+                    if (k + u * nseg < K) {
+                        float z[8];
+                        unpack8(raw[u], z);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
+                            if (a > best[i]) best[i] = a, bi[i] = k + u * nseg, bz[i] = z[i];
+                        }
+                    }
+            }
+            if (seg > 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s_best[seg * C + c0 + i] = best[i];
+                    s_arg[seg * C + c0 + i] = bi[i];
+                    s_z[seg * C + c0 + i] = bz[i];
+                }
+            }
+        }
+        __syncthreads();
+        if (active && seg == 0) {
+            for (int s2 = 1; s2 < nseg; ++s2)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a = s_best[s2 * C + c0 + i];
+                    const int k2 = s_arg[s2 * C + c0 + i];
+                    if (a > best[i] || (a == best[i] && k2 < bi[i])) best[i] = a, bi[i] = k2, bz[i] = s_z[s2 * C + c0 + i];  // first k wins ties
+                }
+            float4 *op = reinterpret_cast<float4 *>(out + g * C + c0);
+            op[0] = make_float4(best[0], best[1], best[2], best[3]);
+            op[1] = make_float4(best[4], best[5], best[6], best[7]);
+            int4 *ap = reinterpret_cast<int4 *>(arg + g * C + c0);
+            ap[0] = make_int4(bi[0], bi[1], bi[2], bi[3]);
+            ap[1] = make_int4(bi[4], bi[5], bi[6], bi[7]);
+            if (zmax) {
+                float4 *zp4 = reinterpret_cast<float4 *>(zmax + g * C + c0);
+                zp4[0] = make_float4(bz[0], bz[1], bz[2], bz[3]);
+                zp4[1] = make_float4(bz[4], bz[5], bz[6], bz[7]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- backward --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
 bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale,
@@ -436,6 +513,9 @@ bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
     const int c0 = w.tc * 8;
     ApplyConst k;
     k.load(scale, shift, mean, rstd, coef, C, c0);
+    // few groups (SA3: G = batch size): gridDim.y splits the K rows of a group so the launch still fills the machine
+    const int kseg = ((K + (int)gridDim.y - 1) / (int)gridDim.y + kRowUnroll - 1) / kRowUnroll * kRowUnroll;
+    const int kb = (int)blockIdx.y * kseg, ke = min(K, kb + kseg);
     for (int64_t g = (int64_t)blockIdx.x * w.rpp + w.tr; g < G; g += (int64_t)gridDim.x * w.rpp) {
         float go[8];
         int am[8];
@@ -446,14 +526,14 @@ bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
         }
         const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
         __nv_bfloat16 *dp = dZ + (g * K) * C + c0;
-        for (int kk = 0; kk < K; kk += kRowUnroll) {
+        for (int kk = kb; kk < ke; kk += kRowUnroll) {
             uint4 raw[kRowUnroll];
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u)
-                if (kk + u < K) raw[u] = ld16(zp + (int64_t)(kk + u) * C);
+                if (kk + u < ke) raw[u] = ld16(zp + (int64_t)(kk + u) * C);
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u)
-                if (kk + u < K) {
+                if (kk + u < ke) {
                     float z[8], d[8];
                     unpack8(raw[u], z);
 #pragma unroll
@@ -573,6 +653,14 @@ extern "C" int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const flo
     MPB_CHECK_C(C);
     MPB_REQUIRE(G >= 0 && K > 0 && Z && scale && shift && out && argmax, "bad argument");
     if (G == 0) return MPB_OK;
+    const int nseg = kWideThreads / (C >> 3);
+    if (G <= 2 * sm_count() && nseg >= 2 && K >= 4 * nseg) {
+        const size_t smem = (size_t)3 * nseg * C * sizeof(float);
+        MPB_ENSURE_DYN_SMEM(bn_relu_max_wide_kernel, smem);
+        bn_relu_max_wide_kernel<<<(unsigned)G, kWideThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
+                                                                                          argmax, zmax);
+        return check_launch("bn_relu_max_wide_kernel");
+    }
     bn_relu_max_kernel<<<row_blocks(G, C, MPB_RESIDENT_PER_SM(bn_relu_max_kernel)), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
                                                                                     argmax, zmax);
     return check_launch("bn_relu_max_kernel");
@@ -629,8 +717,12 @@ extern "C" int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const in
             (const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale, shift, mean, rstd, coef, M, C, (__nv_bfloat16 *)dZ);
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0, "pooled: bad argmax/K");
-        bwd_apply_pooled_kernel<<<row_blocks(M / K, C, MPB_RESIDENT_PER_SM(bwd_apply_pooled_kernel)), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift, mean,
-                                                                               rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
+        const int occ = MPB_RESIDENT_PER_SM(bwd_apply_pooled_kernel);
+        const int bx = row_blocks(M / K, C, occ), cap = occ * sm_count();
+        int ks = (cap + bx - 1) / bx;                       // segments needed to fill one wave ...
+        ks = ks > K / 8 ? K / 8 : ks;                       // ... of at least 8 rows each
+        bwd_apply_pooled_kernel<<<dim3(bx, ks < 1 ? 1 : ks), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift,
+                                                                                  mean, rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
     }
     return check_launch("bwd_apply kernel");
 }
