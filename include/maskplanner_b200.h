@@ -209,6 +209,27 @@ MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32
                                   const float *mean, const float *rstd, const float *coef,
                                   int64_t M, int C, void *dZ, void *stream);
 
+/* Narrow first layer (3 + D <= 8 input channels: SA1 with xyz-only or xyz+normal points, reference :133-138
+ * followed by the first conv of :210-212).  The grouped row [feats(D) | centred xyz(3)] is gathered on the fly
+ * instead of being written as a 64-column GEMM operand:
+ *   forward   Z[M, C] (bf16, M = B*S*K) = bf16(row) . W^T with W = mpb_pack_weight_bf16's Wp (bf16 [C, ldw],
+ *             xyz_last order), fp32 accumulation, plus the BatchNorm statistic partials of the stored values
+ *             (nparts = mpb_bn_stat_partials(M, C), same format as mpb_bn_colstats_bf16);
+ *   backward  dZ as mpb_bn_bwd_apply_bf16 (dense) would form it, reduced on the spot into
+ *             dW[C, ldw] (fp32, pre-zeroed, += dZ^T . row); no dZ tensor, no gradient to xyz / feats. */
+MPB_API int mpb_sa_first_layer_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                                    const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                                    const float *new_xyz, const int64_t *idx, int B, int N, int S, int K,
+                                    int D, const void *W, int ldw, int C, void *Z, float *partials,
+                                    int nparts, void *stream);
+MPB_API int mpb_sa_first_layer_bwd_bf16(const void *dA, const void *Z, const float *scale,
+                                        const float *shift, const float *mean, const float *rstd,
+                                        const float *coef, const float *xyz, int64_t xsb, int64_t xsn,
+                                        int64_t xsc, const float *feats, int64_t fsb, int64_t fsn,
+                                        int64_t fsc, const float *new_xyz, const int64_t *idx, int B,
+                                        int N, int S, int K, int D, int C, float *dW, int ldw,
+                                        void *stream);
+
 /* `padded=True` length scan                             pytorch3d_chamfer.py:138-149 ----------
  * first[n] = first j with y[n,j,0] == sentinel, else P2; *any_flag (int32, caller zero-fills) is
  * set to 1 if any sample is padded.  No host synchronisation (the reference does 2N of them). */

@@ -52,6 +52,9 @@ SIGNATURES = {
     "mpb_bn_bwd_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "mpb_pack_weight_bf16": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "mpb_bn_bwd_apply_bf16": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "mpb_sa_first_layer_bf16": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P]),
+    "mpb_sa_first_layer_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I,
+                                        _P, _I, _P]),
     "mpb_lap_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }
 

@@ -87,28 +87,29 @@ __device__ __forceinline__ int64_t slab_end(int64_t M, int rpp)
 template <class RowFn>
 __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict__ partials, RowFn fn)
 {
-    extern __shared__ float sm_acc[];  // [2][C]
+    extern __shared__ float sm_acc[];  // [rpp][2][C]: one slot per thread, combined in a FIXED order (bitwise reproducible)
     const RowWalk w(C);
-    for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) sm_acc[i] = 0.f;
-    __syncthreads();
-    if (w.active) {
-        float s0[8], s1[8];
+    float s0[8], s1[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+    for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+    if (w.active) {
         // each CTA streams one contiguous slab of rows (consecutive 16-byte x cg x rpp blocks: DRAM-page friendly)
         const int64_t r_end = slab_end(M, w.rpp);
         const int64_t stride = w.rpp;
         int64_t r = slab_begin(M, w.rpp) + w.tr;
         for (; r + (kRowUnroll - 1) * stride < r_end; r += kRowUnroll * stride) fn(r, stride, kRowUnroll, w.tc * 8, s0, s1);
         for (; r < r_end; r += stride) fn(r, stride, 1, w.tc * 8, s0, s1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            atomicAdd(&sm_acc[w.tc * 8 + i], s0[i]);
-            atomicAdd(&sm_acc[C + w.tc * 8 + i], s1[i]);
-        }
+        float4 *d0 = reinterpret_cast<float4 *>(sm_acc + (size_t)w.tr * 2 * C + w.tc * 8);
+        float4 *d1 = reinterpret_cast<float4 *>(sm_acc + (size_t)w.tr * 2 * C + C + w.tc * 8);
+        d0[0] = make_float4(s0[0], s0[1], s0[2], s0[3]), d0[1] = make_float4(s0[4], s0[5], s0[6], s0[7]);
+        d1[0] = make_float4(s1[0], s1[1], s1[2], s1[3]), d1[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) partials[(size_t)blockIdx.x * 2 * C + i] = sm_acc[i];
+    for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) {
+        float t = 0.f;
+        for (int tr = 0; tr < w.rpp; ++tr) t += sm_acc[(size_t)tr * 2 * C + i];
+        partials[(size_t)blockIdx.x * 2 * C + i] = t;
+    }
 }
 
 __global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
@@ -547,6 +548,237 @@ bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
     }
 }
 
+// ---- narrow first layer (SA1: 3 or 6 input channels) ------------------------------------------------
+// When the grouped row is only [feats(D) | centred xyz(3)] with 3 + D <= 8, padding it to a 64-column bf16 GEMM
+// operand costs 128 B/row of HBM three times (write, GEMM read, weight-gradient read) for 6-16 real bytes.  These
+// two kernels never materialise it: the forward gathers the row on the fly (same values, same bf16 rounding as
+// group_rows_bf16_kernel), forms Z = row . W^T on CUDA cores (fp32 FMAs over <= 8 terms; bf16 operands, like the
+// tensor-core path) and emits the BatchNorm statistic partials; the backward recomputes the row, forms dZ exactly
+// like bwd_apply_dense_kernel and reduces dW = dZ^T . row directly (no dZ tensor, no weight-gradient GEMM).
+struct NarrowRows {   // element strides are validated to fit 31 bits on the host: offsets are single IMAD.WIDEs
+    const float *xyz;
+    int32_t xsb, xsn, xsc;
+    const float *feats;
+    int32_t fsb, fsn, fsc;
+    const float *new_xyz;
+    const int64_t *idx;
+    int N, S, K, D;
+};
+
+template <int CIN>
+__device__ __forceinline__ void gather_narrow_row(const NarrowRows &g, uint32_t row, float (&a)[CIN])
+{
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) a[k] = 0.f;
+    const int64_t i = g.idx[row];
+    if (i < 0 || i >= g.N) return;   // empty-ball sentinel (index N): an all-zero row, as in group_rows_bf16_kernel
+    const uint32_t bs = row / (uint32_t)g.K;
+    const int64_t b = bs / (uint32_t)g.S;
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+        float v = 0.f;
+        if (k < g.D)
+            v = g.feats[b * g.fsb + i * g.fsn + k * g.fsc];
+        else if (k < g.D + 3)
+            v = __fsub_rn(g.xyz[b * g.xsb + i * g.xsn + (k - g.D) * g.xsc], g.new_xyz[(int64_t)bs * 3 + (k - g.D)]);
+        a[k] = __bfloat162float(__float2bfloat16_rn(v));
+    }
+}
+
+// The rows one thread visits form an arithmetic progression (r, r + stride, ...), so the decomposition
+// row = (b*S + s)*K + k is carried along instead of being divided out per row (integer division goes through the
+// XU pipe: the first version of these kernels stalled 45 % of its cycles on it).
+struct RowCursor {
+    uint32_t bs, k, b, s;
+    __device__ __forceinline__ void init(const NarrowRows &g, uint32_t row)
+    {
+        bs = row / (uint32_t)g.K, k = row - bs * (uint32_t)g.K;
+        b = bs / (uint32_t)g.S, s = bs - b * (uint32_t)g.S;
+    }
+    __device__ __forceinline__ void advance(const NarrowRows &g, uint32_t step)
+    {
+        k += step;
+        while (k >= (uint32_t)g.K) {
+            k -= (uint32_t)g.K, ++bs;
+            if (++s == (uint32_t)g.S) s = 0, ++b;
+        }
+    }
+};
+
+// The C/8 threads that share a row are adjacent lanes (C/8 = 8, 16 or 32): lane j < 3 + D of the group loads channel j of
+// the grouped row, the group exchanges the values by shuffle.  Groups of one warp may sit in different loop
+// iterations, hence the group-local mask.
+// The gather is split into phases so that the loads of the kRowUnroll rows in flight are independent of each other
+// (index loads, then coordinate loads, then the exchange): one dependent chain per row made the first version
+// latency-bound at 2 CTAs/SM.
+__device__ __forceinline__ float narrow_component(const NarrowRows &g, int64_t i, uint32_t b, uint32_t bs, int sub)
+{
+    float v = 0.f;
+    if (sub < g.D + 3 && i >= 0 && i < g.N) {
+        const int32_t i32 = (int32_t)i;
+        if (sub < g.D)
+            v = g.feats[(int64_t)(int32_t)b * g.fsb + (int64_t)i32 * g.fsn + sub * g.fsc];
+        else
+            v = __fsub_rn(g.xyz[(int64_t)(int32_t)b * g.xsb + (int64_t)i32 * g.xsn + (sub - g.D) * g.xsc], g.new_xyz[bs * 3u + (uint32_t)(sub - g.D)]);
+        v = __bfloat162float(__float2bfloat16_rn(v));
+    }
+    return v;
+}
+template <int CIN>
+__device__ __forceinline__ void narrow_exchange(float v, unsigned gmask, int gbase, float (&a)[CIN])
+{
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) a[k] = __shfl_sync(gmask, v, gbase + k);
+}
+
+// SHARE: C/8 divides the warp, the cooperative gather above applies; otherwise every thread gathers for itself.
+template <int CIN, bool SHARE>
+__global__ void __launch_bounds__(kEwThreads)
+narrow_first_layer_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ W, int ldw, int64_t M, int C, __nv_bfloat16 *__restrict__ Z,
+                          float *__restrict__ partials)
+{
+    const int cg = C >> 3;
+    const int c00 = (threadIdx.x % cg) * 8;
+    const int lane = threadIdx.x & 31, sub = lane % cg, gbase = lane - sub;
+    const unsigned gmask = cg >= 32 ? 0xffffffffu : (((1u << cg) - 1u) << gbase);
+    float2 w2[4][CIN];   // channel pairs (c00 + 2j, c00 + 2j + 1) x input channel
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < CIN; ++k)
+            w2[j][k] = make_float2(__bfloat162float(W[(size_t)(c00 + 2 * j) * ldw + k]), __bfloat162float(W[(size_t)(c00 + 2 * j + 1) * ldw + k]));
+    RowCursor cur;
+    bool started = false;
+    column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
+        if (SHARE && !started) cur.init(g, (uint32_t)r), started = true;
+        int64_t ii[kRowUnroll];
+        uint32_t cb[kRowUnroll], cbs[kRowUnroll];
+        float comp[kRowUnroll];
+        if (SHARE) {
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (u < nr) {
+                    ii[u] = g.idx[r + u * stride];
+                    cb[u] = cur.b, cbs[u] = cur.bs;
+                    cur.advance(g, (uint32_t)stride);
+                }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (u < nr) comp[u] = narrow_component(g, ii[u], cb[u], cbs[u], sub);
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u)
+            if (u < nr) {
+                const int64_t row = r + u * stride;
+                float a[CIN];
+                if (SHARE)
+                    narrow_exchange<CIN>(comp[u], gmask, gbase, a);
+                else
+                    gather_narrow_row<CIN>(g, (uint32_t)row, a);
+                uint4 pk;
+                __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 acc = __fmul2_rn(make_float2(a[0], a[0]), w2[j][0]);
+#pragma unroll
+                    for (int k = 1; k < CIN; ++k) acc = __ffma2_rn(make_float2(a[k], a[k]), w2[j][k], acc);
+                    pp[j] = __floats2bfloat162_rn(acc.x, acc.y);
+                }
+                *reinterpret_cast<uint4 *>(Z + row * C + c0) = pk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {   // statistics of the STORED (bf16) values, like the fused GEMM epilogue
+                    const float2 z = __bfloat1622float2(pp[j]);
+                    s0[2 * j] += z.x, s0[2 * j + 1] += z.y;
+                    s1[2 * j] = fmaf(z.x, z.x, s1[2 * j]), s1[2 * j + 1] = fmaf(z.y, z.y, s1[2 * j + 1]);
+                }
+            }
+    });
+}
+
+constexpr int kNarrowBwdUnroll = 2;   // 4 rows in flight spill at 128 registers (2 CTAs/SM)
+template <int CIN, bool SHARE>
+__global__ void __launch_bounds__(kEwThreads, 2)
+narrow_first_layer_bwd_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z,
+                              const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                              const float *__restrict__ rstd, const float *__restrict__ coef, int64_t M, int C, float *__restrict__ dW,
+                              int ldw)
+{
+    extern __shared__ float sm_dw[];  // [C][CIN]
+    for (int i = threadIdx.x; i < C * CIN; i += kEwThreads) sm_dw[i] = 0.f;
+    __syncthreads();
+    const RowWalk wk(C);
+    if (wk.active) {
+        const int c0 = wk.tc * 8;
+        const int lane = threadIdx.x & 31, sub = lane % wk.cg, gbase = lane - sub;
+        const unsigned gmask = wk.cg >= 32 ? 0xffffffffu : (((1u << wk.cg) - 1u) << gbase);
+        ApplyConst k;
+        k.load(scale, shift, mean, rstd, coef, C, c0);
+        float2 acc[4][CIN];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < CIN; ++q) acc[j][q] = make_float2(0.f, 0.f);
+        const int64_t stride = wk.rpp, r_end = slab_end(M, wk.rpp);
+        int64_t r = slab_begin(M, wk.rpp) + wk.tr;
+        RowCursor cur;
+        if (SHARE && r < r_end) cur.init(g, (uint32_t)r);
+        for (; r < r_end; r += kNarrowBwdUnroll * stride) {
+            uint4 rz[kNarrowBwdUnroll], rd[kNarrowBwdUnroll];
+            int64_t ii[kNarrowBwdUnroll];
+            uint32_t cb[kNarrowBwdUnroll], cbs[kNarrowBwdUnroll];
+            float comp[kNarrowBwdUnroll];
+#pragma unroll
+            for (int u = 0; u < kNarrowBwdUnroll; ++u)
+                if (r + u * stride < r_end) {
+                    rz[u] = ld16(Z + (r + u * stride) * C + c0);
+                    rd[u] = ld16(dA + (r + u * stride) * C + c0);
+                    if (SHARE) {
+                        ii[u] = g.idx[r + u * stride];
+                        cb[u] = cur.b, cbs[u] = cur.bs;
+                        cur.advance(g, (uint32_t)stride);
+                    }
+                }
+            if (SHARE) {
+#pragma unroll
+                for (int u = 0; u < kNarrowBwdUnroll; ++u)
+                    if (r + u * stride < r_end) comp[u] = narrow_component(g, ii[u], cb[u], cbs[u], sub);
+            }
+#pragma unroll
+            for (int u = 0; u < kNarrowBwdUnroll; ++u)
+                if (r + u * stride < r_end) {
+                    float z[8], d[8], a[CIN];
+                    unpack8(rz[u], z);
+                    unpack8(rd[u], d);
+                    if (SHARE)
+                        narrow_exchange<CIN>(comp[u], gmask, gbase, a);
+                    else
+                        gather_narrow_row<CIN>(g, (uint32_t)(r + u * stride), a);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float dy = fmaf(z[i], k.sc[i], k.sh[i]) > 0.f ? d[i] : 0.f;
+                        d[i] = fmaf(k.p[i], dy, fmaf(-k.w[i], z[i], k.e[i]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // the tensor-core path feeds dZ to its weight-gradient GEMM in bf16: same rounding here
+                        const float2 dz = __bfloat1622float2(__floats2bfloat162_rn(d[2 * j], d[2 * j + 1]));
+#pragma unroll
+                        for (int q = 0; q < CIN; ++q) acc[j][q] = __ffma2_rn(dz, make_float2(a[q], a[q]), acc[j][q]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < CIN; ++q) {
+                atomicAdd(&sm_dw[(c0 + 2 * j) * CIN + q], acc[j][q].x);
+                atomicAdd(&sm_dw[(c0 + 2 * j + 1) * CIN + q], acc[j][q].y);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * CIN; i += kEwThreads) atomicAdd(dW + (size_t)(i / CIN) * ldw + (i % CIN), sm_dw[i]);
+}
+
 static inline int row_blocks(int64_t rows, int C, int per_sm)
 {
     const int rpp = kEwThreads / (C >> 3);
@@ -555,6 +787,8 @@ static inline int row_blocks(int64_t rows, int C, int per_sm)
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, kStatCtasPerSm); }
+// dynamic shared memory of a column_sums kernel: one [2][C] slot per row lane of the CTA (16 KB when C/8 divides 256)
+static inline size_t stat_smem(int C) { return (size_t)(kEwThreads / (C >> 3)) * 2 * C * sizeof(float); }
 
 // Resident CTAs per SM of an elementwise kernel (cached per call site; a host-side query, legal during graph capture).
 #define MPB_RESIDENT_PER_SM(kernel)                                                       \
@@ -618,7 +852,7 @@ extern "C" int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *part
     using namespace mpb;
     MPB_CHECK_C(C);
     MPB_REQUIRE(M > 0 && Z && partials && nparts == stat_parts(M, C), "bad argument");
-    colstats_kernel<<<nparts, kEwThreads, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, M, C, partials);
+    colstats_kernel<<<nparts, kEwThreads, stat_smem(C), (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, M, C, partials);
     return check_launch("colstats_kernel");
 }
 
@@ -678,11 +912,11 @@ extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const in
     cudaStream_t st = (cudaStream_t)stream;
     if (dA) {
         MPB_REQUIRE(nparts == stat_parts(M, C), "nparts mismatch");
-        bwd_stats_dense_kernel<<<nparts, kEwThreads, 2 * C * sizeof(float), st>>>((const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale,
+        bwd_stats_dense_kernel<<<nparts, kEwThreads, stat_smem(C), st>>>((const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale,
                                                                                  shift, mean, rstd, M, C, partials);
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0 && nparts == stat_parts(M / K, C), "pooled: bad argmax/K/nparts");
-        bwd_stats_pooled_kernel<<<nparts, kEwThreads, 2 * C * sizeof(float), st>>>(dOut, argmax, (const __nv_bfloat16 *)Z, zmax, scale, shift, mean,
+        bwd_stats_pooled_kernel<<<nparts, kEwThreads, stat_smem(C), st>>>(dOut, argmax, (const __nv_bfloat16 *)Z, zmax, scale, shift, mean,
                                                                                   rstd, M / K, K, C, partials);
     }
     return check_launch("bwd_stats kernel");
@@ -725,4 +959,95 @@ extern "C" int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const in
                                                                                   mean, rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
     }
     return check_launch("bwd_apply kernel");
+}
+
+namespace mpb {
+static inline bool fits31(int64_t v) { return v >= 0 && v < ((int64_t)1 << 31); }
+static inline NarrowRows narrow_rows(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats, int64_t fsb,
+                                     int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx, int N, int S, int K, int D)
+{
+    NarrowRows g;
+    g.xyz = xyz, g.xsb = (int32_t)xsb, g.xsn = (int32_t)xsn, g.xsc = (int32_t)xsc;
+    g.feats = feats, g.fsb = (int32_t)fsb, g.fsn = (int32_t)fsn, g.fsc = (int32_t)fsc;
+    g.new_xyz = new_xyz, g.idx = idx, g.N = N, g.S = S, g.K = K, g.D = D;
+    return g;
+}
+}  // namespace mpb
+
+#define MPB_NARROW_CHECKS()                                                                                    \
+    MPB_CHECK_C(C);                                                                                            \
+    MPB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0 && D + 3 <= 8, "bad size (needs 3 + D <= 8)");       \
+    MPB_REQUIRE(xyz && new_xyz && idx && (D == 0 || feats), "null pointer");                                   \
+    MPB_REQUIRE(ldw >= D + 3, "ldw must cover the 3 + D input channels");                                      \
+    MPB_REQUIRE(mpb::fits31(xsb) && mpb::fits31(xsn) && mpb::fits31(xsc) && mpb::fits31(fsb) && mpb::fits31(fsn) && \
+                    mpb::fits31(fsc) && (int64_t)B * S * 3 < ((int64_t)1 << 31),                                \
+                "strides must fit 31 bits");                                                                   \
+    MPB_REQUIRE((int64_t)B * S * K < ((int64_t)1 << 31), "row count exceeds 32-bit indexing")
+
+extern "C" int mpb_sa_first_layer_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats, int64_t fsb,
+                                       int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx, int B, int N, int S, int K,
+                                       int D, const void *W, int ldw, int C, void *Z, float *partials, int nparts, void *stream)
+{
+    using namespace mpb;
+    MPB_NARROW_CHECKS();
+    const int64_t M = (int64_t)B * S * K;
+    MPB_REQUIRE(W && Z && partials && nparts == stat_parts(M, C), "bad argument");
+    const NarrowRows g = narrow_rows(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = stat_smem(C);
+    const bool share = (32 % (C >> 3)) == 0;
+#define MPB_LAUNCH_NARROW(CIN)                                                                                                     \
+    do {                                                                                                                           \
+        if (share)                                                                                                                 \
+            narrow_first_layer_kernel<CIN, true><<<nparts, kEwThreads, smem, st>>>(g, (const __nv_bfloat16 *)W, ldw, M, C,        \
+                                                                                  (__nv_bfloat16 *)Z, partials);                  \
+        else                                                                                                                       \
+            narrow_first_layer_kernel<CIN, false><<<nparts, kEwThreads, smem, st>>>(g, (const __nv_bfloat16 *)W, ldw, M, C,       \
+                                                                                   (__nv_bfloat16 *)Z, partials);                 \
+    } while (0)
+    if (D + 3 <= 3)
+        MPB_LAUNCH_NARROW(3);
+    else if (D + 3 <= 6)
+        MPB_LAUNCH_NARROW(6);
+    else
+        MPB_LAUNCH_NARROW(8);
+#undef MPB_LAUNCH_NARROW
+    return check_launch("narrow_first_layer_kernel");
+}
+
+extern "C" int mpb_sa_first_layer_bwd_bf16(const void *dA, const void *Z, const float *scale, const float *shift, const float *mean,
+                                           const float *rstd, const float *coef, const float *xyz, int64_t xsb, int64_t xsn,
+                                           int64_t xsc, const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                                           const float *new_xyz, const int64_t *idx, int B, int N, int S, int K, int D, int C,
+                                           float *dW, int ldw, void *stream)
+{
+    using namespace mpb;
+    MPB_NARROW_CHECKS();
+    MPB_REQUIRE(dA && Z && scale && shift && mean && rstd && coef && dW, "bad argument");
+    const int64_t M = (int64_t)B * S * K;
+    const NarrowRows g = narrow_rows(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16 *dA_ = (const __nv_bfloat16 *)dA, *Z_ = (const __nv_bfloat16 *)Z;
+    const bool share = (32 % (C >> 3)) == 0;
+#define MPB_LAUNCH_NARROW_BWD2(CIN, SH)                                                                                     \
+    narrow_first_layer_bwd_kernel<CIN, SH><<<row_blocks((M + kNarrowBwdUnroll - 1) / kNarrowBwdUnroll, C,                               \
+                                                        MPB_RESIDENT_PER_SM((narrow_first_layer_bwd_kernel<CIN, SH>))),     \
+                                             kEwThreads, (size_t)C * CIN * sizeof(float), st>>>(g, dA_, Z_, scale, shift, mean, rstd, \
+                                                                                                coef, M, C, dW, ldw)
+#define MPB_LAUNCH_NARROW_BWD(CIN)            \
+    do {                                      \
+        if (share)                            \
+            MPB_LAUNCH_NARROW_BWD2(CIN, true); \
+        else                                  \
+            MPB_LAUNCH_NARROW_BWD2(CIN, false); \
+    } while (0)
+    if (D + 3 <= 3)
+        MPB_LAUNCH_NARROW_BWD(3);
+    else if (D + 3 <= 6)
+        MPB_LAUNCH_NARROW_BWD(6);
+    else
+        MPB_LAUNCH_NARROW_BWD(8);
+#undef MPB_LAUNCH_NARROW_BWD
+#undef MPB_LAUNCH_NARROW_BWD2
+    return check_launch("narrow_first_layer_bwd_kernel");
 }

@@ -332,7 +332,7 @@ class PointNetSetAbstraction(nn.Module):
     def _forward_tensor_core(self, xyz, points, full_points, seed_idx):
         """Reference :203-215 with the grouped tensor produced directly as bf16 GEMM rows and the MLP on
         tcgen05 (maskplanner_b200.shared_mlp).  xyz [B,N,3], points [B,N,D]|None (already position-major)."""
-        from .shared_mlp import pad64, shared_mlp_max
+        from .shared_mlp import narrow_rows_supported, pad64, shared_mlp_max
         require_cuda(xyz)
         B, N, C = xyz.shape
         if self.group_all:                                                              # :151-168
@@ -348,6 +348,9 @@ class PointNetSetAbstraction(nn.Module):
         if rows is not None:   # group-all / full_points: plain rows, padded and rounded to bf16
             w = rows.shape[-1]
             a0 = F.pad(rows.reshape(B * S * K, w), (0, pad64(w) - w)).to(torch.bfloat16)
+        elif narrow_rows_supported(points, K) and len(self.mlp_convs) >= 2:
+            # <= 8 channels per grouped row (SA1): the first layer gathers its rows on the fly, nothing is materialised
+            a0 = (xyz, points, new_xyz.contiguous(), idx.contiguous())                  # :133-138 fused into :210
         else:
             D = 0 if points is None else points.shape[2]
             a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))        # :133-138

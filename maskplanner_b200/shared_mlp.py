@@ -95,6 +95,27 @@ def _padded_weight(conv_weight, cout_p, cin_p, xyz_last):
     return w, wt
 
 
+NARROW_LDW = 8          # leading dimension of the packed first-layer weight on the narrow path (3 + D <= 8 channels)
+
+
+def narrow_rows_supported(points, K):
+    """The on-the-fly first layer applies when the grouped row has at most 8 channels, its features (if any) need no
+    gradient, and the schedule is not L2-chunked."""
+    D = 0 if points is None else points.shape[2]
+    return 3 + D <= NARROW_LDW and L2_CHUNK_BYTES <= 0 and not (points is not None and points.requires_grad) \
+        and os.environ.get("MPB_NARROW_FIRST", "1") == "1"
+
+
+def _narrow_args(narrow):
+    """(xyz, feats|None, new_xyz, idx) -> the leading arguments of mpb_sa_first_layer[_bwd]_bf16."""
+    xyz, feats, new_xyz, idx = narrow
+    B, N, _ = xyz.shape
+    _, S, K = idx.shape
+    fs = tuple(feats.stride()) if feats is not None else (0, 0, 0)
+    D = 0 if feats is None else feats.shape[2]
+    return (ptr(xyz), *xyz.stride(), ptr(feats), *fs, ptr(new_xyz), ptr(idx), B, N, S, K, D)
+
+
 def _unpermute_wgrad(dw, cout, cin, xyz_last):
     """Inverse of the column order used by _padded_weight, cropped to the real [Cout, Cin]."""
     if xyz_last and cin > 3:
@@ -127,7 +148,9 @@ class SharedMLPMax(torch.autograd.Function):
     """pooled[G, C_L] = max_k relu(bn_L(... relu(bn_1(a0 @ W_1^T)) ...)) over the K rows of each group.
 
     apply(a0, K, training, momentum_eps, xyz_last, *flat) with
-      a0    bf16 [M, pad64(Cin)], M = G*K
+      a0    bf16 [M, pad64(Cin)], M = G*K -- or a NarrowRows tuple (xyz, feats|None, new_xyz, idx) when the grouped row
+            has at most 8 channels: the first layer then gathers its input on the fly (mpb_sa_first_layer_bf16) and
+            the [M, 64] operand is never written
       flat  per layer: conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var
       momentum_eps  tuple of (momentum, eps) per layer
     """
@@ -136,17 +159,25 @@ class SharedMLPMax(torch.autograd.Function):
     def forward(ctx, a0, K, training, momentum_eps, xyz_last, *flat):
         lib = _cabi.load()
         L = len(flat) // 6
-        M = a0.shape[0]
+        narrow = a0 if isinstance(a0, tuple) else None
+        if narrow is not None:
+            n_xyz, n_feats, n_new, n_idx = narrow
+            M = n_idx.numel()
+            dev = n_xyz.device
+            c_in_p = NARROW_LDW
+            a0 = None
+        else:
+            M = a0.shape[0]
+            dev = a0.device
+            c_in_p = a0.shape[1]
         G = M // K
-        dev = a0.device
         st = stream_ptr()
         dims = []
-        c_in_p = a0.shape[1]
         for l in range(L):
             cout, cin = flat[6 * l].shape[0], flat[6 * l].shape[1]
             dims.append((cout, cin, pad64(cout), c_in_p))
             c_in_p = pad64(cout)
-        chunks = _row_chunks(M, K, max(2 * (d[2] + d[3]) for d in dims))
+        chunks = [(0, M)] if narrow is not None else _row_chunks(M, K, max(2 * (d[2] + d[3]) for d in dims))
         acts, zs, stats, wts = [a0], [], [], []
         a = a0
         out = argmax = None
@@ -158,14 +189,20 @@ class SharedMLPMax(torch.autograd.Function):
             sc = torch.empty(4, cout_p, dtype=torch.float32, device=dev)      # rows: scale, shift, mean, rstd
             mom, eps = momentum_eps[l]
             # statistics fused into the GEMM epilogue when the layer fits one column tile (N <= 256), else a separate pass
-            fuse = [lib.mpb_gemm_tn_stat_partials(r1 - r0, cout_p, cin_p) if (training and FUSE_STATS) else 0 for r0, r1 in chunks]
+            gemm_layer = l > 0 or narrow is None
+            fuse = [lib.mpb_gemm_tn_stat_partials(r1 - r0, cout_p, cin_p) if (training and FUSE_STATS and gemm_layer) else 0 for r0, r1 in chunks]
             np_c = [f or lib.mpb_bn_stat_partials(r1 - r0, cout_p) for f, (r0, r1) in zip(fuse, chunks)]
             part = torch.empty(sum(np_c), 2, cout_p, dtype=torch.float32, device=dev) if training else None
+            if l == 0 and narrow is not None:
+                np_c = [lib.mpb_bn_stat_partials(M, cout_p)]
+                part = torch.empty(np_c[0], 2, cout_p, dtype=torch.float32, device=dev)
+                check(lib.mpb_sa_first_layer_bf16(*_narrow_args(narrow), ptr(w), cin_p, cout_p, ptr(z), ptr(part), np_c[0], st),
+                      "mpb_sa_first_layer_bf16")
             if l > 0:
                 a = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev)
                 acts.append(a)
             p0 = 0
-            for ci, (r0, r1) in enumerate(chunks):
+            for ci, (r0, r1) in enumerate(chunks if (l > 0 or narrow is None) else []):
                 if l > 0:   # previous layer's normalise + ReLU for this chunk, consumed from L2 by the GEMM below
                     ps = stats[l - 1]
                     check(lib.mpb_bn_relu_bf16(_off(zs[l - 1], r0), ptr(ps[0]), ptr(ps[1]), r1 - r0, cin_p, _off(a, r0), st),
@@ -201,7 +238,9 @@ class SharedMLPMax(torch.autograd.Function):
         check(lib.mpb_bn_relu_max_bf16(ptr(zs[-1]), ptr(sc[0]), ptr(sc[1]), G, K, cl_p, ptr(out), ptr(argmax), ptr(zmax), st),
               "mpb_bn_relu_max_bf16")
         ctx.K, ctx.L, ctx.dims, ctx.training, ctx.xyz_last, ctx.chunks = K, L, dims, training, xyz_last, chunks
-        ctx.save_for_backward(argmax, *acts, *zs, *stats, *wts, *[flat[6 * l + 2] for l in range(L)], zmax)
+        ctx.narrow = narrow is not None
+        ctx.save_for_backward(argmax, *acts, *zs, *stats, *wts, *[flat[6 * l + 2] for l in range(L)], zmax,
+                              *(narrow if narrow is not None else ()))
         c_last = dims[-1][0]
         return out[:, :c_last] if c_last != out.shape[1] else out
 
@@ -217,7 +256,8 @@ class SharedMLPMax(torch.autograd.Function):
         acts, zs = saved[1:1 + L], saved[1 + L:1 + 2 * L]
         stats, wts, gammas = saved[1 + 2 * L:1 + 3 * L], saved[1 + 3 * L:1 + 4 * L], saved[1 + 4 * L:1 + 5 * L]
         zmax = saved[1 + 5 * L]
-        M = acts[0].shape[0]
+        narrow = tuple(saved[2 + 5 * L:6 + 5 * L]) if ctx.narrow else None
+        M = zs[0].shape[0]
         G = M // K
         dev = d_out.device
         st = stream_ptr()
@@ -257,6 +297,14 @@ class SharedMLPMax(torch.autograd.Function):
             dw, dbias = wbuf[:nw].view(cout_p, cin_p), wbuf[nw:nw + cout]
             check(lib.mpb_bn_bwd_finalize_f32(ptr(part), sum(np_c), cout_p, cout, M, ptr(gamma), ptr(sc[2]), ptr(sc[3]), ptr(dgamma),
                                               ptr(dbeta), ptr(coef), ptr(wbuf), wbuf.numel(), st), "mpb_bn_bwd_finalize_f32")
+            if l == 0 and narrow is not None:
+                # fused dZ + weight gradient against the re-gathered rows; nothing upstream of the grouping needs a gradient
+                check(lib.mpb_sa_first_layer_bwd_bf16(ptr(d_a), ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), ptr(coef),
+                                                      *_narrow_args(narrow), cout_p, ptr(dw), cin_p, st), "mpb_sa_first_layer_bwd_bf16")
+                grads[0] = _unpermute_wgrad(dw, cout, cin, ctx.xyz_last)
+                grads[1], grads[2], grads[3] = dbias, dgamma, dbeta
+                d_a = None
+                break
             dz = torch.empty(M, cout_p, dtype=torch.bfloat16, device=dev)
             need_da = l > 0 or ctx.needs_input_grad[0]
             d_prev = torch.empty(M, cin_p, dtype=torch.bfloat16, device=dev) if need_da else None
@@ -292,8 +340,9 @@ class SharedMLPMax(torch.autograd.Function):
 
 
 def shared_mlp_max(a0, K, convs, bns, training, xyz_last=False):
-    """Run the stack on bf16 rows `a0` [G*K, pad64(Cin)]; returns pooled fp32 [G, C_last].
-    xyz_last=True when `a0` comes from mpb_group_points_bf16 (features first, centred xyz last)."""
+    """Run the stack on bf16 rows `a0` [G*K, pad64(Cin)] -- or on a NarrowRows tuple (xyz [B,N,3] fp32, feats [B,N,D]
+    fp32 | None, new_xyz [B,S,3] contiguous, idx [B,S,K] int64 contiguous), see SharedMLPMax; returns pooled fp32
+    [G, C_last].  xyz_last=True when the rows are in mpb_group_points_bf16 order (features first, centred xyz last)."""
     flat, me = [], []
     for conv, bn in zip(convs, bns):
         flat += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
