@@ -236,6 +236,18 @@ MPB_API int mpb_sa_first_layer_bwd_bf16(const void *dA, const void *Z, const flo
 MPB_API int mpb_padded_lengths_f32(const float *y, int N, int P2, int D, float sentinel,
                                    int64_t *first, int32_t *any_flag, void *stream);
 
+/* ---- f3: optimizer step                               train_maskplanner.py:159, :221 -------------------
+ * torch.optim.Adam semantics (amsgrad = False, maximize = False) for up to 80 fp32 tensors in ONE launch.
+ * params / grads / exp_avg / exp_avg_sq / numel are HOST arrays of length ntensors (device pointers and
+ * element counts); they are copied into the kernel's parameter block, so the call is CUDA-graph capturable
+ * and needs no device-side tables.  step (device float, the 1-based count of completed steps) is read by
+ * the launch and advanced by its last CTA; ticket is a zero-initialised device counter owned by the caller.
+ * lr_dev (optional device float) overrides lr, so a scheduler can change it between graph replays. */
+MPB_API int mpb_adam_step_f32(int ntensors, float *const *params, const float *const *grads,
+                              float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel,
+                              float lr, const float *lr_dev, double beta1, double beta2, double eps,
+                              double weight_decay, float *step, uint32_t *ticket, void *stream);
+
 /* ---- f1 (next row): the mask loss's per-sample Hungarian matching   loss_handler.py:860-877 ------
  * One warp per sample solves min sum_t cost[b, row(t), t] over injective row(.) for the PRESENT
  * targets t (present[b,t] != 0; the reference's per-sample torch.unique), fp64 like scipy's

@@ -16,6 +16,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _L = ctypes.c_int64
 _F = ctypes.c_float
+_D = ctypes.c_double
 
 # name -> (restype, argtypes); must list every symbol of include/maskplanner_b200.h
 SIGNATURES = {
@@ -55,6 +56,7 @@ SIGNATURES = {
     "mpb_sa_first_layer_bf16": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P]),
     "mpb_sa_first_layer_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I,
                                         _P, _I, _P]),
+    "mpb_adam_step_f32": (_I, [_I, _P, _P, _P, _P, _P, _F, _P, _D, _D, _D, _D, _P, _P, _P]),
     "mpb_lap_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }
 

@@ -17,11 +17,13 @@ step instead of ~600, which is what makes a ~5 ms step possible at all from Pyth
 BatchNorm semantics: replica semantics (each rank normalises over its own samples), the standard DDP
 behaviour; single-process-equivalent statistics would need SyncBN and are out of scope for round 1.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import loss as L
-from . import regressor, synthetic
+from . import optim, regressor, synthetic
 from .pointnet2_utils import draw_fps_seed
 
 
@@ -109,7 +111,11 @@ class Trainer:
         # gradients are left unset between steps and autograd hands its freshly computed tensors over as .grad -- this
         # saves one read-modify-write accumulation kernel per parameter (~80 launches) and the flat-buffer memset.
         self.buckets = FlatGradBuckets(self.model) if world_size > 1 else None
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True, capturable=use_graph)
+        # one-launch Adam (csrc/adam.cu); MPB_TORCH_ADAM=1 swaps torch's fused implementation back in for A/B runs
+        if os.environ.get("MPB_TORCH_ADAM", "0") == "1":
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True, capturable=use_graph)
+        else:
+            self.opt = optim.Adam(self.model.parameters(), lr=lr)
         self.comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         self._heads_ready = None
         self._heads_pending = 0

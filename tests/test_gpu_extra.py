@@ -75,3 +75,36 @@ def test_bf16_chamfer_inputs_accumulate_in_fp32():
     b = CH.chamfer_distance(x.bfloat16().float(), y.bfloat16().float())[0]
     c = CH.chamfer_distance(x, y)[0]
     assert torch.equal(a, b) and abs(float(a) - float(c)) / float(c) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("weight_decay", [0.0, 0.01])
+def test_one_launch_adam_matches_torch_adam(weight_decay):
+    """mpb_adam_step_f32 (every tensor in one launch, device-side step count) against torch.optim.Adam on tensors of
+    awkward sizes (scalar, non-multiples of 4, one larger than a CTA chunk, one unaligned view), six steps."""
+    from maskplanner_b200.optim import Adam
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shapes = [(1,), (3,), (7, 5), (4096,), (4099,), (130, 67), (64, 1024)]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    backing = torch.zeros(1001 + 1, device=dev)
+    ours = [b.clone().to(dev).requires_grad_() for b in base]
+    ours.append(backing[1:].detach().requires_grad_())            # 4-byte-aligned only: scalar path
+    ref = [p.detach().clone().requires_grad_() for p in ours]
+    opt_o = Adam(ours, lr=3e-3, weight_decay=weight_decay)
+    opt_r = torch.optim.Adam(ref, lr=3e-3, weight_decay=weight_decay)
+    for step in range(6):
+        for po, pr in zip(ours, ref):
+            gr = torch.randn(po.shape, generator=g).to(dev) * (10.0 ** (step - 3))
+            po.grad = gr.clone()
+            pr.grad = gr.clone()
+        if step == 3:
+            opt_o.set_lr(1e-3)
+            opt_r.param_groups[0]["lr"] = 1e-3
+        opt_o.step()
+        opt_r.step()
+    for po, pr in zip(ours, ref):
+        assert torch.allclose(po, pr, rtol=2e-6, atol=2e-7), float((po - pr).abs().max())
+    sd = opt_o.state_dict()
+    assert float(sd["state"][0]["step"]) == 6.0
+    assert torch.allclose(sd["state"][5]["exp_avg_sq"], opt_r.state[ref[5]]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
