@@ -190,18 +190,20 @@ template <typename IT>
 __global__ void __launch_bounds__(256)
 group_rows_bf16_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *__restrict__ feats,
                        int64_t fsb, int64_t fsn, int64_t fsc, const float *__restrict__ new_xyz, const int64_t *__restrict__ idx,
-                       int N, int S, int K, int D, int ldo, int64_t total_vec, int vec_ok, __nv_bfloat16 *__restrict__ out)
+                       int N, int S, int K, int D, int ldo, int64_t total_vec, int vec_ok, __nv_bfloat16 *__restrict__ out,
+                       FastDiv dnv, FastDiv dk, FastDiv ds)
 {
+    constexpr bool FAST = sizeof(IT) == 4;   // multiply-shift division (common.cuh) on the 32-bit path
     const IT nv = (IT)(ldo >> 3), total = (IT)total_vec, step = (IT)gridDim.x * blockDim.x;
     for (IT v = (IT)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += step) {
-        const IT row = v / nv;
+        const IT row = FAST ? (IT)dnv.div((uint32_t)v) : v / nv;
         const int c0 = (int)(v - row * nv) * 8;
         float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (c0 < D + 3) {
             const int64_t i = idx[row];
             if (i >= 0 && i < N) {
-                const IT bs = row / (IT)K;
-                const int64_t b = (int64_t)(bs / (IT)S);
+                const IT bs = FAST ? (IT)dk.div((uint32_t)row) : row / (IT)K;
+                const int64_t b = (int64_t)(FAST ? (IT)ds.div((uint32_t)bs) : bs / (IT)S);
                 if (vec_ok && c0 + 8 <= D) {
                     const float4 *src = reinterpret_cast<const float4 *>(feats + b * fsb + i * fsn + c0);
                     const float4 lo = src[0], hi = src[1];
@@ -231,15 +233,16 @@ group_rows_bf16_kernel(const float *__restrict__ xyz, int64_t xsb, int64_t xsn, 
 template <typename IT>
 __global__ void __launch_bounds__(256)
 group_rows_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ go, int ldo, const int64_t *__restrict__ idx, int N, int S, int K, int D,
-                           int64_t total_vec, float *__restrict__ gfeats)
+                           int64_t total_vec, float *__restrict__ gfeats, FastDiv dnv, FastDiv dsk)
 {
+    constexpr bool FAST = sizeof(IT) == 4;
     const IT nv = (IT)((D + 3) >> 2), total = (IT)total_vec, step = (IT)gridDim.x * blockDim.x, sk = (IT)S * (IT)K;
     for (IT v = (IT)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += step) {
-        const IT row = v / nv;
+        const IT row = FAST ? (IT)dnv.div((uint32_t)v) : v / nv;
         const int c0 = (int)(v - row * nv) * 4;
         const int64_t i = idx[row];
         if (i < 0 || i >= N) continue;
-        const int64_t b = (int64_t)(row / sk);
+        const int64_t b = (int64_t)(FAST ? (IT)dsk.div((uint32_t)row) : row / sk);
         const uint2 raw = *reinterpret_cast<const uint2 *>(go + (int64_t)row * ldo + c0);
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.x));
         const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.y));
@@ -267,13 +270,14 @@ extern "C" int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn,
     MPB_REQUIRE(xyz && new_xyz && idx && out, "null pointer");
     MPB_REQUIRE(D == 0 || feats, "feats is null but D > 0");
     const int vec_ok = D >= 8 && fsc == 1 && (fsb % 4 == 0) && (fsn % 4 == 0) && (((uintptr_t)feats & 15) == 0);
+    const FastDiv dnv = make_fastdiv((uint32_t)(ldo / 8)), dk = make_fastdiv((uint32_t)(K > 0 ? K : 1)), ds = make_fastdiv((uint32_t)(S > 0 ? S : 1));
     // 32-bit item arithmetic needs total + one grid stride to stay below 2^32
     if (total_vec < (int64_t)3 << 30)
         group_rows_bf16_kernel<uint32_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
-            xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out);
+            xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out, dnv, dk, ds);
     else
         group_rows_bf16_kernel<int64_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
-            xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out);
+            xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D, ldo, total_vec, vec_ok, (__nv_bfloat16 *)out, dnv, dk, ds);
     return check_launch("group_rows_bf16_kernel");
 }
 
@@ -287,11 +291,13 @@ extern "C" int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const in
     if (total_vec == 0) return MPB_OK;
     MPB_REQUIRE(grad_out && idx && grad_feats, "null pointer");
     MPB_REQUIRE(((uintptr_t)grad_feats & 15) == 0, "grad_feats must be 16-byte aligned");
-    if (total_vec < (int64_t)3 << 30)
+    const uint64_t sk64 = (uint64_t)(S > 0 ? S : 1) * (uint64_t)(K > 0 ? K : 1);
+    const FastDiv dnv = make_fastdiv((uint32_t)((D + 3) / 4)), dsk = make_fastdiv((uint32_t)(sk64 < (1ull << 31) ? sk64 : 1));
+    if (total_vec < (int64_t)3 << 30 && sk64 < (1ull << 31))
         group_rows_bwd_bf16_kernel<uint32_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total_vec, grad_feats);
+            (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total_vec, grad_feats, dnv, dsk);
     else
         group_rows_bwd_bf16_kernel<int64_t><<<grid_for(total_vec, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total_vec, grad_feats);
+            (const __nv_bfloat16 *)grad_out, ldo, idx, N, S, K, D, total_vec, grad_feats, dnv, dsk);
     return check_launch("group_rows_bwd_bf16_kernel");
 }

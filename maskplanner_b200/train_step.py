@@ -36,8 +36,9 @@ class FlatGradBuckets:
         heads = [p for n, p in named if not n.startswith(("sa1.", "sa2.", "sa3."))]
         enc = [p for n, p in named if n.startswith(("sa1.", "sa2.", "sa3."))]
         self.params = heads + enc
-        n_heads = sum(p.numel() for p in heads)
-        total = n_heads + sum(p.numel() for p in enc)
+        pad4 = lambda n: (n + 3) // 4 * 4            # every view starts 16-byte aligned (vector path of the Adam kernel)
+        n_heads = sum(pad4(p.numel()) for p in heads)
+        total = n_heads + sum(pad4(p.numel()) for p in enc)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.heads = self.flat[:n_heads]
@@ -45,7 +46,7 @@ class FlatGradBuckets:
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += pad4(p.numel())
         self.head_params = heads
 
     def zero(self):
