@@ -120,6 +120,8 @@ class Trainer:
         self.comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         self._heads_ready = None
         self._heads_pending = 0
+        self._copy_stream = None
+        self._staged = None
         self.use_graph = use_graph
         self._graph = None
         self._static = None
@@ -213,9 +215,34 @@ class Trainer:
         self._graph.replay()
         return self._static_loss
 
-    def step_from_host(self, host_batch, fps_seeds=None):
-        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223)."""
-        loss = self.step(self.to_device(host_batch), fps_seeds)
+    def prefetch(self, host_batch):
+        """Start the H2D copy of a FUTURE step's pinned batch on a side stream, so it overlaps the step in flight (what
+        the reference's DataLoader workers + pin_memory + non_blocking copies do, train_maskplanner.py:207-208)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            dev = self.to_device(host_batch)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (host_batch, dev, ev)
+
+    def step_from_host(self, host_batch, fps_seeds=None, next_host_batch=None):
+        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223).
+        `next_host_batch`: the batch of the following call; its H2D copy is issued right after this step has been
+        enqueued and runs concurrently with it."""
+        staged = self._staged
+        if staged is not None and staged[0] is host_batch:
+            _, dev, ev = staged
+            self._staged = None
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for t in dev.values():
+                t.record_stream(cur)          # allocated on the copy stream, consumed here
+        else:
+            dev = self.to_device(host_batch)
+        loss = self.step(dev, fps_seeds)
+        if next_host_batch is not None:
+            self.prefetch(next_host_batch)
         return float(loss.item())
 
 

@@ -268,3 +268,26 @@ def test_cuda_graph_step_matches_eager_step():
             assert tr._graph is not None and tr.kernels_per_step > 50
     assert np.allclose(curves[0], curves[1], rtol=1e-3), curves
     assert len({round(c, 1) for c in curves[1]}) > 3                  # the replays really saw different inputs
+
+
+@pytest.mark.gpu
+def test_prefetched_host_batches_give_the_same_losses():
+    """step_from_host(batch, next_host_batch=...) overlaps the next batch's H2D copy with the running step (side
+    stream + event); the losses must equal those of the plain call sequence, with and without CUDA graph replay."""
+    from maskplanner_b200 import synthetic
+    from maskplanner_b200.train_step import Trainer, pin_batch
+    B = 4
+    host = [pin_batch(synthetic.make_batch(B, "windows_v2", seed0=70 + 10 * i)) for i in range(3)]
+    gen = torch.Generator().manual_seed(3)
+    seeds = [(torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen)) for _ in range(6)]
+    for use_graph in (False, True):
+        curves = []
+        for prefetch in (False, True):
+            tr = Trainer("windows_v2", torch.device("cuda", 0), seed=4, use_graph=use_graph, lr=0.0)
+            tr.model.dropout.p = 0.0
+            losses = []
+            for i in range(6):
+                nxt = host[(i + 1) % 3] if prefetch else None
+                losses.append(tr.step_from_host(host[i % 3], seeds[i], next_host_batch=nxt))
+            curves.append(losses)
+        assert curves[0] == curves[1], (use_graph, curves)
