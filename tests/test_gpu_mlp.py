@@ -186,3 +186,91 @@ def test_bf16_group_rows_features_first(D, layout):
         fo = feats.clone().requires_grad_(True)
         (T.index_points(fo, idx).reshape(-1, D) * w[:, :D].float()).sum().backward()
         assert torch.allclose(fd.grad.cpu(), fo.grad, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("D,radius", [(0, 0.2), (3, 0.2), (0, 0.004)])
+def test_narrow_first_layer_matches_materialised_rows(D, radius, monkeypatch):
+    """SA1-style module (3 or 6 input channels): the on-the-fly first layer (mpb_sa_first_layer[_bwd]_bf16, rows
+    gathered inside the kernel, fused statistics / fused weight gradient) against the materialised path
+    (mpb_group_points_bf16 -> tcgen05 GEMM -> bwd_apply -> wgrad GEMM) on the same inputs and weights.  Same bf16
+    rounding points, different fp32 summation order: outputs rel 2e-3 (max-abs), every parameter gradient rel-L2 1e-2.
+    radius 0.004 leaves most balls with the centre only (rows padded with the first hit)."""
+    import copy
+    from maskplanner_b200 import pointnet2_utils as P
+    from maskplanner_b200 import synthetic
+    B, N, S, K = 3, 2048, 128, 16
+    cloud = synthetic.make_clouds(B, N, seed0=41 + D).cuda()                    # [B, N, 3]
+    xyz = cloud.permute(0, 2, 1).contiguous()
+    pts = None
+    if D:
+        g = torch.Generator().manual_seed(8)
+        pts = F.normalize(torch.randn(B, D, N, generator=g), dim=1).cuda()
+    torch.manual_seed(12)
+    sa = P.PointNetSetAbstraction(S, radius, K, 3 + D, [32, 48, 64], False).cuda().train()
+    sa.precision = "bf16"
+    sa_ref = copy.deepcopy(sa)
+    seed = torch.tensor([7, 700, 1999])
+    outs = []
+    for mod, narrow in ((sa, "1"), (sa_ref, "0")):
+        monkeypatch.setenv("MPB_NARROW_FIRST", narrow)
+        from maskplanner_b200 import _cabi
+        n0 = _cabi.KERNEL_LAUNCHES
+        new_xyz, feat = mod(xyz, pts, seed_idx=seed)
+        w = torch.linspace(-1.0, 1.0, feat.numel(), device="cuda").view_as(feat)
+        (feat * w).sum().backward()
+        outs.append((new_xyz, feat, _cabi.KERNEL_LAUNCHES - n0))
+    (x1, f1, l1), (x0, f0, l0) = outs
+    assert torch.equal(x1, x0)
+    assert l1 < l0                                             # really took the other code path (fewer launches)
+    assert float((f1 - f0).abs().max() / f0.abs().max()) < 2e-3
+    for (n, p1), (_, p0) in zip(sa.named_parameters(), sa_ref.named_parameters()):
+        if n.endswith("mlp_convs.0.bias") or ".bias" in n and "convs" in n:
+            assert float(p1.grad.abs().max()) == 0.0 and float(p0.grad.abs().max()) == 0.0   # exact zeros under BN
+            continue
+        assert _rel_l2(p1.grad, p0.grad) < 1e-2, (n, _rel_l2(p1.grad, p0.grad))
+    for b1, b0 in zip(sa.mlp_bns, sa_ref.mlp_bns):
+        assert torch.allclose(b1.running_mean, b0.running_mean, rtol=1e-3, atol=1e-5)
+        assert torch.allclose(b1.running_var, b0.running_var, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("cout,cin,xyz_last", [(64, 3, True), (64, 6, True), (128, 131, True), (256, 259, False), (24, 35, False)])
+def test_pack_weight_matches_torch_ops(cout, cin, xyz_last):
+    """mpb_pack_weight_bf16: zero-padded bf16 operand, its transpose, and the xyz-last column permutation."""
+    c = _lib()
+    lib = c.load()
+    g = torch.Generator(device="cuda").manual_seed(cout + cin)
+    W = torch.randn(cout, cin, device="cuda", generator=g)
+    cout_p, cin_p = (cout + 63) // 64 * 64, (8 if cin <= 8 else (cin + 63) // 64 * 64)
+    wp = torch.full((cout_p, cin_p), 7.0, dtype=torch.bfloat16, device="cuda")
+    wt = torch.full((cin_p, cout_p), 7.0, dtype=torch.bfloat16, device="cuda")
+    c.check(lib.mpb_pack_weight_bf16(c.ptr(W), cout, cin, cout_p, cin_p, int(xyz_last), c.ptr(wp), c.ptr(wt), c.stream_ptr()), "pack")
+    want = torch.zeros(cout_p, cin_p, device="cuda")
+    src = torch.cat([W[:, 3:], W[:, :3]], dim=1) if (xyz_last and cin > 3) else W
+    want[:cout, :cin] = src
+    assert torch.equal(wp, want.bfloat16())
+    assert torch.equal(wt, want.bfloat16().t().contiguous())
+
+
+@pytest.mark.parametrize("G,K,C", [(4, 128, 1024), (64, 128, 1024), (3, 70, 512), (5, 33, 64), (1000, 16, 64)])
+def test_bn_relu_max_small_and_large_group_counts(G, K, C):
+    """mpb_bn_relu_max_bf16 picks the 1024-thread K-split kernel for few groups and the one-thread-per-(group, 8
+    channels) kernel otherwise: values, FIRST arg-max (torch.max semantics) and the saved pre-activation must agree
+    with torch on both, including ties (bf16 inputs collide often) and all-negative columns (relu -> 0, arg 0)."""
+    c = _lib()
+    lib = c.load()
+    g = torch.Generator(device="cuda").manual_seed(G * K + C)
+    Z = (torch.randn(G * K, C, device="cuda", generator=g) * 2).bfloat16()
+    Z[:, 0] = -Z[:, 0].abs() - 1.0                                  # a column that relu kills everywhere
+    scale = torch.rand(C, device="cuda", generator=g) + 0.5
+    shift = torch.randn(C, device="cuda", generator=g) * 0.1
+    shift[0] = 0.0
+    out = torch.empty(G, C, device="cuda")
+    arg = torch.empty(G, C, dtype=torch.int32, device="cuda")
+    zmax = torch.empty(G, C, device="cuda")
+    c.check(lib.mpb_bn_relu_max_bf16(c.ptr(Z), c.ptr(scale), c.ptr(shift), G, K, C, c.ptr(out), c.ptr(arg), c.ptr(zmax), c.stream_ptr()), "relu_max")
+    act = torch.relu((Z.double() * scale.double() + shift.double()).float()).view(G, K, C)   # == fmaf(z, scale, shift)
+    want = act.max(dim=1).values
+    assert torch.allclose(out, want, rtol=1e-6, atol=1e-7)
+    first = (act == want.unsqueeze(1)).int().argmax(dim=1).int()     # first k attaining the maximum
+    assert torch.equal(arg, first)
+    assert torch.equal(zmax, Z.float().view(G, K, C).gather(1, first.long().unsqueeze(1)).squeeze(1))
