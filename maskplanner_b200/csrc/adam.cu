@@ -43,7 +43,7 @@ __device__ __forceinline__ void adam_update(float &p, float g, float &m, float &
     p -= step_size * (m / denom);
 }
 
-__global__ void __launch_bounds__(kAdamThreads)
+__global__ void __launch_bounds__(kAdamThreads, 4)
 adam_kernel(const __grid_constant__ AdamTable tab, AdamHyper h, const float *__restrict__ lr_dev, float *__restrict__ step,
             unsigned *__restrict__ ticket)
 {
@@ -67,25 +67,30 @@ adam_kernel(const __grid_constant__ AdamTable tab, AdamHyper h, const float *__r
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                        reinterpret_cast<uintptr_t>(v)) & 15) == 0;
     if (vec && e0 + kAdamChunk <= n) {
-        float4 P[4], G[4], M[4], V[4];
+        // two passes of two float4 per array: 8 loads in flight per thread at ~56 registers (4 CTAs/SM); four float4 per
+        // array at once needed 90 registers and ran at 2 CTAs/SM (ncu: 22 % warps active, 3.96 TB/s)
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float4 P[2], G[2], M[2], V[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t e = e0 + (int64_t)(u * kAdamThreads + threadIdx.x) * 4;
-            P[u] = *reinterpret_cast<const float4 *>(p + e);
-            G[u] = *reinterpret_cast<const float4 *>(g + e);
-            M[u] = *reinterpret_cast<const float4 *>(m + e);
-            V[u] = *reinterpret_cast<const float4 *>(v + e);
-        }
+            for (int u = 0; u < 2; ++u) {
+                const int64_t e = e0 + (int64_t)((2 * half + u) * kAdamThreads + threadIdx.x) * 4;
+                P[u] = *reinterpret_cast<const float4 *>(p + e);
+                G[u] = *reinterpret_cast<const float4 *>(g + e);
+                M[u] = *reinterpret_cast<const float4 *>(m + e);
+                V[u] = *reinterpret_cast<const float4 *>(v + e);
+            }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            adam_update(P[u].x, G[u].x, M[u].x, V[u].x, h, step_size, inv_bc2_sqrt);
-            adam_update(P[u].y, G[u].y, M[u].y, V[u].y, h, step_size, inv_bc2_sqrt);
-            adam_update(P[u].z, G[u].z, M[u].z, V[u].z, h, step_size, inv_bc2_sqrt);
-            adam_update(P[u].w, G[u].w, M[u].w, V[u].w, h, step_size, inv_bc2_sqrt);
-            const int64_t e = e0 + (int64_t)(u * kAdamThreads + threadIdx.x) * 4;
-            *reinterpret_cast<float4 *>(p + e) = P[u];
-            *reinterpret_cast<float4 *>(m + e) = M[u];
-            *reinterpret_cast<float4 *>(v + e) = V[u];
+            for (int u = 0; u < 2; ++u) {
+                adam_update(P[u].x, G[u].x, M[u].x, V[u].x, h, step_size, inv_bc2_sqrt);
+                adam_update(P[u].y, G[u].y, M[u].y, V[u].y, h, step_size, inv_bc2_sqrt);
+                adam_update(P[u].z, G[u].z, M[u].z, V[u].z, h, step_size, inv_bc2_sqrt);
+                adam_update(P[u].w, G[u].w, M[u].w, V[u].w, h, step_size, inv_bc2_sqrt);
+                const int64_t e = e0 + (int64_t)((2 * half + u) * kAdamThreads + threadIdx.x) * 4;
+                *reinterpret_cast<float4 *>(p + e) = P[u];
+                *reinterpret_cast<float4 *>(m + e) = M[u];
+                *reinterpret_cast<float4 *>(v + e) = V[u];
+            }
         }
     } else {
         const int64_t e1 = e0 + kAdamChunk < n ? e0 + kAdamChunk : n;
