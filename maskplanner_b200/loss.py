@@ -26,6 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pytorch3d_chamfer as CH
+from .streams import Fork
 
 
 @dataclass
@@ -40,10 +41,9 @@ class LossConfig:
     pose_dim: int = 6                                    # get_dim_traj_points(['orientnorm'])
 
 
-def chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=True):
-    """Terms 1-3.  Returns (term1, term2, term3, nn_distance [B,P1], pred_to_gt_match [B,P1] int64)."""
+def chamfer_terms_13(y_pred, y, cfg, fused=True):
+    """Terms 1 and 3 (loss_handler.py:604-645).  Returns (term1, term3, nn_distance [B,P1], pred_to_gt_match [B,P1])."""
     B = y_pred.shape[0]
-    points_pred = y_pred.reshape(B, -1, cfg.pose_dim)
     if fused:
         x = y_pred.float().contiguous()
         yy = y.float().contiguous()
@@ -57,7 +57,19 @@ def chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=True):
                                                point_reduction=None, batch_reduction=None)
         term1 = 100 * d_x.mean()
         term3 = 100 * CH.chamfer_distance(y_pred, y, padded=True, reverse_asymmetric=True)[0]
-    term2 = 100 * CH.chamfer_distance(points_pred, traj_as_pc, padded=True, reverse_asymmetric=True)[0]
+    return term1, term3, d_x, match
+
+
+def chamfer_term2(y_pred, traj_as_pc, cfg):
+    """Term 2: ground-truth poses -> predicted poses (loss_handler.py:628-636)."""
+    points_pred = y_pred.reshape(y_pred.shape[0], -1, cfg.pose_dim)
+    return 100 * CH.chamfer_distance(points_pred, traj_as_pc, padded=True, reverse_asymmetric=True)[0]
+
+
+def chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=True):
+    """Terms 1-3.  Returns (term1, term2, term3, nn_distance [B,P1], pred_to_gt_match [B,P1] int64)."""
+    term1, term3, d_x, match = chamfer_terms_13(y_pred, y, cfg, fused=fused)
+    term2 = chamfer_term2(y_pred, traj_as_pc, cfg)
     return term1, term2, term3, d_x, match
 
 
@@ -144,8 +156,13 @@ def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores
                                        fused=True, return_terms=False, matcher="device"):
     """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config."""
     cfg = cfg or LossConfig()
-    t1, t2, t3, _, match = chamfer_terms(y_pred, y, traj_as_pc, cfg, fused=fused)
+    t1, t3, _, match = chamfer_terms_13(y_pred, y, cfg, fused=fused)
+    # term 2 (a second nearest-neighbour search) does not feed the mask loss (cost matrices -> Hungarian solver ->
+    # matched BCE/dice): the two run side by side (maskplanner_b200/streams.py)
+    with Fork(y_pred, traj_as_pc) as fork:
+        t2 = chamfer_term2(y_pred, traj_as_pc, cfg)
     masks = stroke_masks_loss(match, pred_stroke_masks, mask_scores, stroke_ids, cfg, matcher=matcher)
+    fork.join(t2)
     loss = (cfg.weight_asymm_segment_chamfer * t1 + cfg.weight_reverse_asymm_point_chamfer * t2
             + cfg.weight_reverse_asymm_segment_chamfer * t3 + masks)
     if return_terms:

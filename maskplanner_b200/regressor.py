@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 from . import synthetic
 from .pointnet2_utils import PointNetSetAbstraction
+from .streams import Fork
 
 
 class PointNet2Regressor_StrokeMasks(nn.Module):
@@ -86,12 +87,16 @@ class PointNet2Regressor_StrokeMasks(nn.Module):
             seg_conf = torch.sigmoid(self.seg_conf_out(c))
 
         masks, mask_scores = None, None
+        fork = None
         if self.pred_stroke_masks:                                               # :321-329
-            m = self.dropout(F.relu(self.sm_bn1(self.sm_fc1(feat))))
-            m = self.dropout(F.relu(self.sm_bn2(self.sm_fc2(m))))
-            masks = self.sm_fc3(m).view(B, self.n_stroke_masks, -1)
-            if self.mask_confidence_scores:
-                mask_scores = self.mask_conf_out(m)
+            # the stroke-mask head only shares `feat` with the pose head: same host order (dropout RNG consumption as
+            # in the reference), but issued on a side stream so the two chains of M = batch GEMMs overlap
+            with Fork(feat) as fork:
+                m = self.dropout(F.relu(self.sm_bn1(self.sm_fc1(feat))))
+                m = self.dropout(F.relu(self.sm_bn2(self.sm_fc2(m))))
+                masks = self.sm_fc3(m).view(B, self.n_stroke_masks, -1)
+                if self.mask_confidence_scores:
+                    mask_scores = self.mask_conf_out(m)
 
         if self.outdim_orient > 0:                                               # :332-339
             nrm = self.tanh(self.fc_normals(h)).view(B, -1, 3)
@@ -99,6 +104,8 @@ class PointNet2Regressor_StrokeMasks(nn.Module):
             out = torch.cat((seg.view(B, -1, 3), nrm), dim=-1).view(B, self.out_vectors, -1)
         else:
             out = seg.view(B, self.out_vectors, self.outdim)
+        if fork is not None:
+            fork.join(masks, mask_scores)
         return out, masks, mask_scores, seg_conf
 
 
