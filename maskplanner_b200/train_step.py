@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import loss as L
-from . import optim, regressor, synthetic
+from . import optim, regressor, streams, synthetic
 from .pointnet2_utils import draw_fps_seed
 
 
@@ -122,6 +122,7 @@ class Trainer:
         self._heads_pending = 0
         self._copy_stream = None
         self._staged = None
+        self._step_stream = None
         self.use_graph = use_graph
         self._graph = None
         self._static = None
@@ -136,9 +137,13 @@ class Trainer:
             def hook(_p):
                 self._heads_pending += 1
                 if self._heads_pending == n_heads:
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    self.comm_stream.wait_event(ev)
+                    # every head gradient has been ENQUEUED by now, on the step's stream or on the side stream the
+                    # stroke-mask head runs on (maskplanner_b200/streams.py): the collective waits for all of them
+                    producers = {torch.cuda.current_stream(), self._step_stream}
+                    if streams.enabled():
+                        producers.add(streams.side_stream(self.device))
+                    for s in producers:
+                        self.comm_stream.wait_stream(s)
                     with torch.cuda.stream(self.comm_stream):
                         all_reduce_mean_(self.buckets.heads, self.world_size)
                     self._heads_ready = torch.cuda.Event()
@@ -161,6 +166,7 @@ class Trainer:
             torch.backends.cuda.matmul.allow_tf32 = old
 
     def _step_body(self, batch, fps_seeds):
+        self._step_stream = torch.cuda.current_stream()
         if self.buckets is not None:                                              # model.zero_grad()  (:184)
             self.buckets.zero()
         else:

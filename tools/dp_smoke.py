@@ -29,5 +29,11 @@ other = flat.clone()
 dist.broadcast(other, src=0)
 log("param max diff vs rank0", float((flat - other).abs().max()))
 dist.barrier()
-dist.destroy_process_group()
+torch.cuda.synchronize()
 log("done")
+tr._graph = None                      # drop the captured NCCL work before the communicator goes away
+try:
+    dist.destroy_process_group()
+except Exception as e:               # teardown only
+    log("destroy_process_group:", e)
+log("exit")
