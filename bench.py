@@ -61,22 +61,25 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for l in self.proc.stdout:
-            self.lines.append(l.strip())
+            self.lines.append((time.monotonic(), l.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples that arrived inside [t0, t1] (host monotonic clock around the timed region; the
+        sampler is started during warm-up so nvidia-smi's start-up latency does not eat the region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [l for t, l in self.lines if t0 is not None and t0 <= t <= t1 + 0.03]
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        for l in (inside or [l for _, l in self.lines[-5:]]):
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -245,22 +248,24 @@ def run_ours(args, ws, rank, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        trainer.step(resident[i % 3])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        trainer.step(resident[i % 3])
+    barrier()
     l0 = _cabi.KERNEL_LAUNCHES
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.monotonic()
     a.record()
     for i in range(args.steps):
         loss = trainer.step(resident[i % 3])
     b.record()
     barrier()
+    t_region1 = time.monotonic()
     ms = a.elapsed_time(b)
     launches = getattr(trainer, "kernels_per_step", None) or (_cabi.KERNEL_LAUNCHES - l0) // max(args.steps, 1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
