@@ -75,3 +75,49 @@ def test_two_rank_gloo_allreduce_equals_full_batch_gradient(tmp_path):
     x, y = _data()
     ((m(x) - y) ** 2).mean().backward()
     assert torch.allclose(got, b.flat, rtol=1e-5, atol=1e-7)
+
+
+def test_flat_bucket_views_are_16_byte_aligned_and_disjoint():
+    """Every .grad view starts on a 16-byte boundary of the flat buffer (vector path of the one-launch Adam kernel),
+    views do not overlap, heads come first, and the padding between views stays zero through backward."""
+    torch.manual_seed(3)
+    m = torch.nn.Sequential()
+    m.add_module("sa1", torch.nn.Linear(5, 7))          # 35 + 7 elements: not multiples of 4
+    m.add_module("act", torch.nn.Tanh())
+    m.add_module("fc1", torch.nn.Linear(7, 3))          # 21 + 3
+    b = FlatGradBuckets(m)
+    spans = []
+    for p in b.params:
+        off = (p.grad.data_ptr() - b.flat.data_ptr()) // 4
+        assert (p.grad.data_ptr() - b.flat.data_ptr()) % 16 == 0
+        assert p.grad.shape == p.shape
+        spans.append((off, off + p.numel()))
+    spans.sort()
+    assert all(a_end <= b_start for (_, a_end), (b_start, _) in zip(spans, spans[1:]))
+    n_heads = sum((p.numel() + 3) // 4 * 4 for p in b.head_params)
+    assert b.heads.numel() == n_heads and b.heads.numel() + b.encoder.numel() == b.flat.numel()
+    assert all(any(p is q for q in b.head_params) for p in [m.fc1.weight, m.fc1.bias])
+    b.zero()
+    (m(torch.randn(4, 5)) ** 2).sum().backward()
+    used = torch.zeros_like(b.flat, dtype=torch.bool)
+    for lo, hi in spans:
+        used[lo:hi] = True
+    assert float(b.flat[~used].abs().max()) == 0.0 and float(b.flat[used].abs().max()) > 0.0
+
+
+def test_narrow_first_layer_eligibility(monkeypatch):
+    """Host-side switch of the on-the-fly first SA layer: <= 8 channels per grouped row, no gradient into the point
+    features, not under L2 chunking, and the MPB_NARROW_FIRST escape hatch."""
+    from maskplanner_b200 import shared_mlp as SM
+    monkeypatch.delenv("MPB_NARROW_FIRST", raising=False)
+    monkeypatch.setattr(SM, "L2_CHUNK_BYTES", 0)
+    assert SM.narrow_rows_supported(None, 32)
+    assert SM.narrow_rows_supported(torch.zeros(2, 10, 3), 32)
+    assert SM.narrow_rows_supported(torch.zeros(2, 10, 5), 32)
+    assert not SM.narrow_rows_supported(torch.zeros(2, 10, 6), 32)              # 3 + 6 > 8 channels
+    assert not SM.narrow_rows_supported(torch.zeros(2, 10, 3, requires_grad=True), 32)
+    monkeypatch.setenv("MPB_NARROW_FIRST", "0")
+    assert not SM.narrow_rows_supported(None, 32)
+    monkeypatch.delenv("MPB_NARROW_FIRST")
+    monkeypatch.setattr(SM, "L2_CHUNK_BYTES", 1 << 20)
+    assert not SM.narrow_rows_supported(None, 32)
