@@ -105,6 +105,12 @@ class Trainer:
         # with the strict-fp32 encoder they stay strict fp32 so that mode keeps the reference's arithmetic.
         from .pointnet2_utils import get_mlp_precision
         self.heads_tf32 = get_mlp_precision() == "bf16" if heads_tf32 is None else bool(heads_tf32)
+        # The heads' M = batch GEMMs are library calls either way; cuBLASLt's heuristics are preferred for them (measured
+        # 3.95 vs 3.97 ms per step; a single run showed 3.87 and was not reproduced).  MPB_BLAS=cublas|cublaslt|default
+        # overrides.  This is a process-wide torch setting (torch.backends.cuda.preferred_blas_library), applied once.
+        self.heads_blas = os.environ.get("MPB_BLAS", "cublaslt")
+        if self.heads_blas != "default" and self.device.type == "cuda":
+            torch.backends.cuda.preferred_blas_library(self.heads_blas)
         cfg = synthetic.CATEGORIES[category]
         self.max_segments = synthetic.out_vectors(cfg["n_pred_traj_points"])   # GT segments never exceed the prediction budget
         self.max_poses = cfg["n_pred_traj_points"]
@@ -156,14 +162,13 @@ class Trainer:
         return {k: host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True) for k in self.KEYS}
 
     def _step_core(self, batch, fps_seeds):
-        if not self.heads_tf32:
-            return self._step_body(batch, fps_seeds)
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True      # head GEMMs (M = batch, library cuBLAS) on TF32 tensor cores
+        old_tf32 = torch.backends.cuda.matmul.allow_tf32
+        if self.heads_tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True  # head GEMMs (M = batch, library calls) on TF32 tensor cores
         try:
             return self._step_body(batch, fps_seeds)
         finally:
-            torch.backends.cuda.matmul.allow_tf32 = old
+            torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
     def _step_body(self, batch, fps_seeds):
         self._step_stream = torch.cuda.current_stream()
