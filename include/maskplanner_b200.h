@@ -44,6 +44,13 @@ MPB_API const char *mpb_last_error_string(void);
 MPB_API int mpb_device_sm_count(void);
 MPB_API int mpb_device_arch(void);
 
+/* ---- measurement helper (the FP32 SIMT roof "must be measured by the builder") ----
+ * Launches sm_count*ctas_per_sm CTAs of 256 threads, each thread running `iters` rounds of 16 independent
+ * fma chains (packed != 0: fma.rn.f32x2, two per lane per instruction).  out holds one float per thread
+ * (mpb_peak_fp32_threads(ctas_per_sm) of them).  flops = 2 * threads * iters * 16 * (packed ? 2 : 1). */
+MPB_API int64_t mpb_peak_fp32_threads(int ctas_per_sm);
+MPB_API int mpb_peak_fp32_ffma(int packed, int iters, int ctas_per_sm, float *out, void *stream);
+
 /* ---- a1: farthest_point_sample(xyz, npoint)            models/pointnet2_utils.py:65-86 -------
  * xyz [B,N,3] f32 through (sb,sn,sc); seed_idx [B] i64 = the reference's CPU randint draw (:77),
  * made by the caller; out_idx [B,npoint] i64.  Distance ((dx*dx)+(dy*dy))+(dz*dz), every op
@@ -242,11 +249,13 @@ MPB_API int mpb_padded_lengths_f32(const float *y, int N, int P2, int D, float s
  * element counts); they are copied into the kernel's parameter block, so the call is CUDA-graph capturable
  * and needs no device-side tables.  step (device float, the 1-based count of completed steps) is read by
  * the launch and advanced by its last CTA; ticket is a zero-initialised device counter owned by the caller.
- * lr_dev (optional device float) overrides lr, so a scheduler can change it between graph replays. */
+ * lr_dev (optional device float) overrides lr, so a scheduler can change it between graph replays.
+ * grad_scale multiplies every gradient on load (1/world_size when the buffer holds the SUM over ranks). */
 MPB_API int mpb_adam_step_f32(int ntensors, float *const *params, const float *const *grads,
                               float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel,
                               float lr, const float *lr_dev, double beta1, double beta2, double eps,
-                              double weight_decay, float *step, uint32_t *ticket, void *stream);
+                              double weight_decay, float grad_scale, float *step, uint32_t *ticket,
+                              void *stream);
 
 /* ---- f1 (next row): the mask loss's per-sample Hungarian matching   loss_handler.py:860-877 ------
  * One warp per sample solves min sum_t cost[b, row(t), t] over injective row(.) for the PRESENT

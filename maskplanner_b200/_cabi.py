@@ -24,6 +24,8 @@ SIGNATURES = {
     "mpb_last_error_string": (ctypes.c_char_p, []),
     "mpb_device_sm_count": (_I, []),
     "mpb_device_arch": (_I, []),
+    "mpb_peak_fp32_threads": (_L, [_I]),
+    "mpb_peak_fp32_ffma": (_I, [_I, _I, _I, _P, _P]),
     "mpb_fps_workspace_bytes": (_L, [_I, _I]),
     "mpb_fps_f32": (_I, [_P, _L, _L, _L, _I, _I, _P, _I, _P, _P, _P]),
     "mpb_square_distance_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
@@ -56,7 +58,7 @@ SIGNATURES = {
     "mpb_sa_first_layer_bf16": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P]),
     "mpb_sa_first_layer_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I,
                                         _P, _I, _P]),
-    "mpb_adam_step_f32": (_I, [_I, _P, _P, _P, _P, _P, _F, _P, _D, _D, _D, _D, _P, _P, _P]),
+    "mpb_adam_step_f32": (_I, [_I, _P, _P, _P, _P, _P, _F, _P, _D, _D, _D, _D, _F, _P, _P, _P]),
     "mpb_lap_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }
 
@@ -73,12 +75,12 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path):
+    if _build.is_stale():   # missing, or built from other sources than the ones in csrc/ now (hash, not mtime)
         try:
             _build.build()
         except Exception as e:  # no silent degradation: surface why the native path is unavailable
             raise ImportError(
-                "libmaskplanner_b200.so is missing and could not be built (%s). maskplanner_b200 has no "
+                "libmaskplanner_b200.so is missing or stale and could not be built (%s). maskplanner_b200 has no "
                 "CPU or pure-torch fallback; run `python -m maskplanner_b200.build`." % (e,)) from e
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():

@@ -34,6 +34,31 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def source_hash():
+    """sha256 over every csrc/ source, header and the public C header: identifies the build the .so came from."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(HERE, "..", "include", "maskplanner_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(ARCH + NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+HASH_FILE = LIB + ".srchash"
+
+
+def is_stale():
+    """True when the .so is missing or was built from different sources (mtime-independent: snapshots reset mtimes)."""
+    if not os.path.exists(LIB) or not os.path.exists(HASH_FILE):
+        return True
+    with open(HASH_FILE) as f:
+        return f.read().strip() != source_hash()
+
+
 def _deps_mtime():
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(HERE, "..", "include", "maskplanner_b200.h"))
@@ -46,6 +71,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
     hdr_t = _deps_mtime()
+    force = force or (os.path.exists(HASH_FILE) and is_stale())   # a stale hash means mtimes cannot be trusted either
     jobs = []
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
@@ -75,6 +101,8 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(HASH_FILE, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

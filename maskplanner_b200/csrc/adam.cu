@@ -31,11 +31,12 @@ struct AdamTable {
 
 struct AdamHyper {   // betas arrive as doubles: torch forms 1 - beta and beta^t in double before rounding to fp32
     double beta1_d, beta2_d;
-    float lr, beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay;
+    float lr, beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, grad_scale;
 };
 
 __device__ __forceinline__ void adam_update(float &p, float g, float &m, float &v, const AdamHyper &h, float step_size, float inv_bc2_sqrt)
 {
+    g *= h.grad_scale;   // 1 on one GPU; 1/world_size when the gradient buffer holds the SUM over ranks (exact for powers of two)
     if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
     m = fmaf(g - m, h.one_minus_beta1, m);
     v = fmaf(h.beta2, v, h.one_minus_beta2 * g * g);
@@ -115,7 +116,8 @@ adam_kernel(const __grid_constant__ AdamTable tab, AdamHyper h, const float *__r
 
 extern "C" int mpb_adam_step_f32(int ntensors, float *const *params, const float *const *grads, float *const *exp_avg,
                                  float *const *exp_avg_sq, const int64_t *numel, float lr, const float *lr_dev, double beta1,
-                                 double beta2, double eps, double weight_decay, float *step, uint32_t *ticket, void *stream)
+                                 double beta2, double eps, double weight_decay, float grad_scale, float *step, uint32_t *ticket,
+                                 void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(ntensors >= 0, "negative tensor count");
@@ -142,7 +144,7 @@ extern "C" int mpb_adam_step_f32(int ntensors, float *const *params, const float
     h.beta1_d = beta1, h.beta2_d = beta2;
     h.lr = lr, h.beta1 = (float)beta1, h.beta2 = (float)beta2;
     h.one_minus_beta1 = (float)(1.0 - beta1), h.one_minus_beta2 = (float)(1.0 - beta2);
-    h.eps = (float)eps, h.weight_decay = (float)weight_decay;
+    h.eps = (float)eps, h.weight_decay = (float)weight_decay, h.grad_scale = grad_scale;
     adam_kernel<<<chunks, kAdamThreads, 0, (cudaStream_t)stream>>>(tab, h, lr_dev, step, ticket);
     return check_launch("adam_kernel");
 }

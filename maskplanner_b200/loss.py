@@ -112,20 +112,41 @@ def hungarian_device(cost, present):
     return row
 
 
-def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, cfg, matcher="device"):
+def validate_stroke_ids(stroke_ids, n_pred_masks):
+    """Host-side precondition of the fixed-shape mask loss: every real stroke id lies in [0, n_pred_masks) and the
+    padding id is -1 (utils/dataset/paintnet_ODv1.py:746).  The reference builds its masks with torch.unique over
+    arbitrary id values (loss_handler.py:938-967) and then requires n_strokes <= n_pred_masks for the assignment;
+    here the ids index a one-hot of width n_pred_masks, so a larger id would silently drop its segments.  Called on
+    the HOST copy of the batch (Trainer.to_device / pad_batch): no device synchronisation."""
+    ids = stroke_ids.detach()
+    if ids.numel() == 0:
+        return
+    lo, hi = float(ids.min()), float(ids.max())
+    if hi >= n_pred_masks or lo < -1 or not bool((ids == ids.round()).all()):
+        raise ValueError("stroke ids must be integers in [-1, %d) (-1 = padding); got range [%g, %g]" % (n_pred_masks, lo, hi))
+
+
+def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, cfg, matcher="device", check_ids=False):
     """loss_handler.py:816-935 with smooth_targets=False (binary masks, BCE).
 
     matcher="device" (default): batched on-device assignment and fixed-shape masked reductions -- no
     host round trip, CUDA-graph capturable.  matcher="host": scipy on the host from one D2H copy (the
-    reference's own solver; used by the parity tests)."""
+    reference's own solver; used by the parity tests).
+    check_ids=True re-creates the reference's sanity asserts (:852-854: no predicted segment matched to the padding
+    id, ids inside the mask budget) with one device->host synchronisation; never set inside a captured step -- the
+    Trainer validates the host batch instead (validate_stroke_ids)."""
     dev = pred_stroke_masks.device
     B, n_pred_masks, out_segments = pred_stroke_masks.shape
     ids = stroke_ids.to(dev).gather(1, pred_to_gt_match)                         # :838  [B, out_segments], float
     ids = ids.long()                                                             # the -1 padding id is never matched (:852)
     n_ids = n_pred_masks                                                         # ids < max_n_strokes == n_pred_masks
+    if check_ids and not torch.cuda.is_current_stream_capturing():
+        assert not bool((ids == -1).any()), "no predicted segment should be associated with the fake stroke id -1"   # :852
+        assert int(ids.max()) < n_ids, "stroke id %d outside the mask budget %d" % (int(ids.max()), n_ids)
     if matcher == "device":
         with torch.no_grad():
-            cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids.clamp_min(0), n_ids)
+            # ids are NOT clamped: a (never expected) -1 matches no class and leaves an all-zero one-hot row
+            cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids, n_ids)
             row = hungarian_device(cost, present)                                # [B, T]  (:860-877)
             pres_f = present.to(pred_stroke_masks.dtype)
             row_c = row.clamp_min(0)
@@ -138,7 +159,7 @@ def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, c
         conf_loss = F.binary_cross_entropy_with_logits(scores, target_scores, reduction="none", weight=weights).mean()   # :930
         return cfg.explicit_weight_stroke_masks * mask_loss + cfg.explicit_weight_stroke_masks_confidence * conf_loss
     with torch.no_grad():
-        cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids.clamp_min(0), n_ids)
+        cost, present, onehot = mask_cost_matrices(pred_stroke_masks, ids, n_ids)
         b_idx, p_idx, t_idx = hungarian_host(cost, present)                      # :860-877
         b_idx, p_idx, t_idx = b_idx.to(dev), p_idx.to(dev), t_idx.to(dev)
     matched_pred = pred_stroke_masks[b_idx, p_idx]                               # :886  [M, out_segments]
@@ -152,10 +173,39 @@ def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, c
     return cfg.explicit_weight_stroke_masks * mask_loss + cfg.explicit_weight_stroke_masks_confidence * conf_loss
 
 
+SCHEDULABLE = ("weight_asymm_segment_chamfer", "weight_reverse_asymm_point_chamfer", "weight_reverse_asymm_segment_chamfer",
+               "explicit_weight_stroke_masks", "explicit_weight_stroke_masks_confidence")
+
+
+class DeviceLossWeights:
+    """The five schedulable loss weights (delayMasksLoss, PSACDScheduler: train_maskplanner.py:186-199 rewrite them
+    between epochs) as ONE device tensor read by the step's kernels, so a step captured in a CUDA graph follows the
+    schedule: `sync(cfg)` pushes changed host values (outside capture); inside the loss they are 0-d tensor views."""
+
+    def __init__(self, device):
+        self.t = torch.zeros(len(SCHEDULABLE), dtype=torch.float32, device=device)
+        self._host = None
+
+    def sync(self, cfg):
+        vals = tuple(float(getattr(cfg, k)) for k in SCHEDULABLE)
+        if vals != self._host:
+            self.t.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
+            self._host = vals
+
+    def __getitem__(self, name):
+        return self.t[SCHEDULABLE.index(name)]
+
+
 def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores, stroke_ids, traj_as_pc, cfg=None,
-                                       fused=True, return_terms=False, matcher="device"):
-    """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config."""
+                                       fused=True, return_terms=False, matcher="device", weights=None):
+    """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config.
+    weights: optional DeviceLossWeights overriding cfg's five schedulable weights (CUDA-graph replays)."""
     cfg = cfg or LossConfig()
+    if weights is not None:
+        import copy
+        cfg = copy.copy(cfg)
+        for k in SCHEDULABLE:
+            setattr(cfg, k, weights[k])
     t1, t3, _, match = chamfer_terms_13(y_pred, y, cfg, fused=fused)
     # term 2 (a second nearest-neighbour search) does not feed the mask loss (cost matrices -> Hungarian solver ->
     # matched BCE/dice): the two run side by side (maskplanner_b200/streams.py)

@@ -123,6 +123,9 @@ class Trainer:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True, capturable=use_graph)
         else:
             self.opt = optim.Adam(self.model.parameters(), lr=lr)
+        # schedulable loss weights live in device memory when the step is replayed from a graph
+        self.loss_weights = L.DeviceLossWeights(self.device) if use_graph else None
+        self.n_masks = cfg["max_n_strokes"]
         self.comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         self._heads_ready = None
         self._heads_pending = 0
@@ -159,6 +162,8 @@ class Trainer:
 
     def to_device(self, host_batch):
         """The step's H2D boundary (train_maskplanner.py:207-208, loss_handler.py:628-629): pinned -> device, async."""
+        if not host_batch["stroke_ids"].is_cuda:
+            L.validate_stroke_ids(host_batch["stroke_ids"], self.n_masks)       # host-side, no synchronisation
         return {k: host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True) for k in self.KEYS}
 
     def _step_core(self, batch, fps_seeds):
@@ -180,7 +185,8 @@ class Trainer:
         cloud = batch["point_cloud"].permute(0, 2, 1)                             # :207
         pred, masks, scores, _ = self.model(cloud, fps_seeds)                     # :210
         loss = L.asymm_v6_chamfer_with_stroke_masks(pred, batch["traj"], masks, scores, batch["stroke_ids"],
-                                                    batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss)   # :212-218
+                                                    batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss,
+                                                    weights=self.loss_weights)    # :212-218
         self._heads_pending = 0
         loss.backward()                                                           # :220
         if self.world_size > 1:
@@ -200,6 +206,11 @@ class Trainer:
         if not self.use_graph:
             return self._step_core(batch, fps_seeds)
         self._calls += 1
+        # host-side hyper-parameters a scheduler may have changed since the last call (learning rate:
+        # train_maskplanner.py:230; loss weights: :186-199) -> device scalars the captured kernels read
+        if hasattr(self.opt, "sync_hyper"):
+            self.opt.sync_hyper()
+        self.loss_weights.sync(self.loss_cfg)
         batch = pad_batch(batch, self.max_segments, self.max_poses)
         B = batch["point_cloud"].shape[0]
         if fps_seeds is None:

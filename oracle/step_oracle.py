@@ -67,7 +67,7 @@ def _masks_from_ids(ids):
 
 def stroke_masks_loss(match, pred_masks, scores, stroke_ids, w_masks=1.0, w_conf=100.0, no_stroke_weight=1.0):
     """loss_handler.py:816-935, smooth_targets=False."""
-    tgt_ids = stroke_ids.gather(dim=1, index=match)                                            # :838
+    tgt_ids = stroke_ids.to(pred_masks.device).gather(dim=1, index=match)                      # :838 (`stroke_ids.cuda()`)
     tgt_masks = [_masks_from_ids(t) for t in tgt_ids]                                          # :847-848
     assert not torch.any(tgt_ids == -1)                                                        # :852
     B, P, S = pred_masks.shape
@@ -78,16 +78,17 @@ def stroke_masks_loss(match, pred_masks, scores, stroke_ids, w_masks=1.0, w_conf
             a = pm.repeat_interleave(nt, dim=0)                                                # :867
             b = tm.repeat(P, 1).to(pm.dtype)                                                  # :868
             cost = F.binary_cross_entropy_with_logits(a, b, reduction="none").sum(-1).view(P, nt)   # :871-873
-            pairs.append(linear_sum_assignment(cost.numpy()))                                  # :875
-    bi = torch.cat([torch.full((len(r),), i, dtype=torch.int64) for i, (r, _) in enumerate(pairs)])
-    pi = torch.cat([torch.as_tensor(r, dtype=torch.int64) for r, _ in pairs])
-    ti = torch.cat([torch.as_tensor(c, dtype=torch.int64) for _, c in pairs])
+            pairs.append(linear_sum_assignment(cost.cpu().numpy()))                            # :875 (per-sample .cpu())
+    dev = pred_masks.device
+    bi = torch.cat([torch.full((len(r),), i, dtype=torch.int64) for i, (r, _) in enumerate(pairs)]).to(dev)
+    pi = torch.cat([torch.as_tensor(r, dtype=torch.int64) for r, _ in pairs]).to(dev)
+    ti = torch.cat([torch.as_tensor(c, dtype=torch.int64) for _, c in pairs]).to(dev)
     matched_pred = pred_masks[bi, pi]                                                          # :886
     matched_tgt = torch.stack([tgt_masks[b][t] for b, t in zip(bi.tolist(), ti.tolist())]).to(pred_masks.dtype)    # :896-902
     mask_loss = F.binary_cross_entropy_with_logits(matched_pred, matched_tgt, reduction="none").sum(-1).mean()   # :906
-    tgt_scores = torch.zeros(scores.shape, dtype=scores.dtype)                                 # :920-921
+    tgt_scores = torch.zeros(scores.shape, dtype=scores.dtype, device=dev)                     # :920-921
     tgt_scores[bi, pi] = 1.0
-    w = no_stroke_weight * torch.ones(scores.shape, dtype=scores.dtype)                        # :924-925
+    w = no_stroke_weight * torch.ones(scores.shape, dtype=scores.dtype, device=dev)            # :924-925
     w[bi, pi] = 1.0
     conf = F.binary_cross_entropy_with_logits(scores, tgt_scores, reduction="none", weight=w).mean()   # :930
     return w_masks * mask_loss + w_conf * conf, (bi, pi, ti)
@@ -113,10 +114,11 @@ def asymm_v6_loss(y_pred, y, pred_masks, scores, stroke_ids, traj_as_pc, w=(1.0,
 def train_step(model, opt, batch, fps_seeds=None):
     """train_maskplanner.py:183-227 for one batch (dict from maskplanner_b200.synthetic.make_batch)."""
     model.zero_grad()
-    cloud = batch["point_cloud"].permute(0, 2, 1).float()                                      # :207-208
+    dev = next(model.parameters()).device
+    cloud = batch["point_cloud"].permute(0, 2, 1).float().to(dev)                              # :207-208
     pred, masks, scores, _ = model(cloud, fps_seeds)                                           # :210
-    loss = asymm_v6_loss(pred, batch["traj"].float().clone(), masks, scores, batch["stroke_ids"],
-                         batch["traj_as_pc"].float().clone())                                  # :212-218
+    loss = asymm_v6_loss(pred, batch["traj"].float().clone().to(dev), masks, scores, batch["stroke_ids"].to(dev),
+                         batch["traj_as_pc"].float().clone().to(dev))                          # :212-218 (:629 `.to('cuda')`)
     loss.backward()                                                                            # :220
     opt.step()                                                                                 # :221
     return float(loss.item())                                                                  # :223

@@ -36,18 +36,19 @@ def index_points(points, idx):
     return points[bidx, idx, :]
 
 
-def draw_fps_seed(B, N):
-    """models/pointnet2_utils.py:77: one CPU-generator randint(0, N, (B,)) per FPS call."""
-    return torch.randint(0, N, (B,), dtype=torch.long)
+def draw_fps_seed(B, N, device=None):
+    """models/pointnet2_utils.py:77: one CPU-generator randint(0, N, (B,)) per FPS call (then `.to(device)`)."""
+    return torch.randint(0, N, (B,), dtype=torch.long).to(device or "cpu")
 
 
 def farthest_point_sample(xyz, npoint, seed_idx=None):
     """models/pointnet2_utils.py:65-86.  `seed_idx` replaces the :77 draw when given."""
     B, N, _ = xyz.shape
-    picked = torch.zeros(B, npoint, dtype=torch.long)
-    nearest = torch.ones(B, N) * 1e10                                  # :76
-    cur = draw_fps_seed(B, N) if seed_idx is None else seed_idx.clone().long()
-    rows = torch.arange(B, dtype=torch.long)
+    dev = xyz.device                                                   # :74 (every allocation follows the input's device)
+    picked = torch.zeros(B, npoint, dtype=torch.long, device=dev)
+    nearest = torch.ones(B, N, device=dev) * 1e10                      # :76
+    cur = draw_fps_seed(B, N, dev) if seed_idx is None else seed_idx.clone().long().to(dev)
+    rows = torch.arange(B, dtype=torch.long, device=dev)
     for i in range(npoint):                                            # :79
         picked[:, i] = cur                                             # :80
         c = xyz[rows, cur, :].view(B, 1, 3)                            # :81
@@ -61,7 +62,7 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     """models/pointnet2_utils.py:89-109, same sort-based construction as the reference."""
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
-    gi = torch.arange(N, dtype=torch.long).view(1, 1, N).repeat(B, S, 1)    # :102
+    gi = torch.arange(N, dtype=torch.long, device=xyz.device).view(1, 1, N).repeat(B, S, 1)    # :102
     d = square_distance(new_xyz, xyz)                                        # :103
     gi[d > radius ** 2] = N                                                  # :104
     gi = gi.sort(dim=-1)[0][:, :, :nsample]                                  # :105
@@ -91,7 +92,7 @@ def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, full
 def sample_and_group_all(xyz, points):
     """models/pointnet2_utils.py:151-168: one group holding every point, not centred."""
     B, N, C = xyz.shape
-    new_xyz = torch.zeros(B, 1, C)
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
     g = xyz.view(B, 1, N, C)
     if points is not None:
         g = torch.cat([g, points.view(B, 1, N, -1)], dim=-1)
@@ -139,15 +140,26 @@ class _KnnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, p1, p2, len1, len2, K):
-        if p1.dtype == torch.float64:
-            # float64 "ground truth" variant (tests use it to separate conditioning from kernel error):
-            # brute force in torch, same candidate/length/tie rules (stable sort => lowest index first)
-            full = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
-            full = full.masked_fill(torch.arange(p2.shape[1])[None, None, :] >= len2[:, None, None], float("inf"))
-            d, i = torch.sort(full, dim=-1, stable=True)
-            d, i = d[:, :, :K].clone(), i[:, :, :K].clone()
-            dead = (torch.arange(p1.shape[1])[None, :, None] >= len1[:, None, None]) | torch.isinf(d)
-            d, i = d.masked_fill(dead, 0.0), i.masked_fill(dead, 0)
+        dev = p1.device
+        if p1.dtype == torch.float64 or p1.is_cuda:
+            # float64 "ground truth" variant (tests use it to separate conditioning from kernel error) and the
+            # CUDA stand-in for pytorch3d's knn kernel (bench.py's same-box reference arm): brute force in torch,
+            # direct-form distances, same candidate/length/tie rules (stable sort / first minimum => lowest index)
+            d, i = [], []
+            step = max(1, (64 << 20) // max(1, p1.shape[1] * p2.shape[1] * p1.shape[2]))    # <= 256 MB of differences
+            for b0 in range(0, p1.shape[0], step):
+                q, t, l1, l2 = p1[b0:b0 + step], p2[b0:b0 + step], len1[b0:b0 + step], len2[b0:b0 + step]
+                full = ((q[:, :, None, :] - t[:, None, :, :]) ** 2).sum(-1)
+                full = full.masked_fill(torch.arange(t.shape[1], device=dev)[None, None, :] >= l2[:, None, None], float("inf"))
+                if K == 1:
+                    dd, ii = full.min(dim=-1, keepdim=True)
+                else:
+                    dd, ii = torch.sort(full, dim=-1, stable=True)
+                    dd, ii = dd[:, :, :K].clone(), ii[:, :, :K].clone()
+                dead = (torch.arange(q.shape[1], device=dev)[None, :, None] >= l1[:, None, None]) | torch.isinf(dd)
+                d.append(dd.masked_fill(dead, 0.0))
+                i.append(ii.masked_fill(dead, 0))
+            d, i = torch.cat(d), torch.cat(i)
         else:
             d, i = c_oracle.knn(p1, p2, len1, len2, K=K, use_fma=True)
             d, i = torch.from_numpy(d), torch.from_numpy(i)
@@ -161,9 +173,10 @@ class _KnnFn(torch.autograd.Function):
         N, P1, D = p1.shape
         K = idx.shape[2]
         # pytorch3d's backward kernel: only (p1_idx < lengths1[n] and k < lengths2[n]) contribute
-        valid = ((torch.arange(P1)[None, :, None] < len1[:, None, None])
-                 & (torch.arange(K)[None, None, :] < len2[:, None, None])).to(p1.dtype)[..., None]
-        nb = p2[torch.arange(N)[:, None, None], idx]                                          # [N,P1,K,D]
+        dev = p1.device
+        valid = ((torch.arange(P1, device=dev)[None, :, None] < len1[:, None, None])
+                 & (torch.arange(K, device=dev)[None, None, :] < len2[:, None, None])).to(p1.dtype)[..., None]
+        nb = p2[torch.arange(N, device=dev)[:, None, None], idx]                              # [N,P1,K,D]
         diff = (p1[:, :, None, :] - nb) * (2.0 * gd[..., None]) * valid
         g1 = diff.sum(2)
         g2 = torch.zeros_like(p2)
@@ -177,9 +190,9 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
     N, P1, _ = p1.shape
     P2 = p2.shape[1]
     if lengths1 is None:
-        lengths1 = torch.full((N,), P1, dtype=torch.int64)
+        lengths1 = torch.full((N,), P1, dtype=torch.int64, device=p1.device)
     if lengths2 is None:
-        lengths2 = torch.full((N,), P2, dtype=torch.int64)
+        lengths2 = torch.full((N,), P2, dtype=torch.int64, device=p1.device)
     keep = torch.float64 if p1.dtype == torch.float64 else torch.float32
     d, i = _KnnFn.apply(p1.contiguous().to(keep), p2.contiguous().to(keep), lengths1.long(), lengths2.long(), K)
     nn_pts = knn_gather(p2, i, lengths2) if return_nn else None
@@ -191,9 +204,9 @@ def knn_gather(x, idx, lengths=None):
     zero-filled where k >= lengths[n]."""
     N, M, U = x.shape
     _, L, K = idx.shape
-    out = x[torch.arange(N)[:, None, None], idx]
+    out = x[torch.arange(N, device=x.device)[:, None, None], idx]
     if lengths is not None:
-        short = lengths[:, None] <= torch.arange(K)[None]
+        short = lengths[:, None] <= torch.arange(K, device=x.device)[None]
         if short.any():
             out = out.masked_fill(short[:, None, :, None].expand(N, L, K, U), 0.0)
     return out
@@ -211,7 +224,7 @@ def padded_lengths(y, y_lengths, sentinel=-100):
     if not hit.any():
         return y_lengths
     P2 = y.shape[1]
-    first = torch.where(hit.any(1), hit.float().argmax(1), torch.full((y.shape[0],), P2, dtype=torch.long))
+    first = torch.where(hit.any(1), hit.float().argmax(1), torch.full((y.shape[0],), P2, dtype=torch.long, device=y.device))
     y_lengths[:] = first.to(y_lengths.dtype)
     return y_lengths
 
@@ -237,7 +250,7 @@ def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_nor
         if lengths is not None and (lengths.ndim != 1 or lengths.shape[0] != pts.shape[0]):
             raise ValueError("Expected lengths to be of shape (N,)")
         if lengths is None:
-            lengths = torch.full((pts.shape[0],), pts.shape[1], dtype=torch.int64)
+            lengths = torch.full((pts.shape[0],), pts.shape[1], dtype=torch.int64, device=pts.device)
         if normals is not None and normals.ndim != 3:
             raise ValueError("Expected normals to be of shape (N, P, 3")
         return pts, lengths, normals
@@ -251,8 +264,8 @@ def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_nor
         y_lengths = padded_lengths(y, y_lengths)                                  # :138-149
     x_ragged = bool((x_lengths != P1).any())                                      # :152-153
     y_ragged = bool((y_lengths != P2).any())
-    x_mask = torch.arange(P1)[None] >= x_lengths[:, None]                         # :154-159
-    y_mask = torch.arange(P2)[None] >= y_lengths[:, None]
+    x_mask = torch.arange(P1, device=x.device)[None] >= x_lengths[:, None]        # :154-159
+    y_mask = torch.arange(P2, device=x.device)[None] >= y_lengths[:, None]
     if y.shape[0] != N or y.shape[2] != D:
         raise ValueError("y does not have the correct shape.")                    # :161-162
     if weights is not None:                                                       # :163-176
@@ -274,11 +287,11 @@ def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_nor
         assert D == 6, 'Velocities is True but traj does not contain velocities'
         xi = knn_points(x[:, :, :3], y[:, :, :3], lengths1=x_lengths, lengths2=y_lengths, K=1).idx
         yi = knn_points(y[:, :, :3], x[:, :, :3], lengths1=y_lengths, lengths2=x_lengths, K=1).idx
-        cham_x = torch.linalg.norm(x - y[torch.arange(N)[:, None], xi[..., 0]], dim=-1).square()
-        cham_y = torch.linalg.norm(y - x[torch.arange(N)[:, None], yi[..., 0]], dim=-1).square()
+        cham_x = torch.linalg.norm(x - y[torch.arange(N, device=x.device)[:, None], xi[..., 0]], dim=-1).square()
+        cham_y = torch.linalg.norm(y - x[torch.arange(N, device=x.device)[:, None], yi[..., 0]], dim=-1).square()
     elif avoid_in_sequence_collapsing:                                            # :200-239
         assert P1 == P2
-        seq = torch.arange(P1)
+        seq = torch.arange(P1, device=x.device)
         x_nn = knn_points(x, y, lengths1=x_lengths, lengths2=y_lengths, K=2)
         y_nn = knn_points(y, x, lengths1=y_lengths, lengths2=x_lengths, K=2)
         x_self = x_nn.idx[:, :, 0] == seq[None]

@@ -108,3 +108,39 @@ def test_one_launch_adam_matches_torch_adam(weight_decay):
     sd = opt_o.state_dict()
     assert float(sd["state"][0]["step"]) == 6.0
     assert torch.allclose(sd["state"][5]["exp_avg_sq"], opt_r.state[ref[5]]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_a12_reference_on_cuda_vs_reference_on_cpu():
+    """the reference's op sequence (oracle torch modules) on CUDA tensors vs on CPU.  This library must be
+    bit-equal to the CPU reference; the CUDA reference itself may differ in a handful of indices (cuBLAS K = 3 bmm and
+    CUDA reduction order are not the CPU's) -- the test bounds that and bench.py reports the exact counts."""
+    import bench
+    r = bench.a12_check(torch.device("cuda", 0))
+    assert r["ours_fps_eq_cpu_reference"] and r["ours_ball_eq_cpu_reference"], r
+    assert r["fps_mismatching_indices"] <= 0.01 * 4 * 512, r
+    assert r["ball_mismatching_indices"] <= 0.01 * r["ball_total_indices"], r
+
+
+@pytest.mark.gpu
+def test_reference_gpu_arm_computes_the_same_step_as_the_cpu_oracle():
+    """bench.py's same-box arm runs oracle/step_oracle.py on CUDA tensors: its loss must agree with the CPU oracle's
+    (same weights, same batch, same FPS seeds; dropout off), i.e. it times the same computation."""
+    import copy
+    from maskplanner_b200 import synthetic
+    from oracle import step_oracle as SO
+    torch.manual_seed(0)
+    cfg = synthetic.CATEGORIES["windows_v2"]
+    cpu = SO.Regressor(synthetic.out_vectors(cfg["n_pred_traj_points"]), n_stroke_masks=cfg["max_n_strokes"])
+    cpu.dropout.p = 0.0
+    gpu = copy.deepcopy(cpu).cuda()
+    batch = synthetic.make_batch(2, "windows_v2", seed0=3)
+    seeds = (torch.tensor([5, 77]), torch.tensor([1, 300]))
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        l_cpu = SO.train_step(cpu, torch.optim.Adam(cpu.parameters(), lr=1e-3), batch, seeds)
+        l_gpu = SO.train_step(gpu, torch.optim.Adam(gpu.parameters(), lr=1e-3), batch, seeds)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert abs(l_cpu - l_gpu) <= 2e-3 * abs(l_cpu), (l_cpu, l_gpu)

@@ -291,3 +291,57 @@ def test_prefetched_host_batches_give_the_same_losses():
                 losses.append(tr.step_from_host(host[i % 3], seeds[i], next_host_batch=nxt))
             curves.append(losses)
         assert curves[0] == curves[1], (use_graph, curves)
+
+
+def test_graph_replay_follows_lr_scheduler_and_loss_weight_schedule():
+    """after capture only graph.replay() runs, so host-side changes must reach the device scalars the
+    captured kernels read.  (a) a torch LR scheduler accepts optim.Adam (it is a torch.optim.Optimizer) and its lr
+    reaches the replayed Adam kernel: lr = 0 freezes the weights; (b) a rewritten loss weight (delayMasksLoss /
+    PSACDScheduler, train_maskplanner.py:186-199) changes the replayed loss by exactly that term."""
+    from maskplanner_b200 import synthetic
+    from maskplanner_b200.train_step import Trainer
+    B = 4
+    batch = synthetic.make_batch(B, "windows_v2", seed0=50)
+    tr = Trainer("windows_v2", torch.device("cuda", 0), seed=2, use_graph=True, lr=1e-3)
+    tr.model.dropout.p = 0.0
+    sched = torch.optim.lr_scheduler.LambdaLR(tr.opt, lambda epoch: 0.0 if epoch >= 1 else 1.0)
+    gen = torch.Generator().manual_seed(9)
+    seeds = (torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen))
+    dev_batch = tr.to_device(batch)
+    for _ in range(4):                      # 2 eager + capture + 1 replay, lr = 1e-3
+        tr.step(dev_batch, seeds)
+    assert tr._graph is not None
+    w0 = tr.model.fc1.weight.detach().clone()
+    tr.step(dev_batch, seeds)
+    assert not torch.equal(w0, tr.model.fc1.weight)            # lr > 0: the replay moves the weights
+    sched.step()                                               # lr -> 0 on the host only
+    assert tr.opt.param_groups[0]["lr"] == 0.0
+    w1 = tr.model.fc1.weight.detach().clone()
+    l_a = float(tr.step(dev_batch, seeds).item())
+    assert torch.equal(w1, tr.model.fc1.weight)                # the replayed Adam kernel saw lr = 0
+    # loss-weight schedule: drop the point-chamfer weight to 0, the replayed loss must fall by that term
+    from maskplanner_b200 import loss as L
+    with torch.no_grad():
+        pred, masks, scores, _ = tr.model(dev_batch["point_cloud"].permute(0, 2, 1), tuple(s.cuda() for s in seeds))
+    tr.loss_cfg.weight_reverse_asymm_point_chamfer = 0.0
+    l_b = float(tr.step(dev_batch, seeds).item())
+    assert l_b < l_a and abs(l_b - l_a) > 1e-3 * abs(l_a)
+    tr.loss_cfg.weight_reverse_asymm_point_chamfer = 100.0
+    l_c = float(tr.step(dev_batch, seeds).item())
+    assert abs(l_c - l_a) <= 1e-5 * abs(l_a)                   # weights frozen (lr = 0): same loss again
+
+
+def test_stroke_id_validation_and_padding_ids():
+    """ids >= n_pred_masks must raise on the host path instead of silently dropping segments; a padding id
+    (-1) reaching the one-hot contributes an all-zero target row instead of being counted as stroke 0."""
+    from maskplanner_b200 import loss as L
+    ok = torch.tensor([[0., 1., 2., -1.]])
+    L.validate_stroke_ids(ok, 3)
+    with pytest.raises(ValueError):
+        L.validate_stroke_ids(torch.tensor([[0., 3.]]), 3)
+    with pytest.raises(ValueError):
+        L.validate_stroke_ids(torch.tensor([[0., 0.5]]), 3)
+    pm = torch.randn(1, 3, 4, device="cuda")
+    ids = torch.tensor([[0, 1, -1, 1]], device="cuda")
+    cost, present, onehot = L.mask_cost_matrices(pm, ids, 3)
+    assert onehot[0, 2].sum() == 0 and bool(present[0, 0]) and bool(present[0, 1]) and not bool(present[0, 2])

@@ -273,3 +273,14 @@ def test_live_reference_model_and_loss_handler():
                             stroke_ids=batch["stroke_ids"], traj_as_pc=batch["traj_as_pc"].clone())
     lm = SO.asymm_v6_loss(b[0], batch["traj"].clone(), b[1], b[2], batch["stroke_ids"], batch["traj_as_pc"].clone())
     assert torch.equal(lr_, lm)
+
+
+def test_validate_stroke_ids_host_side():
+    """maskplanner_b200.loss.validate_stroke_ids is pure host logic (no CUDA): the Trainer calls it on the host batch."""
+    import pytest as _pt
+    from maskplanner_b200 import loss as L
+    L.validate_stroke_ids(torch.tensor([[0., 21., -1.]]), 22)
+    with _pt.raises(ValueError):
+        L.validate_stroke_ids(torch.tensor([[22.]]), 22)
+    with _pt.raises(ValueError):
+        L.validate_stroke_ids(torch.tensor([[-2.]]), 22)
