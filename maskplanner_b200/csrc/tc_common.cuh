@@ -122,6 +122,29 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n, bool a_mn_major,
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// Instruction descriptor for kind::tf32 (A/B format 2 = TF32: fp32 containers, the low 13 mantissa bits are ignored),
+// FP32 accumulate, M = 128.  UMMA_K = 8 elements (32 bytes).
+__device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n, bool a_mn_major, bool b_mn_major)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// fp32 -> tf32 (round to nearest, ties away), result in an fp32 container with the low 13 mantissa bits zero.
+__device__ __forceinline__ float to_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
