@@ -143,24 +143,31 @@ MPB_API int mpb_knn_points_bwd_f32(const float *p1, const float *p2, int N, int 
                                    int K, const float *grad_dists, float *grad_p1, float *grad_p2,
                                    void *stream);
 
-/* Conv2d/Conv1d 1x1 weight (fp32 [cout, cin], models/pointnet2_utils.py:166-169) -> the two bf16 GEMM
- * operands of the tensor-core path in ONE launch: Wp [cout_p, cin_p] (zero padded) and its transpose
- * Wt [cin_p, cout_p].  xyz_last != 0: the three leading (centred xyz) input channels of the reference's
- * concatenation order (:137) move behind the feature channels, matching mpb_group_points_bf16 rows. */
-MPB_API int mpb_pack_weight_bf16(const float *W, int cout, int cin, int cout_p, int cin_p, int xyz_last,
-                                 void *Wp, void *Wt, void *stream);
-
 /* ---- a7: PointNetSetAbstraction's shared MLP        models/pointnet2_utils.py:208-214 -------------
  * relu(bn(conv1x1(x))) per layer then max over the K neighbours.  The 1x1 conv over [B,C,K,S] is the
- * row-wise GEMM Z[M,Cout] = A[M,Cin] * W[Cout,Cin]^T (M = B*S*K); activations travel as bf16 [M,C]
+ * row-wise GEMM Z[M,Cout] = A[M,Cin] * W[Cout,Cin]^T (M = B*S*K); activations travel as bf16 or fp32 [M,C]
  * row-major with C a multiple of 64 (zero padded), accumulation / statistics in fp32.
  *
  * mpb_group_points_bf16 / _bwd_bf16: a5 emitted as bf16 GEMM rows [B*S*K, ldo], columns in the order
  *                      [feats (D), centred xyz (3), zero padding]; ldo % 8 == 0.  _bwd adds the feature
  *                      columns of grad_out into grad_feats [B,N,D] (fp32, caller zero-fills).
- * mpb_gemm_bf16_tn:    C[M,N] = A[M,K] * B[N,K]^T   (tcgen05 + TMA; K % 64 == 0, N % 32 == 0;
- *                      C is bf16, or fp32 when out_fp32 != 0).  Forward (B = W) and dgrad (A = dZ, B = W^T).
- * mpb_gemm_bf16_wgrad: dW[N,K] (fp32, caller zero-fills) += dZ[M,N]^T * A[M,K]   (K % 64 == 0, N % 8 == 0).
+ * mpb_sa_gemm_tn:      C[M,N] = f(A)[M,K] * B[N,K]^T on tcgen05 + TMA.  Forward (B = W) and dgrad (A = dZ, B = W^T).
+ *                      dtype 0: bf16 operands/outputs (K % 64 == 0); 1: fp32 storage, one TF32 pass; 2: fp32 storage,
+ *                      3xTF32 (hi/lo split of A in shared memory, B_lo = W - tf32(W) supplied by the caller) --
+ *                      the reference-precision mode (K % 32 == 0).  N % 32 == 0.
+ *                      a_scale/a_shift (optional, [K]): f(a) = relu(a_scale[k]*a + a_shift[k]) applied to the A tile
+ *                      between TMA landing and MMA issue -- the previous layer's BatchNorm + ReLU (:211-212), so
+ *                      the normalised activation never exists in HBM.
+ *                      epi 1: also write per-column (sum, sum of squares) partial rows of the stored C (the
+ *                      layer's training-mode BatchNorm statistics); epi 2: also write per-column (sum dY,
+ *                      sum dY*z) with dY = C * [z_scale*z + z_shift > 0] against Z [M,N] (same dtype as C): the
+ *                      BatchNorm-backward statistics of the layer below, fused into the dgrad GEMM.
+ *                      partials: [nparts][2][N] fp32, nparts = mpb_sa_gemm_stat_partials(...) (0: cannot fuse).
+ * mpb_sa_gemm_wgrad:   dW[cout,cin] (fp32, reference layout, overwritten) = crop/unpermute(dZ[M,N]^T * f(A)[M,K]);
+ *                      both operands read as MN-major straight from their row-major layout; the contraction
+ *                      rows are split over CTAs whose partial tiles go to `workspace`
+ *                      (mpb_sa_gemm_wgrad_workspace bytes) and are summed in a fixed order: bitwise reproducible.
+ *                      xyz_last undoes mpb_pack_weight_*'s column permutation.
  * mpb_bn_*:            training-mode BatchNorm2d statistics, normalise + ReLU (+ max-pool with arg-max),
  *                      and the matching backward; `partials` is a [nparts, 2, C] fp32 workspace with
  *                      nparts = mpb_bn_stat_partials(rows, C).  running_mean / running_var are updated in
@@ -172,70 +179,70 @@ MPB_API int mpb_group_points_bf16(const float *xyz, int64_t xsb, int64_t xsn, in
                                   int K, int D, int ldo, void *out, void *stream);
 MPB_API int mpb_group_points_bwd_bf16(const void *grad_out, int ldo, const int64_t *idx, int B,
                                       int N, int S, int K, int D, float *grad_feats, void *stream);
-MPB_API int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, int N, int K,
-                             int out_fp32, void *stream);
-MPB_API int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int M, int N, int K,
-                                void *stream);
-/* Forward GEMM with the layer's BatchNorm statistics fused into the epilogue: besides C (bf16) it writes
- * `nparts` partial rows [2][N] (sum, sum of squares of the stored bf16 values over disjoint row sets) that
- * mpb_bn_finalize_f32 combines.  nparts = mpb_gemm_tn_stat_partials(M,N,K); 0 means the shape cannot be
- * fused (N > 256) and the caller uses mpb_gemm_bf16_tn + mpb_bn_colstats_bf16. */
-MPB_API int mpb_gemm_tn_stat_partials(int M, int N, int K);
-MPB_API int mpb_gemm_bf16_tn_stats(const void *A, const void *B, void *C, int M, int N, int K,
-                                   float *partials, int nparts, void *stream);
+MPB_API int mpb_sa_gemm_stat_partials(int dtype, int M, int N, int K, int xform, int epi);
+MPB_API int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const void *B_lo, void *C, int M,
+                           int N, int K, const float *a_scale, const float *a_shift, int epi,
+                           float *partials, int nparts, const void *Z, const float *z_scale,
+                           const float *z_shift, void *stream);
+MPB_API int64_t mpb_sa_gemm_wgrad_workspace(int dtype, int M, int N, int K, int xform);
+MPB_API int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K,
+                              const float *a_scale, const float *a_shift, float *workspace, int cout,
+                              int cin, int xyz_last, float *dW, void *stream);
 MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
-MPB_API int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *partials, int nparts,
-                                 void *stream);
+/* dtype of the mpb_bn_* / mpb_sa_first_layer* calls: storage type of the activations, 0 = bf16, 1 = fp32. */
+MPB_API int mpb_bn_colstats(int dtype, const void *Z, int64_t M, int C, float *partials, int nparts,
+                            void *stream);
 /* C_valid <= C: channels >= C_valid are alignment padding (scale = shift = 0, no parameter access). */
 MPB_API int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                 const float *bias, const float *gamma, const float *beta,
                                 float *running_mean, float *running_var, float momentum, float eps,
                                 float *scale, float *shift, float *mean, float *rstd, void *stream);
-MPB_API int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *shift, int64_t M,
-                             int C, void *A, void *stream);
+/* A = relu(scale*Z + shift) as a separate pass (A/B switch MPB_FUSE_APPLY=0; the default path applies it inside
+ * the consumer GEMM's operand path instead, mpb_sa_gemm_tn a_scale/a_shift). */
+MPB_API int mpb_bn_relu(int dtype, const void *Z, const float *scale, const float *shift, int64_t M,
+                        int C, void *A, void *stream);
 /* zmax (optional, fp32 [G,C]): the pre-activation Z at the arg-max row, consumed by _bwd_stats (pooled). */
-MPB_API int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const float *shift, int64_t G,
-                                 int K, int C, float *out, int32_t *argmax, float *zmax,
-                                 void *stream);
-/* Backward: exactly one of dA (dense upstream gradient, bf16 [M,C]) and dOut (pooled upstream gradient,
- * fp32 [M/K, C], with argmax and K) is non-NULL. */
-MPB_API int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax,
-                                  const float *zmax, int K, const void *Z, const float *scale,
-                                  const float *shift,
-                                  const float *mean, const float *rstd, int64_t M, int C,
-                                  float *partials, int nparts, void *stream);
-/* clear / clear_count (optional, count a multiple of 4 floats, 16-byte aligned): a buffer this launch
- * also zero-fills -- the fp32 accumulator of the mpb_gemm_bf16_wgrad call that follows, plus any
- * exactly-zero gradients (conv bias under training-mode BatchNorm). */
+MPB_API int mpb_bn_relu_max(int dtype, const void *Z, const float *scale, const float *shift,
+                            int64_t G, int K, int C, float *out, int32_t *argmax, float *zmax,
+                            void *stream);
+/* Backward: exactly one of dA (dense upstream gradient, activation dtype [M,C]) and dOut (pooled upstream
+ * gradient, fp32 [M/K,C], with argmax int32 [M/K,C]) is non-NULL.  partials hold the raw moments
+ * (sum dY, sum dY*z), dY = upstream * [scale*z + shift > 0]; _bwd_finalize turns them into dgamma, dbeta and coef
+ * and zero-fills `clear` (clear_count floats, multiple of 4) as a side job. */
+MPB_API int mpb_bn_bwd_stats(int dtype, const void *dA, const float *dOut, const int32_t *argmax,
+                             const float *zmax, int K, const void *Z, const float *scale,
+                             const float *shift, const float *mean, const float *rstd, int64_t M, int C,
+                             float *partials, int nparts, void *stream);
 MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                     const float *gamma, const float *mean, const float *rstd,
                                     float *dgamma, float *dbeta, float *coef, float *clear,
                                     int64_t clear_count, void *stream);
-MPB_API int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K,
-                                  const void *Z, const float *scale, const float *shift,
-                                  const float *mean, const float *rstd, const float *coef,
-                                  int64_t M, int C, void *dZ, void *stream);
-
-/* Narrow first layer (3 + D <= 8 input channels: SA1 with xyz-only or xyz+normal points, reference :133-138
- * followed by the first conv of :210-212).  The grouped row [feats(D) | centred xyz(3)] is gathered on the fly
- * instead of being written as a 64-column GEMM operand:
- *   forward   Z[M, C] (bf16, M = B*S*K) = bf16(row) . W^T with W = mpb_pack_weight_bf16's Wp (bf16 [C, ldw],
- *             xyz_last order), fp32 accumulation, plus the BatchNorm statistic partials of the stored values
- *             (nparts = mpb_bn_stat_partials(M, C), same format as mpb_bn_colstats_bf16);
- *   backward  dZ as mpb_bn_bwd_apply_bf16 (dense) would form it, reduced on the spot into
- *             dW[C, ldw] (fp32, pre-zeroed, += dZ^T . row); no dZ tensor, no gradient to xyz / feats. */
-MPB_API int mpb_sa_first_layer_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
-                                    const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
-                                    const float *new_xyz, const int64_t *idx, int B, int N, int S, int K,
-                                    int D, const void *W, int ldw, int C, void *Z, float *partials,
-                                    int nparts, void *stream);
-MPB_API int mpb_sa_first_layer_bwd_bf16(const void *dA, const void *Z, const float *scale,
-                                        const float *shift, const float *mean, const float *rstd,
-                                        const float *coef, const float *xyz, int64_t xsb, int64_t xsn,
-                                        int64_t xsc, const float *feats, int64_t fsb, int64_t fsn,
-                                        int64_t fsc, const float *new_xyz, const int64_t *idx, int B,
-                                        int N, int S, int K, int D, int C, float *dW, int ldw,
-                                        void *stream);
+MPB_API int mpb_bn_bwd_apply(int dtype, const void *dA, const float *dOut, const int32_t *argmax, int K,
+                             const void *Z, const float *scale, const float *shift, const float *mean,
+                             const float *rstd, const float *coef, int64_t M, int C, void *dZ,
+                             void *stream);
+/* Weight packing.  _bf16: conv weight fp32 [cout,cin] -> bf16 Wp [cout_p,cin_p] (zero padded; xyz_last moves the 3
+ * leading input channels behind the features) and its transpose Wt.  _tf32: the same as fp32 with the 3xTF32 split,
+ * hi = tf32(w) in (Wp_hi, Wt_hi) and lo = w - hi in (Wp_lo, Wt_lo); both lo pointers NULL: unsplit fp32 copy. */
+MPB_API int mpb_pack_weight_bf16(const float *W, int cout, int cin, int cout_p, int cin_p, int xyz_last,
+                                 void *Wp, void *Wt, void *stream);
+MPB_API int mpb_pack_weight_tf32(const float *W, int cout, int cin, int cout_p, int cin_p, int xyz_last,
+                                 float *Wp_hi, float *Wp_lo, float *Wt_hi, float *Wt_lo, void *stream);
+/* On-the-fly first SA layer (3 + D <= 8 input channels): Z = row . W^T with the row gathered from xyz / feats /
+ * new_xyz / idx (never materialised), BatchNorm statistic partials fused; _bwd re-gathers the row, forms dZ like
+ * mpb_bn_bwd_apply and ACCUMULATES dW [C, ldw] (caller zero-fills).  W [C, ldw] in the activation dtype, xyz-last
+ * column order (fp32: the unsplit weight -- the kernel's CUDA-core FMAs are exact fp32). */
+MPB_API int mpb_sa_first_layer(int dtype, const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc,
+                               const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                               const float *new_xyz, const int64_t *idx, int B, int N, int S, int K,
+                               int D, const void *W, int ldw, int C, void *Z, float *partials,
+                               int nparts, void *stream);
+MPB_API int mpb_sa_first_layer_bwd(int dtype, const void *dA, const void *Z, const float *scale,
+                                   const float *shift, const float *mean, const float *rstd,
+                                   const float *coef, const float *xyz, int64_t xsb, int64_t xsn,
+                                   int64_t xsc, const float *feats, int64_t fsb, int64_t fsn,
+                                   int64_t fsc, const float *new_xyz, const int64_t *idx, int B, int N,
+                                   int S, int K, int D, int C, float *dW, int ldw, void *stream);
 
 /* `padded=True` length scan                             pytorch3d_chamfer.py:138-149 ----------
  * first[n] = first j with y[n,j,0] == sentinel, else P2; *any_flag (int32, caller zero-fills) is

@@ -42,22 +42,23 @@ SIGNATURES = {
     "mpb_padded_lengths_f32": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
     "mpb_group_points_bf16": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mpb_group_points_bwd_bf16": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "mpb_gemm_bf16_tn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
-    "mpb_gemm_bf16_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    "mpb_gemm_tn_stat_partials": (_I, [_I, _I, _I]),
-    "mpb_gemm_bf16_tn_stats": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _P]),
+    "mpb_sa_gemm_stat_partials": (_I, [_I, _I, _I, _I, _I, _I]),
+    "mpb_sa_gemm_tn": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "mpb_sa_gemm_wgrad_workspace": (_L, [_I, _I, _I, _I, _I]),
+    "mpb_sa_gemm_wgrad": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P]),
     "mpb_bn_stat_partials": (_I, [_L, _I]),
-    "mpb_bn_colstats_bf16": (_I, [_P, _L, _I, _P, _I, _P]),
+    "mpb_bn_colstats": (_I, [_I, _P, _L, _I, _P, _I, _P]),
     "mpb_bn_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
-    "mpb_bn_relu_bf16": (_I, [_P, _P, _P, _L, _I, _P, _P]),
-    "mpb_bn_relu_max_bf16": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
-    "mpb_bn_bwd_stats_bf16": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _I, _P]),
+    "mpb_bn_relu": (_I, [_I, _P, _P, _P, _L, _I, _P, _P]),
+    "mpb_bn_relu_max": (_I, [_I, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
+    "mpb_bn_bwd_stats": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _I, _P]),
     "mpb_bn_bwd_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "mpb_pack_weight_bf16": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
-    "mpb_bn_bwd_apply_bf16": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
-    "mpb_sa_first_layer_bf16": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P]),
-    "mpb_sa_first_layer_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I,
-                                        _P, _I, _P]),
+    "mpb_pack_weight_tf32": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mpb_bn_bwd_apply": (_I, [_I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "mpb_sa_first_layer": (_I, [_I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P]),
+    "mpb_sa_first_layer_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I,
+                                   _P, _I, _P]),
     "mpb_adam_step_f32": (_I, [_I, _P, _P, _P, _P, _P, _F, _P, _D, _D, _D, _D, _F, _P, _P, _P]),
     "mpb_lap_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }

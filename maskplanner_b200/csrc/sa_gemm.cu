@@ -1,26 +1,38 @@
 // Shared-MLP GEMMs of PointNetSetAbstraction on 5th-gen tensor cores (sm_100a).
-// Reference: models/pointnet2_utils.py:210-212 -- `conv(new_points)` with a 1x1 Conv2d over the grouped
-// tensor [B, C, K, S] is a row-wise GEMM  Z[M, Cout] = A[M, Cin] * W[Cout, Cin]^T  with M = B*S*K rows.
+// Reference: models/pointnet2_utils.py:210-212 -- `F.relu(bn(conv(new_points)))` with a 1x1 Conv2d over the grouped
+// tensor [B, C, K, S] is a row-wise GEMM  Z[M, Cout] = A[M, Cin] * W[Cout, Cin]^T  with M = B*S*K rows, followed by a
+// per-channel affine + ReLU that this file applies INSIDE the consumer GEMM's operand path instead of a separate pass.
 //
-//   gemm_tn_kernel   : C[M,N] = A[M,K] * B[N,K]^T      forward (B = W) and dgrad (A = dZ, B = W^T)
-//   wgrad_kernel     : dW[N,K] += dZ[M,N]^T * A[M,K]   contraction over the M rows, split across CTAs
+//   gemm_tn_kernel : C[M,N] = f(A)[M,K] * B[N,K]^T       forward (B = W) and dgrad (A = dZ, B = W^T)
+//   wgrad_kernel   : dW[N,K] = dZ[M,N]^T * f(A)[M,K]     contraction over the M rows, split across CTAs,
+//                                                         per-split partial tiles summed in a fixed order (deterministic)
 //
-// Both: bf16 operands, fp32 accumulation in TMEM, operands staged by TMA (SWIZZLE_128B) through a
-// multi-stage mbarrier ring, tcgen05.mma (cta_group::1, UMMA 128 x N x 16) issued by one elected thread,
-// epilogue warps drain TMEM with tcgen05.ld.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM
-// allocator, 4..7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Arithmetic (template parameter DT):
+//   DT_BF16    bf16 operands (tcgen05 kind::f16), fp32 accumulation in TMEM, bf16 output          tolerance 1e-2
+//   DT_TF32    fp32 operands read as TF32 (kind::tf32, one pass: what cuDNN does for the reference on a GPU)
+//   DT_TF32X3  fp32 operands split hi + lo in shared memory, three TF32 products hi*hi + hi*lo + lo*hi,
+//              fp32 accumulation: error ~2^-21 relative per product, the reference-precision mode  tolerance 1e-4
 //
-// gemm_tn: operands are K-major ([rows][64 bf16 = 128 B] swizzle atoms, SBO = 1024 B); persistent over
-// (m-tile, n-tile) pairs with a double-buffered TMEM accumulator so the epilogue of tile i overlaps the
-// MMAs of tile i+1.
-// wgrad:   both operands are read exactly as they sit in HBM (row-major [M, C]) and fed to the tensor
-// core as MN-major operands (contraction index = row), so no transposed copy of dZ or A is ever made.
+// Common structure: operands staged by TMA (SWIZZLE_128B) through a multi-stage mbarrier ring, tcgen05.mma
+// (cta_group::1, UMMA 128 x N x {16 bf16 | 8 tf32}) issued by one elected thread, epilogue warps drain TMEM with
+// tcgen05.ld.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 (+ 8..11 in gemm_tn) =
+// epilogue, and -- new -- a TRANSFORM warpgroup that rewrites the landed A tile in place between the TMA's
+// mbarrier and the MMA issue:
+//     f(a) = relu(scale[k] * a + shift[k])      the previous layer's BatchNorm + ReLU (XFORM), so the normalised
+//                                               activation tensor is never written to or read from HBM;
+//     a -> (tf32(a), a - tf32(a))               the hi/lo split of DT_TF32X3.
+// Epilogue options of gemm_tn: plain store (one TMA store per 128-row x 128-byte block through a swizzled staging
+// tile); + per-column sum / sum of squares of the stored values (forward BatchNorm statistics); + per-column
+// sum dY / sum dY*z with dY = C * [zscale*z + zshift > 0] against a TMA-loaded tile of the previous layer's
+// pre-activation z (the BatchNorm-backward statistics of the layer below, fused into the dgrad GEMM).
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace mpb {
 
 using namespace tc;
+
+enum { DT_BF16 = 0, DT_TF32 = 1, DT_TF32X3 = 2 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -39,8 +51,10 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
-// bf16 row-major [rows, cols] (row stride = ld elements); box = 64 columns (128 B) x box_rows, SWIZZLE_128B.
-static int make_map_bf16(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows)
+// Row-major [rows, cols] matrix of bf16 (esz = 2) or fp32 (esz = 4), row stride = ld elements;
+// box = one 128-byte swizzle row (64 bf16 / 32 fp32 columns) x box_rows, SWIZZLE_128B -- or, atom32, the 32-byte-atom
+// variant (32-byte chunks XOR row & 3) that MN-major 32-bit tensor-core operands require.
+static int make_map(CUtensorMap *map, int esz, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32 = false)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -48,32 +62,32 @@ static int make_map_bf16(CUtensorMap *map, const void *ptr, int64_t rows, int64_
         return MPB_ERR_CUDA;
     }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * (cuuint64_t)esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr),
+                     gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d ptr=%p", (int)r, (long long)rows,
+        set_error("cuTensorMapEncodeTiled failed (%d) esz=%d rows=%lld cols=%lld ld=%lld box_rows=%d ptr=%p", (int)r, esz, (long long)rows,
                   (long long)cols, (long long)ld, box_rows, ptr);
         return MPB_ERR_CUDA;
     }
     return MPB_OK;
 }
 
-constexpr int kGemmThreads = 256;     // wgrad: producer, MMA, allocator, spare + one epilogue warpgroup
-constexpr int kGemmTnThreads = 384;   // gemm_tn: the same + a second epilogue warpgroup
 constexpr int kTileM = 128;
-constexpr int kTileK = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int kABytes = kTileM * 128; // 16 KB per A stage
+constexpr int kABytes = kTileM * 128;   // one 128-row x 128-byte operand / staging tile
 constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxVec = 1024;           // longest per-channel vector (scale/shift) kept in shared memory
 
 struct GemmSmemTail {
     uint64_t full[8];
     uint64_t empty[8];
+    uint64_t ready[8];      // transform warps -> MMA issuer
     uint64_t tfull[2];
     uint64_t tempty[2];
+    uint64_t zfull[2][2];   // [epilogue warpgroup][z staging buffer]
     uint32_t tmem_base;
 };
 
@@ -82,11 +96,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u)
+{
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+}
 
 // Column sums of a 32 x 32 block held one ROW per lane (v[c] = this lane's value in column c): a transpose-reduce
 // butterfly.  Each step halves the live registers -- a lane keeps the half of the columns selected by one bit of its
 // lane index and receives the other lanes' contributions for that half -- so after 16+8+4+2+1 = 31 shuffles lane L
-// holds the sum over all 32 rows of column L.  No shared memory, no atomics.
+// holds the sum over all 32 rows of column L.  No shared memory, no atomics, fixed order (bitwise reproducible).
 __device__ __forceinline__ float warp_column_sum_32x32(float (&v)[32], int lane)
 {
 #pragma unroll
@@ -102,40 +120,116 @@ __device__ __forceinline__ float warp_column_sum_32x32(float (&v)[32], int lane)
     return v[0];
 }
 
-// STATS: additionally accumulate per-column sum / sum of squares of the (bf16-rounded) outputs -- the training-mode
-// BatchNorm statistics of the layer (reference :210-212) -- in the epilogue, so Z is not read again for them.
-// Each epilogue warp keeps its own [2][BN] accumulator in shared memory (lane L owns column 32j+L: no conflicts, no
-// atomics) and writes it as one partial row at the end: partials[(blockIdx.x*8 + epilogue warp)][2][N].
-template <bool OUT_F32, bool STATS>
-__global__ void __launch_bounds__(kGemmTnThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, void *__restrict__ Cout, int M, int N, int K, int BN, int ldc, int stages,
-               float *__restrict__ stat_partials)
+// In-place transform of one 128-byte row chunk set: `row` points at a 128-byte swizzled row (8 chunks of 16 bytes),
+// `r7` = row index & 7 (the swizzle key), `ch0` = channel of the row's first element, `lo` = where the low part of the
+// TF32 split goes (same swizzled offsets in a second tile).  sc/sh: per-channel scale / shift in shared memory.
+template <int DT, bool XFORM, bool ATOM32 = false>
+__device__ __forceinline__ void transform_row(uint8_t *row, uint8_t *row_lo, int r7, const float *sc, const float *sh, bool valid)
 {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        // SWIZZLE_128B: logical 16-byte chunk c sits at physical chunk c ^ (row & 7);
+        // 32-byte-atom variant: logical 32-byte chunk c >> 1 sits at (c >> 1) ^ (row & 3), its two halves stay in order
+        const int off = ATOM32 ? (((((c >> 1) ^ (r7 & 3)) << 1) | (c & 1)) << 4) : ((c ^ r7) << 4);
+        uint4 raw = *reinterpret_cast<const uint4 *>(row + off);
+        if (DT == DT_BF16) {
+            float f[8];
+            float2 t;
+            t = unpack_bf16(raw.x), f[0] = t.x, f[1] = t.y;
+            t = unpack_bf16(raw.y), f[2] = t.x, f[3] = t.y;
+            t = unpack_bf16(raw.z), f[4] = t.x, f[5] = t.y;
+            t = unpack_bf16(raw.w), f[6] = t.x, f[7] = t.y;
+            if (XFORM) {
+                const float4 s0 = *reinterpret_cast<const float4 *>(sc + c * 8), s1 = *reinterpret_cast<const float4 *>(sc + c * 8 + 4);
+                const float4 h0 = *reinterpret_cast<const float4 *>(sh + c * 8), h1 = *reinterpret_cast<const float4 *>(sh + c * 8 + 4);
+                f[0] = fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), f[1] = fmaxf(fmaf(f[1], s0.y, h0.y), 0.f);
+                f[2] = fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), f[3] = fmaxf(fmaf(f[3], s0.w, h0.w), 0.f);
+                f[4] = fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), f[5] = fmaxf(fmaf(f[5], s1.y, h1.y), 0.f);
+                f[6] = fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), f[7] = fmaxf(fmaf(f[7], s1.w, h1.w), 0.f);
+            }
+            if (!valid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = 0.f;
+            }
+            *reinterpret_cast<uint4 *>(row + off) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        } else {
+            float f[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+            if (XFORM) {
+                const float4 s0 = *reinterpret_cast<const float4 *>(sc + c * 4), h0 = *reinterpret_cast<const float4 *>(sh + c * 4);
+                f[0] = fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), f[1] = fmaxf(fmaf(f[1], s0.y, h0.y), 0.f);
+                f[2] = fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), f[3] = fmaxf(fmaf(f[3], s0.w, h0.w), 0.f);
+            }
+            if (!valid) f[0] = f[1] = f[2] = f[3] = 0.f;
+            if (DT == DT_TF32X3) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hi[i] = to_tf32(f[i]), lo[i] = f[i] - hi[i];   // exact difference; the MMA truncates lo to TF32
+                *reinterpret_cast<float4 *>(row + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(row_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            } else {
+                *reinterpret_cast<float4 *>(row + off) = make_float4(f[0], f[1], f[2], f[3]);
+            }
+        }
+    }
+}
+
+struct GemmTnArgs {
+    int M, N, K, BN, stages, out_bufs;
+    const float *a_scale, *a_shift;    // XFORM: A' = relu(a_scale[k] * A + a_shift[k])
+    const float *z_scale, *z_shift;    // EPI 2: relu mask of the layer below
+    float *partials;                   // EPI 1/2: [8 * gridDim.x][2][N]
+};
+
+constexpr int kGemmTnThreads = 384;    // producer, MMA, allocator, spare + two epilogue warpgroups
+constexpr int kGemmTnThreadsXf = 512;  // + the transform warpgroup
+
+// EPI: 0 = store only; 1 = + column sum / sum of squares of the stored values (forward BatchNorm statistics);
+//      2 = + column sum dY / sum dY*z, dY = C * [z_scale*z + z_shift > 0], z = tmZ tile (BatchNorm-backward statistics)
+template <int DT, bool XFORM, int EPI>
+__global__ void __launch_bounds__((XFORM || DT == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const GemmTnArgs p)
+{
+    constexpr bool kXf = XFORM || DT == DT_TF32X3;
+    constexpr int EPR = DT == DT_BF16 ? 64 : 32;          // elements per 128-byte row = columns per k-block and per output block
+    constexpr int NA = DT == DT_TF32X3 ? 2 : 1;           // operand copies per stage (hi, lo)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
-    // [stages x (A | B)] [bf16 path: 2 warpgroups x 2 output staging tiles of 128 rows x 128 B] [barriers]
-    uint8_t *staging = smem + (size_t)stages * stage_bytes;
-    float *stat_acc = reinterpret_cast<float *>(staging + (OUT_F32 ? 0 : 4 * kABytes));          // STATS: [8 warps][2][BN]
-    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(reinterpret_cast<uint8_t *>(stat_acc) + (STATS ? 8 * 2 * 256 * 4 : 0));
-    const int num_kb = K / kTileK;
+    const int M = p.M, N = p.N, K = p.K, BN = p.BN, stages = p.stages;
+    const uint32_t b_bytes = (uint32_t)BN * 128u;
+    const uint32_t stage_bytes = NA * (kABytes + b_bytes);   // [A | A_lo | B | B_lo]
+    uint8_t *staging = smem + (size_t)stages * stage_bytes;                                   // [2 warpgroups][out_bufs] output tiles
+    uint8_t *zstage = staging + (size_t)2 * p.out_bufs * kABytes;                             // EPI 2: [2 warpgroups][2] z tiles
+    float *stat_acc = reinterpret_cast<float *>(zstage + (EPI == 2 ? 4 * kABytes : 0));       // EPI != 0: [8 warps][2][BN]
+    float *vec = stat_acc + (EPI != 0 ? 8 * 2 * 256 : 0);                                     // [a_scale K][a_shift K][z_scale N][z_shift N]
+    float *s_ascale = vec, *s_ashift = vec + (XFORM ? K : 0);
+    float *s_zscale = s_ashift + (XFORM ? K : 0), *s_zshift = s_zscale + (EPI == 2 ? N : 0);
+    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(s_zshift + (EPI == 2 ? N : 0));
+    const int num_kb = K / EPR;
     const int tiles_m = (M + kTileM - 1) / kTileM, tiles_n = N / BN;
     const int total = tiles_m * tiles_n;
 
+    if (XFORM)
+        for (int i = threadIdx.x; i < K; i += blockDim.x) s_ascale[i] = p.a_scale[i], s_ashift[i] = p.a_shift[i];
+    if (EPI == 2)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_zscale[i] = p.z_scale[i], s_zshift[i] = p.z_shift[i];
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmA);
         prefetch_tensormap(&tmB);
+        prefetch_tensormap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&tail->full[s], 1);
             mbar_init(&tail->empty[s], 1);
+            mbar_init(&tail->ready[s], 4);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tail->tfull[a], 1);
             mbar_init(&tail->tempty[a], 4);
+            mbar_init(&tail->zfull[a][0], 1);
+            mbar_init(&tail->zfull[a][1], 1);
         }
         fence_barrier_init();
     }
@@ -153,17 +247,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&tail->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&tail->full[stage], stage_bytes);
+                    mbar_arrive_expect_tx(&tail->full[stage], kABytes + NA * b_bytes);
                     uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                    tma_load_2d(sa, &tmA, kb * kTileK, m0, &tail->full[stage]);
-                    tma_load_2d(sa + kABytes, &tmB, kb * kTileK, n0, &tail->full[stage]);
+                    tma_load_2d(sa, &tmA, kb * EPR, m0, &tail->full[stage]);
+                    tma_load_2d(sa + NA * kABytes, &tmB, kb * EPR, n0, &tail->full[stage]);
+                    if (DT == DT_TF32X3) tma_load_2d(sa + NA * kABytes + b_bytes, &tmBlo, kb * EPR, n0, &tail->full[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16((uint32_t)BN, false, false);
+            const uint32_t idesc = DT == DT_BF16 ? make_idesc_bf16((uint32_t)BN, false, false) : make_idesc_tf32((uint32_t)BN, false, false);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -171,14 +266,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&tail->full[stage], phase);
+                    mbar_wait(&tail->full[stage], phase);              // B (and the raw A) have landed
+                    if (kXf) mbar_wait(&tail->ready[stage], phase);    // A has been rewritten by the transform warps
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(sa + NA * kABytes, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < kTileK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B inside the 128-B swizzle row
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {   // one MMA consumes 32 bytes of every 128-byte row (16 bf16 / 8 tf32)
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        if (DT == DT_BF16) {
+                            umma_bf16(d_tmem, adesc + ko, bdesc + ko, idesc, (kb | k) ? 1u : 0u);
+                        } else if (DT == DT_TF32) {
+                            umma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (kb | k) ? 1u : 0u);
+                        } else {
+                            const uint64_t alo = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+                            const uint64_t blo = make_smem_desc_sw128(sa + NA * kABytes + b_bytes, 16, 1024);
+                            umma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, (kb | k) ? 1u : 0u);   // small terms first
+                            umma_tf32(d_tmem, adesc + ko, blo + ko, idesc, 1u);
+                            umma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);
+                        }
+                    }
                     umma_commit(&tail->empty[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
@@ -186,95 +294,173 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if ((acc ^= 1) == 0) acc_phase ^= 1;
             }
         }
-    } else if (warp >= 4) {
+    } else if (kXf && warp >= 12) {
+        // transform warpgroup: thread t owns row t of the landed A tile
+        const int t = threadIdx.x - 384;
+        const int r7 = t & 7;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * kTileM;
+            const bool valid = m0 + t < M;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&tail->full[stage], phase);
+                uint8_t *row = smem + (size_t)stage * stage_bytes + t * 128;
+                transform_row<DT, XFORM>(row, row + kABytes, r7, s_ascale + kb * EPR, s_ashift + kb * EPR, valid);
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                if (++stage == stages) stage = 0, phase ^= 1;
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
         // Two epilogue warpgroups: warps 4-7 drain accumulator 0 (even tiles of this CTA), warps 8-11 accumulator 1
         // (odd tiles), so TMEM->register->global of one tile overlaps the next tile's drain as well as its MMAs.
         const int ew = warp & 3;           // the TMEM lane quarter this warp may read (warp % 4)
         const int acc = (warp - 4) >> 2;   // accumulator buffer owned by this warpgroup
         uint32_t acc_phase = 0;
-        int t = 0;
-        int nstore = 0;                                 // 64-column blocks stored so far by this warpgroup (staging ring of 2)
-        const bool issuer = ew == 0 && lane == 0;       // the one thread of the warpgroup that owns its bulk-store groups
+        int nblk = 0;                                   // 128-byte column blocks processed so far by this warpgroup
+        const bool issuer = ew == 0 && lane == 0;       // the one thread of the warpgroup that owns its bulk-store groups / z loads
         const int r_in_tile = ew * 32 + lane;
-        float *my_stat = stat_acc + (size_t)(warp - 4) * 2 * BN;
-        if (STATS)
+        const int r7 = r_in_tile & 7;
+        float *my_stat = stat_acc + (size_t)(warp - 4) * 2 * 256;
+        if (EPI != 0)
             for (int c = lane; c < 2 * BN; c += 32) my_stat[c] = 0.f;
+        uint8_t *my_staging = staging + (size_t)acc * p.out_bufs * kABytes;
+        uint8_t *my_z = zstage + (size_t)acc * 2 * kABytes;
+        // z-tile prefetch ring (EPI 2): the issuer keeps two blocks in flight ahead of the warpgroup
+        int z_tile = blockIdx.x + acc * (int)gridDim.x, z_c0 = 0, z_issued = 0;
+        auto issue_z = [&]() {
+            if (z_tile >= total) return;
+            const int zm0 = (z_tile / tiles_n) * kTileM, zn0 = (z_tile % tiles_n) * BN;
+            uint64_t *bar = &tail->zfull[acc][z_issued & 1];
+            mbar_arrive_expect_tx(bar, kABytes);
+            tma_load_2d(my_z + (size_t)(z_issued & 1) * kABytes, &tmZ, zn0 + z_c0, zm0, bar);
+            ++z_issued;
+            z_c0 += EPR;
+            if (z_c0 >= BN) z_c0 = 0, z_tile += 2 * (int)gridDim.x;
+        };
+        if (EPI == 2 && issuer) {
+            issue_z();
+            issue_z();
+        }
+        int t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
             if ((t & 1) != acc) continue;
             const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tail->tfull[acc], acc_phase);
             tc_fence_after();
-            const int row = m0 + r_in_tile;
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(ew * 32) << 16);
-            if (OUT_F32) {
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                    if (row < M) {
-                        float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(Cout) + (size_t)row * ldc + n0 + c0);
-#pragma unroll
-                        for (int v = 0; v < 8; ++v)
-                            dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-                    }
+            for (int c0 = 0; c0 < BN; c0 += EPR, ++nblk) {
+                uint8_t *buf = my_staging + (size_t)(p.out_bufs == 2 ? (nblk & 1) : 0) * kABytes;
+                if (issuer) {                                        // the store that used this buffer has drained its reads
+                    if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tail->tempty[acc]);
-            } else {
-                // bf16: TMEM -> registers -> swizzled staging tile in shared memory -> ONE TMA store per 128 x 64 block
-                // (full 128-byte lines to L2 instead of 32 half-sector writes per warp instruction)
-                for (int c0 = 0; c0 < BN; c0 += 64, ++nstore) {
-                    uint8_t *buf = staging + (size_t)(acc * 2 + (nstore & 1)) * kABytes;
-                    if (issuer) bulk_wait_read<1>();                 // the store that used this buffer two blocks ago has drained
-                    named_bar_sync(1 + acc, 128);
-                    uint8_t *rowp = buf + r_in_tile * 128;
+                const uint8_t *zrow = my_z + (size_t)(nblk & 1) * kABytes + r_in_tile * 128;
+                if (EPI == 2) mbar_wait(&tail->zfull[acc][nblk & 1], (uint32_t)(nblk >> 1) & 1u);
+                named_bar_sync(1 + acc, 128);
+                uint8_t *rowp = buf + r_in_tile * 128;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (c0 + 32 * h < BN) {
-                            uint32_t r[32];
-                            tmem_ld_32x32(taddr + (uint32_t)(c0 + 32 * h), r);
+                for (int h = 0; h < EPR / 32; ++h) {                 // 32 accumulator columns per TMEM load
+                    if (c0 + 32 * h < BN) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + (uint32_t)(c0 + 32 * h), r);
+                        float zv[32], zq[32];
+                        if (DT == DT_BF16) {
                             uint32_t pk[16];
 #pragma unroll
                             for (int v = 0; v < 16; ++v) pk[v] = pack_bf16(__uint_as_float(r[2 * v]), __uint_as_float(r[2 * v + 1]));
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
-                                const int chunk = (4 * h + v) ^ (r_in_tile & 7);   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+                                const int chunk = (4 * h + v) ^ r7;   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
                                 *reinterpret_cast<uint4 *>(rowp + chunk * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
                             }
-                            if (STATS) {   // statistics of exactly what was stored (rows past M are zero: TMA zero-fills A)
-                                float zv[32], zq[32];
+                            if (EPI != 0) {   // statistics of exactly what was stored
 #pragma unroll
                                 for (int v = 0; v < 16; ++v) {
-                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk[v]));
+                                    const float2 f = unpack_bf16(pk[v]);
                                     zv[2 * v] = f.x, zv[2 * v + 1] = f.y;
-                                    zq[2 * v] = f.x * f.x, zq[2 * v + 1] = f.y * f.y;
                                 }
-                                const float cs = warp_column_sum_32x32(zv, lane), cq = warp_column_sum_32x32(zq, lane);
-                                my_stat[c0 + 32 * h + lane] += cs;
-                                my_stat[BN + c0 + 32 * h + lane] += cq;
+                            }
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < 8; ++v) {
+                                const int chunk = v ^ r7;
+                                *reinterpret_cast<uint4 *>(rowp + chunk * 16) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                            }
+                            if (EPI != 0) {
+#pragma unroll
+                                for (int v = 0; v < 32; ++v) zv[v] = __uint_as_float(r[v]);
                             }
                         }
+                        if (EPI == 1) {
+#pragma unroll
+                            for (int v = 0; v < 32; ++v) zq[v] = zv[v] * zv[v];
+                        }
+                        if (EPI == 2) {   // dY = C * [relu mask of the layer below]; second moment against the raw pre-activation z
+                            const float *zs = s_zscale + n0 + c0 + 32 * h, *zh = s_zshift + n0 + c0 + 32 * h;
+                            if (DT == DT_BF16) {
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) {
+                                    const uint4 zr = *reinterpret_cast<const uint4 *>(zrow + (((4 * h + v) ^ r7) << 4));
+                                    const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float2 z2 = unpack_bf16(zw[u]);
+                                        const int j = 8 * v + 2 * u;
+                                        const float d0 = fmaf(z2.x, zs[j], zh[j]) > 0.f ? zv[j] : 0.f;
+                                        const float d1 = fmaf(z2.y, zs[j + 1], zh[j + 1]) > 0.f ? zv[j + 1] : 0.f;
+                                        zv[j] = d0, zv[j + 1] = d1;
+                                        zq[j] = d0 * z2.x, zq[j + 1] = d1 * z2.y;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < 8; ++v) {
+                                    const float4 z4 = *reinterpret_cast<const float4 *>(zrow + ((v ^ r7) << 4));
+                                    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const int j = 4 * v + u;
+                                        const float d0 = fmaf(zz[u], zs[j], zh[j]) > 0.f ? zv[j] : 0.f;
+                                        zv[j] = d0;
+                                        zq[j] = d0 * zz[u];
+                                    }
+                                }
+                            }
+                        }
+                        if (EPI != 0) {
+                            const float cs = warp_column_sum_32x32(zv, lane), cq = warp_column_sum_32x32(zq, lane);
+                            my_stat[c0 + 32 * h + lane] += cs;
+                            my_stat[BN + c0 + 32 * h + lane] += cq;
+                        }
                     }
-                    if (c0 + 64 >= BN) {                               // accumulator fully drained: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tail->tempty[acc]);
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + acc, 128);
-                    if (issuer) {
-                        tma_store_2d(&tmC, buf, n0 + c0, m0);
-                        bulk_commit();
-                    }
+                }
+                if (c0 + EPR >= BN) {                              // accumulator fully drained: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + acc, 128);                      // staging tile complete, z tile fully read
+                if (issuer) {
+                    tma_store_2d(&tmC, buf, n0 + c0, m0);
+                    bulk_commit();
+                    if (EPI == 2) issue_z();                        // refill the z buffer this block just released
                 }
             }
             acc_phase ^= 1;
         }
-        if (!OUT_F32 && issuer) bulk_wait<0>();          // all stores complete before the CTA (and its shared memory) goes away
-        if (STATS) {
-            float *dst = stat_partials + ((size_t)blockIdx.x * 8 + (warp - 4)) * 2 * N;      // tiles_n == 1 here: BN == N
-            for (int c = lane; c < 2 * BN; c += 32) dst[c] = my_stat[c];
+        if (issuer) bulk_wait<0>();          // all stores complete before the CTA (and its shared memory) goes away
+        if (EPI != 0) {
+            // one partial row per epilogue warp; a CTA always owns the same column tile (gridDim.x % tiles_n == 0)
+            const int n0 = ((int)blockIdx.x % tiles_n) * BN;
+            float *dst = p.partials + ((size_t)blockIdx.x * 8 + (warp - 4)) * 2 * N;
+            for (int c = lane; c < N; c += 32) {
+                const bool mine = c >= n0 && c < n0 + BN;
+                dst[c] = mine ? my_stat[c - n0] : 0.f;
+                dst[N + c] = mine ? my_stat[BN + c - n0] : 0.f;
+            }
         }
     }
     tc_fence_before();
@@ -282,28 +468,55 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// dW[n0 + i, k0 + j] += sum_{m in this CTA's row range} dZ[m, n0 + i] * A[m, k0 + j]
+// ---- weight gradient ------------------------------------------------------------------------------------------------
+// dW_partial[ms][n0 + i, k0 + j] = sum_{m in split ms} dZ[m, n0 + i] * f(A)[m, k0 + j]
+// Both operands are read exactly as they sit in HBM (row-major [M, C]) and fed to the tensor core as MN-major
+// operands (contraction index = row), so no transposed copy of dZ or A is ever made.
 // blockIdx.x = ((n_tile * k_tiles) + k_tile) * m_splits + m_split
-__global__ void __launch_bounds__(kGemmThreads, 2)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmA, float *__restrict__ dW, int M,
-             int N, int K, int ldw, int k_tiles, int m_splits, int rows_per_split, int stages)
+struct WgradArgs {
+    int M, N, K, k_tiles, m_splits, rows_per_split, stages;
+    const float *a_scale, *a_shift;   // XFORM on A
+    float *partials;                  // [m_splits][N_pad128][K] fp32
+    int n_pad;
+};
+
+constexpr int kWgradThreads = 256;
+constexpr int kWgradThreadsXf = 384;
+
+template <int DT, bool XFORM>
+__global__ void __launch_bounds__((XFORM || DT == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads, DT == DT_BF16 ? 2 : 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmA, const WgradArgs p)
 {
+    constexpr bool kXf = XFORM || DT == DT_TF32X3;
+    constexpr int EPR = DT == DT_BF16 ? 64 : 32;          // channels per 128-byte box row
+    constexpr int RB = DT == DT_BF16 ? 64 : 32;           // contraction rows per stage
+    constexpr int kBox = RB * 128;                        // one box: RB rows x 128 bytes
+    constexpr int KT = DT == DT_BF16 ? 256 : 128;         // A channels (dW columns) per CTA
+    constexpr int ZB = 128 / EPR;                         // dZ boxes per stage (128 channels)
+    constexpr int AB = KT / EPR;                          // A boxes per stage (max)
+    constexpr int NA = DT == DT_TF32X3 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ms = blockIdx.x % m_splits;
-    const int kt = (blockIdx.x / m_splits) % k_tiles;
-    const int nt = blockIdx.x / (m_splits * k_tiles);
-    const int n0 = nt * 128, k0 = kt * 256;
-    const int NU = min(256, K - k0);                 // multiple of 64
-    const int a_boxes = min(2, (N - n0 + 63) / 64);   // 64-channel boxes of dZ that hold real data
-    const int b_boxes = NU / 64;
-    constexpr int kBox = 64 * 128;                    // 64 rows x 128 B
-    const uint32_t stage_bytes = (uint32_t)(2 + b_boxes) * kBox;
-    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(smem + (size_t)stages * stage_bytes);
-    const int m_begin = ms * rows_per_split, m_end = min(M, m_begin + rows_per_split);
-    const int num_rb = m_end > m_begin ? (m_end - m_begin + 63) / 64 : 0;
+    const int M = p.M, N = p.N, K = p.K, stages = p.stages;
+    const int ms = blockIdx.x % p.m_splits;
+    const int kt = (blockIdx.x / p.m_splits) % p.k_tiles;
+    const int nt = blockIdx.x / (p.m_splits * p.k_tiles);
+    const int n0 = nt * 128, k0 = kt * KT;
+    const int NU = min(KT, K - k0);                       // multiple of EPR
+    const int a_boxes = min(ZB, (N - n0 + EPR - 1) / EPR);   // boxes of dZ that hold real data
+    const int b_boxes = NU / EPR;
+    // stage layout: [dZ boxes (ZB)] [A boxes (AB)] and, for the split, the same again for the low parts
+    const uint32_t half_bytes = (uint32_t)(ZB + AB) * kBox;
+    const uint32_t stage_bytes = NA * half_bytes;
+    float *s_ascale = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes);
+    float *s_ashift = s_ascale + (XFORM ? KT : 0);
+    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(s_ashift + (XFORM ? KT : 0));
+    const int m_begin = ms * p.rows_per_split, m_end = min(M, m_begin + p.rows_per_split);
+    const int num_rb = m_end > m_begin ? (m_end - m_begin + RB - 1) / RB : 0;
 
+    if (XFORM)
+        for (int i = threadIdx.x; i < NU; i += blockDim.x) s_ascale[i] = p.a_scale[k0 + i], s_ashift[i] = p.a_shift[k0 + i];
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmZ);
         prefetch_tensormap(&tmA);
@@ -312,6 +525,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
         for (int s = 0; s < stages; ++s) {
             mbar_init(&tail->full[s], 1);
             mbar_init(&tail->empty[s], 1);
+            mbar_init(&tail->ready[s], 4);
         }
         mbar_init(&tail->tfull[0], 1);
         fence_barrier_init();
@@ -331,51 +545,98 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
                     mbar_wait(&tail->empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&tail->full[stage], (uint32_t)(a_boxes + b_boxes) * kBox);
                     uint8_t *s = smem + (size_t)stage * stage_bytes;
-                    const int r0 = m_begin + rb * 64;  // rows past m_end but < M belong to the next split: mask below
-                    for (int b = 0; b < a_boxes; ++b) tma_load_2d(s + b * kBox, &tmZ, n0 + b * 64, r0, &tail->full[stage]);
-                    for (int b = 0; b < b_boxes; ++b) tma_load_2d(s + (2 + b) * kBox, &tmA, k0 + b * 64, r0, &tail->full[stage]);
+                    const int r0 = m_begin + rb * RB;   // rows_per_split is a multiple of RB: a box never straddles two splits
+                    for (int b = 0; b < a_boxes; ++b) tma_load_2d(s + b * kBox, &tmZ, n0 + b * EPR, r0, &tail->full[stage]);
+                    for (int b = 0; b < b_boxes; ++b) tma_load_2d(s + (ZB + b) * kBox, &tmA, k0 + b * EPR, r0, &tail->full[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
             }
         } else if (warp == 1) {
             if (lane == 0) {
-                const uint32_t idesc = make_idesc_bf16((uint32_t)NU, true, true);
+                const uint32_t idesc = DT == DT_BF16 ? make_idesc_bf16((uint32_t)NU, true, true) : make_idesc_tf32((uint32_t)NU, true, true);
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int rb = 0; rb < num_rb; ++rb) {
                     mbar_wait(&tail->full[stage], phase);
+                    if (kXf) mbar_wait(&tail->ready[stage], phase);
                     tc_fence_after();
                     const uint32_t s = smem_u32(smem + (size_t)stage * stage_bytes);
-                    // MN-major SWIZZLE_128B: LBO = distance between 64-channel column blocks (one box),
+                    // MN-major SWIZZLE_128B: LBO = distance between EPR-channel column blocks (one box),
                     // SBO = distance between 8-row groups along the contraction (1024 B)
-                    const uint64_t adesc = make_smem_desc_sw128(s, kBox, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(s + 2 * kBox, kBox, 1024);
+                    // (32-bit operands: the 32-byte-atom swizzle, whose pattern repeats every 4 rows -> SBO = 512 B)
+                    constexpr uint32_t kLt = DT == DT_BF16 ? 2u : 1u, kSbo = DT == DT_BF16 ? 1024u : 512u;
+                    const uint64_t adesc = make_smem_desc(s, kBox, kSbo, kLt);
+                    const uint64_t bdesc = make_smem_desc(s + ZB * kBox, kBox, kSbo, kLt);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)   // 16 contraction rows per MMA = two 8-row groups = 2048 B
-                        umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (rb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        // one MMA: 16 contraction rows (bf16) = 2048 B, 8 rows (tf32) = 1024 B
+                        const uint64_t ko = (uint64_t)(k * (DT == DT_BF16 ? 128 : 64));
+                        if (DT == DT_BF16) {
+                            umma_bf16(tmem_base, adesc + ko, bdesc + ko, idesc, (rb | k) ? 1u : 0u);
+                        } else if (DT == DT_TF32) {
+                            umma_tf32(tmem_base, adesc + ko, bdesc + ko, idesc, (rb | k) ? 1u : 0u);
+                        } else {
+                            const uint64_t alo = make_smem_desc(s + half_bytes, kBox, kSbo, kLt);
+                            const uint64_t blo = make_smem_desc(s + half_bytes + ZB * kBox, kBox, kSbo, kLt);
+                            umma_tf32(tmem_base, alo + ko, bdesc + ko, idesc, (rb | k) ? 1u : 0u);
+                            umma_tf32(tmem_base, adesc + ko, blo + ko, idesc, 1u);
+                            umma_tf32(tmem_base, adesc + ko, bdesc + ko, idesc, 1u);
+                        }
+                    }
                     umma_commit(&tail->empty[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
                 umma_commit(&tail->tfull[0]);
             }
-        } else if (warp >= 4) {
-            const int ew = warp - 4;
+        } else if (kXf && warp >= 8) {
+            // transform warpgroup: 128 threads walk the (box, row) pairs of the stage that need rewriting
+            const int t = threadIdx.x - 256;
+            int stage = 0;
+            uint32_t phase = 0;
+            const int first_box = DT == DT_TF32X3 ? 0 : ZB;            // bf16 / single-pass tf32: only the A boxes change
+            for (int rb = 0; rb < num_rb; ++rb) {
+                mbar_wait(&tail->full[stage], phase);
+                uint8_t *s = smem + (size_t)stage * stage_bytes;
+                const int r0 = m_begin + rb * RB;
+                for (int item = t; item < (ZB + AB) * RB; item += 128) {
+                    const int box = item / RB, r = item - box * RB;
+                    if (box < first_box) continue;
+                    if (box < ZB ? (box >= a_boxes) : (box - ZB >= b_boxes)) continue;
+                    uint8_t *row = s + (size_t)box * kBox + r * 128;
+                    const bool is_a = box >= ZB;
+                    const float *sc = s_ascale + (is_a ? (box - ZB) * EPR : 0), *sh = s_ashift + (is_a ? (box - ZB) * EPR : 0);
+                    // rows past M were zero-filled by the TMA; they must stay zero through relu(shift)
+                    const bool valid = r0 + r < M;
+                    if (XFORM && is_a)
+                        transform_row<DT, true, DT != DT_BF16>(row, row + half_bytes, r & 7, sc, sh, valid);
+                    else
+                        transform_row<DT, false, DT != DT_BF16>(row, row + half_bytes, r & 7, sc, sh, valid);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                if (++stage == stages) stage = 0, phase ^= 1;
+            }
+        }
+    }
+    if (warp >= 4 && warp < 8) {
+        const int ew = warp - 4;
+        const int row = n0 + ew * 32 + lane;
+        float *dst_row = p.partials + ((size_t)ms * p.n_pad + row) * K + k0;
+        if (num_rb > 0) {
             mbar_wait(&tail->tfull[0], 0);
             tc_fence_after();
-            const int row = n0 + ew * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
             for (int c0 = 0; c0 < NU; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                if (row < N) {
-                    float *dst = dW + (size_t)row * ldw + k0 + c0;
 #pragma unroll
-                    for (int v = 0; v < 32; v += 4)   // 16-byte vector reductions (RED.E.ADD.F32x4)
-                        atomicAdd(reinterpret_cast<float4 *>(dst + v),
-                                  make_float4(__uint_as_float(r[v]), __uint_as_float(r[v + 1]), __uint_as_float(r[v + 2]),
-                                              __uint_as_float(r[v + 3])));
-                }
+                for (int v = 0; v < 32; v += 4)
+                    *reinterpret_cast<float4 *>(dst_row + c0 + v) = make_float4(__uint_as_float(r[v]), __uint_as_float(r[v + 1]),
+                                                                                __uint_as_float(r[v + 2]), __uint_as_float(r[v + 3]));
             }
+        } else {
+            for (int c0 = 0; c0 < NU; c0 += 4) *reinterpret_cast<float4 *>(dst_row + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     tc_fence_before();
@@ -383,118 +644,240 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
     if (warp == 2) tmem_dealloc<256>(tmem_base);
 }
 
-// Columns per tile: the whole N when it fits one UMMA (N <= 256, multiple of 32); otherwise the largest multiple of
-// 64 dividing N (the bf16 epilogue stores whole 64-column blocks, which must not straddle two tiles).
-static int pick_bn(int N)
+// dW[r, c] = sum over splits (fixed order) of the partial tiles, cropped to the real [cout, cin] and with the packed
+// column order undone (xyz_last: the three coordinate channels were moved behind the features by the weight packing).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float *__restrict__ partials, int m_splits, int n_pad, int K, int cout, int cin, int xyz_last, float *__restrict__ dW)
 {
-    if (N <= 256) return N % 32 == 0 ? N : 0;
-    for (int bn = 256; bn >= 64; bn -= 64)
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= cout * cin) return;
+    const int r = e / cin, c = e - r * cin;
+    const int pc = (xyz_last && cin > 3) ? (c < 3 ? cin - 3 + c : c - 3) : c;
+    const float *src = partials + (size_t)r * K + pc;
+    const size_t stride = (size_t)n_pad * K;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = 0;
+    for (; i + 4 <= m_splits; i += 4) {        // four interleaved chains (loads in flight), combined in a fixed order
+        s0 += src[(size_t)i * stride];
+        s1 += src[(size_t)(i + 1) * stride];
+        s2 += src[(size_t)(i + 2) * stride];
+        s3 += src[(size_t)(i + 3) * stride];
+    }
+    for (; i < m_splits; ++i) s0 += src[(size_t)i * stride];
+    dW[e] = (s0 + s1) + (s2 + s3);
+}
+
+// Columns per tile: the whole N when it fits one UMMA (N <= cap, multiple of 32); otherwise the largest multiple of
+// the 128-byte block width dividing N.
+static int pick_bn(int N, int cap, int blk)
+{
+    if (N <= cap) return N % 32 == 0 ? N : 0;
+    for (int bn = cap; bn >= blk; bn -= blk)
         if (N % bn == 0) return bn;
     return 0;
 }
 
-}  // namespace mpb
+struct TnPlan {
+    int BN, stages, out_bufs, grid, threads;
+    size_t smem;
+};
 
-namespace mpb {
-static int gemm_tn_launch(const void *A, const void *B, void *C, int M, int N, int K, int out_fp32, float *stat_partials, int nparts,
-                          void *stream);
-}
-
-extern "C" int mpb_gemm_bf16_tn(const void *A, const void *B, void *C, int M, int N, int K, int out_fp32, void *stream)
+static bool plan_gemm_tn(int dt, bool xform, int epi, int M, int N, int K, TnPlan *pl)
 {
-    return mpb::gemm_tn_launch(A, B, C, M, N, K, out_fp32, nullptr, 0, stream);
-}
-
-// Number of [2][N] partial rows mpb_gemm_bf16_tn_stats writes (0: this shape cannot fuse the statistics).
-extern "C" int mpb_gemm_tn_stat_partials(int M, int N, int K)
-{
-    if (M <= 0 || N <= 0 || N > 256 || N % 32 || K % 64) return 0;
-    const int tiles = (M + mpb::kTileM - 1) / mpb::kTileM;
-    return 8 * (tiles < mpb::sm_count() ? tiles : mpb::sm_count());
-}
-
-extern "C" int mpb_gemm_bf16_tn_stats(const void *A, const void *B, void *C, int M, int N, int K, float *partials, int nparts,
-                                      void *stream)
-{
-    using namespace mpb;
-    MPB_REQUIRE(partials && nparts > 0 && nparts == mpb_gemm_tn_stat_partials(M, N, K), "partials / nparts mismatch");
-    return gemm_tn_launch(A, B, C, M, N, K, 0, partials, nparts, stream);
-}
-
-static int mpb::gemm_tn_launch(const void *A, const void *B, void *C, int M, int N, int K, int out_fp32, float *stat_partials,
-                               int nparts, void *stream)
-{
-    using namespace mpb;
-    MPB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad size");
-    if (M == 0) return MPB_OK;
-    MPB_REQUIRE(A && B && C, "null pointer");
-    MPB_REQUIRE(K % 64 == 0, "K must be a multiple of 64 (pad the operands)");
-    const int BN = pick_bn(N);
-    MPB_REQUIRE(BN > 0, "N must be a multiple of 32");
-    MPB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
-    MPB_REQUIRE(BN == N || BN % 64 == 0, "N > 256 must be a multiple of 64");
-    CUtensorMap tmA, tmB, tmC;
-    int rc = make_map_bf16(&tmA, A, M, K, K, kTileM);
-    if (rc) return rc;
-    rc = make_map_bf16(&tmB, B, N, K, K, BN);
-    if (rc) return rc;
-    const int stage_bytes = kABytes + BN * 128;
-    const int staging_bytes = (out_fp32 ? 0 : 4 * kABytes)    // bf16 output: 2 warpgroups x 2 staging tiles for the TMA stores
-                              + (stat_partials ? 8 * 2 * 256 * 4 : 0);   // fused statistics: 8 warps x [2][256] floats
-    int stages = (224 * 1024 - staging_bytes) / stage_bytes;
-    stages = stages > 8 ? 8 : stages;
-    const size_t smem = (size_t)stages * stage_bytes + staging_bytes + sizeof(GemmSmemTail) + 1024;
-    const int tiles = ((M + kTileM - 1) / kTileM) * (N / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    cudaStream_t st = (cudaStream_t)stream;
-    if (out_fp32) {
-        auto kern = gemm_tn_kernel<true, false>;
-        MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-        kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmA, C, M, N, K, BN, N, stages, nullptr);
-    } else {
-        rc = make_map_bf16(&tmC, C, M, N, N, kTileM);          // output tiles: 128 rows x 64 columns, SWIZZLE_128B
-        if (rc) return rc;
-        if (stat_partials) {
-            MPB_REQUIRE(BN == N && nparts == 8 * grid, "fused statistics need a single column tile");
-            auto kern = gemm_tn_kernel<false, true>;
-            MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-            kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmC, C, M, N, K, BN, N, stages, stat_partials);
-        } else {
-            auto kern = gemm_tn_kernel<false, false>;
-            MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-            kern<<<grid, kGemmTnThreads, smem, st>>>(tmA, tmB, tmC, C, M, N, K, BN, N, stages, nullptr);
-        }
+    const int epr = dt == DT_BF16 ? 64 : 32;
+    const int na = dt == DT_TF32X3 ? 2 : 1;
+    if (M <= 0 || N <= 0 || K <= 0 || K % epr || N % 32 || (xform && K > kMaxVec) || (epi == 2 && N > kMaxVec)) return false;
+    const int bn = pick_bn(N, dt == DT_TF32X3 ? 128 : 256, epr);
+    if (bn <= 0 || (bn != N && bn % epr)) return false;
+    if (dt != DT_BF16 && bn % 32) return false;
+    const int stage_bytes = na * (kABytes + bn * 128);
+    const int fixed0 = (epi == 2 ? 4 * kABytes : 0) + (epi != 0 ? 8 * 2 * 256 * 4 : 0) + (xform ? 2 * K * 4 : 0) + (epi == 2 ? 2 * N * 4 : 0) +
+                       (int)sizeof(GemmSmemTail) + 1024;
+    int out_bufs = 2;
+    int stages = (227 * 1024 - fixed0 - 2 * out_bufs * kABytes) / stage_bytes;
+    if (stages < 3) {
+        out_bufs = 1;
+        stages = (227 * 1024 - fixed0 - 2 * out_bufs * kABytes) / stage_bytes;
     }
+    if (stages < 2) return false;
+    stages = stages > 8 ? 8 : stages;
+    const int tiles_n = N / bn;
+    const int tiles = ((M + kTileM - 1) / kTileM) * tiles_n;
+    int grid = tiles < sm_count() ? tiles : sm_count();
+    grid = grid / tiles_n * tiles_n;       // a CTA always owns the same column tile (statistics partial rows)
+    if (grid < tiles_n) return false;
+    pl->BN = bn, pl->stages = stages, pl->out_bufs = out_bufs, pl->grid = grid;
+    pl->threads = (xform || dt == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads;
+    pl->smem = (size_t)stages * stage_bytes + 2 * out_bufs * kABytes + fixed0;
+    return true;
+}
+
+template <int DT, bool XFORM, int EPI>
+static int launch_tn(const TnPlan &pl, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmBlo, const CUtensorMap &tmC,
+                     const CUtensorMap &tmZ, const GemmTnArgs &args, cudaStream_t st)
+{
+    auto kern = gemm_tn_kernel<DT, XFORM, EPI>;
+    MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
+    kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmA, tmB, tmBlo, tmC, tmZ, args);
     return check_launch("gemm_tn_kernel");
 }
 
-extern "C" int mpb_gemm_bf16_wgrad(const void *dZ, const void *A, float *dW, int M, int N, int K, void *stream)
+}  // namespace mpb
+
+// Number of [2][N] partial rows a fused-statistics launch writes (0: this shape cannot fuse the statistics).
+extern "C" int mpb_sa_gemm_stat_partials(int dtype, int M, int N, int K, int xform, int epi)
+{
+    mpb::TnPlan pl;
+    if (epi == 0 || !mpb::plan_gemm_tn(dtype, xform != 0, epi, M, N, K, &pl)) return 0;
+    return 8 * pl.grid;
+}
+
+extern "C" int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const void *B_lo, void *C, int M, int N, int K,
+                              const float *a_scale, const float *a_shift, int epi, float *partials, int nparts, const void *Z,
+                              const float *z_scale, const float *z_shift, void *stream)
 {
     using namespace mpb;
+    MPB_REQUIRE(dtype >= DT_BF16 && dtype <= DT_TF32X3, "dtype must be 0 (bf16), 1 (tf32) or 2 (tf32x3)");
     MPB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad size");
     if (M == 0) return MPB_OK;
-    MPB_REQUIRE(dZ && A && dW, "null pointer");
-    MPB_REQUIRE(N % 8 == 0 && K % 64 == 0, "N must be a multiple of 8 and K a multiple of 64");
-    MPB_REQUIRE(((uintptr_t)dZ & 15) == 0 && ((uintptr_t)A & 15) == 0, "operands must be 16-byte aligned");
-    CUtensorMap tmZ, tmA;
-    int rc = make_map_bf16(&tmZ, dZ, M, N, N, 64);
+    MPB_REQUIRE(A && B && C, "null pointer");
+    MPB_REQUIRE(dtype != DT_TF32X3 || B_lo, "tf32x3 needs the low part of B");
+    MPB_REQUIRE((a_scale != nullptr) == (a_shift != nullptr), "a_scale / a_shift must come together");
+    MPB_REQUIRE(epi >= 0 && epi <= 2, "epi must be 0, 1 or 2");
+    MPB_REQUIRE(epi == 0 || partials, "statistics need a partials buffer");
+    MPB_REQUIRE(epi != 2 || (Z && z_scale && z_shift), "epi 2 needs Z, z_scale, z_shift");
+    MPB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
+    const bool xform = a_scale != nullptr;
+    TnPlan pl;
+    MPB_REQUIRE(plan_gemm_tn(dtype, xform, epi, M, N, K, &pl), "unsupported shape (K multiple of 64 bf16 / 32 tf32, N multiple of 32, tiles must fit)");
+    MPB_REQUIRE(epi == 0 || nparts == 8 * pl.grid, "nparts mismatch (ask mpb_sa_gemm_stat_partials)");
+    const int esz = dtype == DT_BF16 ? 2 : 4;
+    CUtensorMap tmA, tmB, tmBlo, tmC, tmZ;
+    int rc = make_map(&tmA, esz, A, M, K, K, kTileM);
     if (rc) return rc;
-    rc = make_map_bf16(&tmA, A, M, K, K, 64);
+    rc = make_map(&tmB, esz, B, N, K, K, pl.BN);
     if (rc) return rc;
-    const int n_tiles = (N + 127) / 128, k_tiles = (K + 255) / 256;
-    const int row_blocks = (M + 63) / 64;
-    int m_splits = (2 * sm_count()) / (n_tiles * k_tiles);
+    tmBlo = tmB;
+    if (dtype == DT_TF32X3) {
+        rc = make_map(&tmBlo, esz, B_lo, N, K, K, pl.BN);
+        if (rc) return rc;
+    }
+    rc = make_map(&tmC, esz, C, M, N, N, kTileM);
+    if (rc) return rc;
+    tmZ = tmC;
+    if (epi == 2) {
+        rc = make_map(&tmZ, esz, Z, M, N, N, kTileM);
+        if (rc) return rc;
+    }
+    GemmTnArgs args;
+    args.M = M, args.N = N, args.K = K, args.BN = pl.BN, args.stages = pl.stages, args.out_bufs = pl.out_bufs;
+    args.a_scale = a_scale, args.a_shift = a_shift, args.z_scale = z_scale, args.z_shift = z_shift, args.partials = partials;
+    cudaStream_t st = (cudaStream_t)stream;
+#define MPB_TN_CASE(DT, XF, EP) \
+    if (dtype == DT && xform == XF && epi == EP) return launch_tn<DT, XF, EP>(pl, tmA, tmB, tmBlo, tmC, tmZ, args, st)
+    MPB_TN_CASE(DT_BF16, false, 0);
+    MPB_TN_CASE(DT_BF16, false, 1);
+    MPB_TN_CASE(DT_BF16, false, 2);
+    MPB_TN_CASE(DT_BF16, true, 0);
+    MPB_TN_CASE(DT_BF16, true, 1);
+    MPB_TN_CASE(DT_TF32, false, 0);
+    MPB_TN_CASE(DT_TF32, false, 1);
+    MPB_TN_CASE(DT_TF32, false, 2);
+    MPB_TN_CASE(DT_TF32, true, 0);
+    MPB_TN_CASE(DT_TF32, true, 1);
+    MPB_TN_CASE(DT_TF32X3, false, 0);
+    MPB_TN_CASE(DT_TF32X3, false, 1);
+    MPB_TN_CASE(DT_TF32X3, false, 2);
+    MPB_TN_CASE(DT_TF32X3, true, 0);
+    MPB_TN_CASE(DT_TF32X3, true, 1);
+#undef MPB_TN_CASE
+    set_error("mpb_sa_gemm_tn: combination dtype=%d xform=%d epi=%d not built", dtype, (int)xform, epi);
+    return MPB_ERR_UNSUPPORTED;
+}
+
+namespace mpb {
+struct WgPlan {
+    int n_tiles, k_tiles, m_splits, rows_per_split, stages, n_pad, threads, grid;
+    size_t smem;
+};
+static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl)
+{
+    const int epr = dt == DT_BF16 ? 64 : 32, rb = dt == DT_BF16 ? 64 : 32, kt = dt == DT_BF16 ? 256 : 128;
+    const int na = dt == DT_TF32X3 ? 2 : 1;
+    if (M <= 0 || N <= 0 || K <= 0 || N % 8 || K % epr) return false;
+    pl->n_tiles = (N + 127) / 128, pl->k_tiles = (K + kt - 1) / kt;
+    const int row_blocks = (M + rb - 1) / rb;
+    const int per_sm = dt == DT_BF16 ? 2 : 1;
+    int m_splits = (per_sm * sm_count()) / (pl->n_tiles * pl->k_tiles);
     m_splits = m_splits < 1 ? 1 : (m_splits > row_blocks ? row_blocks : m_splits);
-    const int rows_per_split = ((row_blocks + m_splits - 1) / m_splits) * 64;
-    m_splits = (M + rows_per_split - 1) / rows_per_split;
-    // stage = 64 contraction rows x (128 dZ channels + up to 256 A channels); sized so that two CTAs share an SM
-    // (one CTA's TMEM drain + reductions overlap the other's loads)
-    const int stage_bytes = (2 + (K < 256 ? K : 256) / 64) * 64 * 128;
-    int stages = (100 * 1024) / stage_bytes;
+    pl->rows_per_split = ((row_blocks + m_splits - 1) / m_splits) * rb;
+    pl->m_splits = (M + pl->rows_per_split - 1) / pl->rows_per_split;
+    const int box = rb * 128;
+    const int stage_bytes = na * (128 / epr + kt / epr) * box;
+    const int budget = dt == DT_BF16 ? 100 * 1024 : 200 * 1024;
+    int stages = budget / stage_bytes;
     stages = stages < 2 ? 2 : (stages > 4 ? 4 : stages);
-    const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmSmemTail) + 1024;
-    MPB_ENSURE_DYN_SMEM(wgrad_kernel, 227 * 1024);
-    wgrad_kernel<<<n_tiles * k_tiles * m_splits, kGemmThreads, smem, (cudaStream_t)stream>>>(tmZ, tmA, dW, M, N, K, K, k_tiles, m_splits,
-                                                                                            rows_per_split, stages);
+    pl->stages = stages;
+    pl->n_pad = pl->n_tiles * 128;
+    pl->threads = (xform || dt == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads;
+    pl->grid = pl->n_tiles * pl->k_tiles * pl->m_splits;
+    pl->smem = (size_t)stages * stage_bytes + (xform ? 2 * kt * 4 : 0) + sizeof(GemmSmemTail) + 1024;
+    return pl->smem <= 227 * 1024;
+}
+template <int DT, bool XFORM>
+static int launch_wg(const WgPlan &pl, const CUtensorMap &tmZ, const CUtensorMap &tmA, const WgradArgs &args, cudaStream_t st)
+{
+    auto kern = wgrad_kernel<DT, XFORM>;
+    MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
+    kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmZ, tmA, args);
     return check_launch("wgrad_kernel");
 }
+}  // namespace mpb
+
+// Bytes of fp32 workspace the weight-gradient call needs for its per-split partial tiles.
+extern "C" int64_t mpb_sa_gemm_wgrad_workspace(int dtype, int M, int N, int K, int xform)
+{
+    mpb::WgPlan pl;
+    if (!mpb::plan_wgrad(dtype, xform != 0, M, N, K, &pl)) return -1;
+    return (int64_t)pl.m_splits * pl.n_pad * K * 4;
+}
+
+extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K, const float *a_scale,
+                                 const float *a_shift, float *workspace, int cout, int cin, int xyz_last, float *dW, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(dtype >= DT_BF16 && dtype <= DT_TF32X3, "dtype must be 0 (bf16), 1 (tf32) or 2 (tf32x3)");
+    MPB_REQUIRE(M > 0 && N > 0 && K > 0, "bad size");
+    MPB_REQUIRE(dZ && A && dW && workspace, "null pointer");
+    MPB_REQUIRE((a_scale != nullptr) == (a_shift != nullptr), "a_scale / a_shift must come together");
+    MPB_REQUIRE(cout > 0 && cout <= N && cin > 0 && cin <= K, "cout / cin must fit the padded operand widths");
+    MPB_REQUIRE(((uintptr_t)dZ & 15) == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "operands must be 16-byte aligned");
+    const bool xform = a_scale != nullptr;
+    WgPlan pl;
+    MPB_REQUIRE(plan_wgrad(dtype, xform, M, N, K, &pl), "unsupported shape (N multiple of 8, K multiple of 64 bf16 / 32 tf32)");
+    const int esz = dtype == DT_BF16 ? 2 : 4;
+    const int rb = dtype == DT_BF16 ? 64 : 32;
+    CUtensorMap tmZ, tmA;
+    int rc = make_map(&tmZ, esz, dZ, M, N, N, rb, dtype != DT_BF16);
+    if (rc) return rc;
+    rc = make_map(&tmA, esz, A, M, K, K, rb, dtype != DT_BF16);
+    if (rc) return rc;
+    WgradArgs args;
+    args.M = M, args.N = N, args.K = K, args.k_tiles = pl.k_tiles, args.m_splits = pl.m_splits, args.rows_per_split = pl.rows_per_split;
+    args.stages = pl.stages, args.a_scale = a_scale, args.a_shift = a_shift, args.partials = workspace, args.n_pad = pl.n_pad;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = MPB_ERR_UNSUPPORTED;
+#define MPB_WG_CASE(DT, XF) \
+    if (dtype == DT && xform == XF) rc = launch_wg<DT, XF>(pl, tmZ, tmA, args, st)
+    MPB_WG_CASE(DT_BF16, false);
+    MPB_WG_CASE(DT_BF16, true);
+    MPB_WG_CASE(DT_TF32, false);
+    MPB_WG_CASE(DT_TF32, true);
+    MPB_WG_CASE(DT_TF32X3, false);
+    MPB_WG_CASE(DT_TF32X3, true);
+#undef MPB_WG_CASE
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<(cout * cin + 255) / 256, 256, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, dW);
+    return check_launch("wgrad_reduce_kernel");
+}
+

@@ -23,25 +23,64 @@
 
 namespace mpb {
 
-__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8])
-{
-    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+// Storage type of the activations: bf16 (tensor-core path, tolerance 1e-2) or fp32 (TF32 / 3xTF32 path, tolerance 1e-4).
+// A thread always handles 8 consecutive channels of a row: one 16-byte access for bf16, two for fp32.
+template <class T>
+struct Act;
+template <>
+struct Act<__nv_bfloat16> {
+    typedef uint4 raw_t;
+    static __device__ __forceinline__ raw_t ld(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+    static __device__ __forceinline__ void st(__nv_bfloat16 *p, const raw_t &v) { *reinterpret_cast<uint4 *>(p) = v; }
+    static __device__ __forceinline__ void unpack(const raw_t &v, float (&f)[8])
+    {
+        const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 t = __bfloat1622float2(p[i]);
-        f[2 * i] = t.x;
-        f[2 * i + 1] = t.y;
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __bfloat1622float2(p[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
     }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8])
-{
-    uint4 v;
-    __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+    static __device__ __forceinline__ raw_t pack(const float (&f)[8])
+    {
+        uint4 v;
+        __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    return v;
-}
-__device__ __forceinline__ uint4 ld16(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+        for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        return v;
+    }
+    static __device__ __forceinline__ float round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }   // what a store keeps
+    static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+template <>
+struct Act<float> {
+    struct raw_t {
+        float4 a, b;
+    };
+    static __device__ __forceinline__ raw_t ld(const float *p)
+    {
+        raw_t r;
+        r.a = *reinterpret_cast<const float4 *>(p), r.b = *reinterpret_cast<const float4 *>(p + 4);
+        return r;
+    }
+    static __device__ __forceinline__ void st(float *p, const raw_t &v)
+    {
+        *reinterpret_cast<float4 *>(p) = v.a, *reinterpret_cast<float4 *>(p + 4) = v.b;
+    }
+    static __device__ __forceinline__ void unpack(const raw_t &v, float (&f)[8])
+    {
+        f[0] = v.a.x, f[1] = v.a.y, f[2] = v.a.z, f[3] = v.a.w, f[4] = v.b.x, f[5] = v.b.y, f[6] = v.b.z, f[7] = v.b.w;
+    }
+    static __device__ __forceinline__ raw_t pack(const float (&f)[8])
+    {
+        raw_t r;
+        r.a = make_float4(f[0], f[1], f[2], f[3]), r.b = make_float4(f[4], f[5], f[6], f[7]);
+        return r;
+    }
+    static __device__ __forceinline__ float round(float v) { return v; }
+    static __device__ __forceinline__ float to_float(float v) { return v; }
+};
 __device__ __forceinline__ void load8(const float *__restrict__ p, float (&f)[8])
 {
     const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
@@ -112,19 +151,20 @@ __device__ __forceinline__ void column_sums(int64_t M, int C, float *__restrict_
     }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
-colstats_kernel(const __nv_bfloat16 *__restrict__ Z, int64_t M, int C, float *__restrict__ partials)
+colstats_kernel(const T *__restrict__ Z, int64_t M, int C, float *__restrict__ partials)
 {
     column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
-        uint4 raw[kRowUnroll];
+        typename Act<T>::raw_t raw[kRowUnroll];
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
-            if (u < nr) raw[u] = ld16(Z + (r + u * stride) * C + c0);
+            if (u < nr) raw[u] = Act<T>::ld(Z + (r + u * stride) * C + c0);
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
             if (u < nr) {
                 float z[8];
-                unpack8(raw[u], z);
+                Act<T>::unpack(raw[u], z);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     s0[i] += z[i];
@@ -208,9 +248,10 @@ bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_
 }
 
 // ---- forward elementwise ---------------------------------------------------------------------------
+template <class T>
 __global__ void __launch_bounds__(kEwThreads)
-bn_relu_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t M, int C,
-               __nv_bfloat16 *__restrict__ A)
+bn_relu_kernel(const T *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t M, int C,
+               T *__restrict__ A)
 {
     const RowWalk w(C);
     if (!w.active) return;
@@ -220,26 +261,27 @@ bn_relu_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ sc
     load8(shift + c0, sh);
     const int64_t stride = w.rpp, r_end = slab_end(M, w.rpp);
     for (int64_t r = slab_begin(M, w.rpp) + w.tr; r < r_end; r += kRowUnroll * stride) {
-        uint4 raw[kRowUnroll];
+        typename Act<T>::raw_t raw[kRowUnroll];
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
-            if (r + u * stride < r_end) raw[u] = ld16(Z + (r + u * stride) * C + c0);
+            if (r + u * stride < r_end) raw[u] = Act<T>::ld(Z + (r + u * stride) * C + c0);
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
             if (r + u * stride < r_end) {
                 float z[8];
-                unpack8(raw[u], z);
+                Act<T>::unpack(raw[u], z);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[i] = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
-                *reinterpret_cast<uint4 *>(A + (r + u * stride) * C + c0) = pack8(z);
+                Act<T>::st(A + (r + u * stride) * C + c0, Act<T>::pack(z));
             }
     }
 }
 
 constexpr int kMaxUnroll = 4;   // rows in flight per thread in the pooling kernel (8 was measured no faster)
 // out[g, c] = max_k relu(scale*Z[g*K + k, c] + shift); arg[g, c] = first k attaining it (torch.max semantics).
+template <class T>
 __global__ void __launch_bounds__(kEwThreads)
-bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
+bn_relu_max_kernel(const T *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
                    int K, int C, float *__restrict__ out, int *__restrict__ arg, float *__restrict__ zmax)
 {
     const RowWalk w(C);
@@ -253,17 +295,17 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
         int bi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0, bz[i] = 0.f;
-        const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
+        const T *zp = Z + (g * K) * C + c0;
         for (int k = 0; k < K; k += kMaxUnroll) {
-            uint4 raw[kMaxUnroll];
+            typename Act<T>::raw_t raw[kMaxUnroll];
 #pragma unroll
             for (int u = 0; u < kMaxUnroll; ++u)
-                if (k + u < K) raw[u] = ld16(zp + (int64_t)(k + u) * C);
+                if (k + u < K) raw[u] = Act<T>::ld(zp + (int64_t)(k + u) * C);
 #pragma unroll
             for (int u = 0; u < kMaxUnroll; ++u)
                 if (k + u < K) {
                     float z[8];
-                    unpack8(raw[u], z);
+                    Act<T>::unpack(raw[u], z);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
@@ -288,8 +330,9 @@ bn_relu_max_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict_
 // Few groups, many rows per group (SA3: G = batch size, K = 128): one 1024-thread CTA per group, the K rows are
 // interleaved over 1024/(C/8) segments and the per-segment (max, arg, z) triples meet in shared memory.
 constexpr int kWideThreads = 1024;
+template <class T>
 __global__ void __launch_bounds__(kWideThreads)
-bn_relu_max_wide_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
+bn_relu_max_wide_kernel(const T *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
                         int K, int C, float *__restrict__ out, int *__restrict__ arg, float *__restrict__ zmax)
 {
     extern __shared__ float sm_wide[];           // [3][segments][C]: best, arg (as int bits), z
@@ -310,17 +353,17 @@ bn_relu_max_wide_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__rest
 #pragma unroll
         for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0, bz[i] = 0.f;
         if (active) {
-            const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
+            const T *zp = Z + (g * K) * C + c0;
             for (int k = seg; k < K; k += kRowUnroll * nseg) {
-                uint4 raw[kRowUnroll];
+                typename Act<T>::raw_t raw[kRowUnroll];
 #pragma unroll
                 for (int u = 0; u < kRowUnroll; ++u)
-                    if (k + u * nseg < K) raw[u] = ld16(zp + (int64_t)(k + u * nseg) * C);
+                    if (k + u * nseg < K) raw[u] = Act<T>::ld(zp + (int64_t)(k + u * nseg) * C);
 #pragma unroll
                 for (int u = 0; u < kRowUnroll; ++u)
                     if (k + u * nseg < K) {
                         float z[8];
-                        unpack8(raw[u], z);
+                        Act<T>::unpack(raw[u], z);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
@@ -363,8 +406,9 @@ bn_relu_max_wide_kernel(const __nv_bfloat16 *__restrict__ Z, const float *__rest
 }
 
 // ---- backward --------------------------------------------------------------------------------------
+template <class T>
 __global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
-bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale,
+bwd_stats_dense_kernel(const T *__restrict__ dA, const T *__restrict__ Z, const float *__restrict__ scale,
                        const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd, int64_t M,
                        int C, float *__restrict__ partials)
 {
@@ -374,19 +418,19 @@ bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
     load8(shift + c00, sh);
     (void)mean, (void)rstd;
     column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
-        uint4 rz[kRowUnroll], rd[kRowUnroll];
+        typename Act<T>::raw_t rz[kRowUnroll], rd[kRowUnroll];
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
             if (u < nr) {
-                rz[u] = ld16(Z + (r + u * stride) * C + c0);
-                rd[u] = ld16(dA + (r + u * stride) * C + c0);
+                rz[u] = Act<T>::ld(Z + (r + u * stride) * C + c0);
+                rd[u] = Act<T>::ld(dA + (r + u * stride) * C + c0);
             }
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
             if (u < nr) {
                 float z[8], d[8];
-                unpack8(rz[u], z);
-                unpack8(rd[u], d);
+                Act<T>::unpack(rz[u], z);
+                Act<T>::unpack(rd[u], d);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {   // raw moments sum dY, sum dY*z; the finalize kernel turns them into sum dY*zhat in fp64
                     const float dy = fmaf(z[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
@@ -398,8 +442,9 @@ bwd_stats_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
 }
 
 // Upstream gradient is the pooled one: only the arg-max row of each (group, channel) carries dOut.
+template <class T>
 __global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
-bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, const __nv_bfloat16 *__restrict__ Z,
+bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, const T *__restrict__ Z,
                         const float *__restrict__ zmax, const float *__restrict__ scale, const float *__restrict__ shift,
                         const float *__restrict__ mean, const float *__restrict__ rstd, int64_t G, int K, int C,
                         float *__restrict__ partials)
@@ -410,7 +455,7 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = c0 + i;
-                const float z = zmax ? zmax[g * C + c] : __bfloat162float(Z[(g * K + arg[g * C + c]) * C + c]);
+                const float z = zmax ? zmax[g * C + c] : Act<T>::to_float(Z[(g * K + arg[g * C + c]) * C + c]);
                 const float dy = fmaf(z, scale[c], shift[c]) > 0.f ? dOut[g * C + c] : 0.f;
                 s0[i] += dy;
                 s1[i] = fmaf(dy, z, s1[i]);
@@ -468,10 +513,11 @@ struct ApplyConst {
     }
 };
 
+template <class T>
 __global__ void __launch_bounds__(kEwThreads)
-bwd_apply_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z, const float *__restrict__ scale,
+bwd_apply_dense_kernel(const T *__restrict__ dA, const T *__restrict__ Z, const float *__restrict__ scale,
                        const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
-                       const float *__restrict__ coef, int64_t M, int C, __nv_bfloat16 *__restrict__ dZ)
+                       const float *__restrict__ coef, int64_t M, int C, T *__restrict__ dZ)
 {
     const RowWalk w(C);
     if (!w.active) return;
@@ -480,35 +526,36 @@ bwd_apply_dense_kernel(const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16
     k.load(scale, shift, mean, rstd, coef, C, c0);
     const int64_t stride = w.rpp, r_end = slab_end(M, w.rpp);
     for (int64_t r = slab_begin(M, w.rpp) + w.tr; r < r_end; r += kRowUnroll * stride) {
-        uint4 rz[kRowUnroll], rd[kRowUnroll];
+        typename Act<T>::raw_t rz[kRowUnroll], rd[kRowUnroll];
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
             if (r + u * stride < r_end) {
-                rz[u] = ld16(Z + (r + u * stride) * C + c0);
-                rd[u] = ld16(dA + (r + u * stride) * C + c0);
+                rz[u] = Act<T>::ld(Z + (r + u * stride) * C + c0);
+                rd[u] = Act<T>::ld(dA + (r + u * stride) * C + c0);
             }
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
             if (r + u * stride < r_end) {
                 float z[8], d[8];
-                unpack8(rz[u], z);
-                unpack8(rd[u], d);
+                Act<T>::unpack(rz[u], z);
+                Act<T>::unpack(rd[u], d);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float dy = fmaf(z[i], k.sc[i], k.sh[i]) > 0.f ? d[i] : 0.f;
                     d[i] = fmaf(k.p[i], dy, fmaf(-k.w[i], z[i], k.e[i]));
                 }
-                *reinterpret_cast<uint4 *>(dZ + (r + u * stride) * C + c0) = pack8(d);
+                Act<T>::st(dZ + (r + u * stride) * C + c0, Act<T>::pack(d));
             }
     }
 }
 
 // Pooled upstream gradient: a thread owns (group, 8 channels), loads arg-max / dOut once and walks the K rows.
+template <class T>
 __global__ void __launch_bounds__(kEwThreads)
-bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, int K, const __nv_bfloat16 *__restrict__ Z,
+bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, int K, const T *__restrict__ Z,
                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                         const float *__restrict__ rstd, const float *__restrict__ coef, int64_t G, int C,
-                        __nv_bfloat16 *__restrict__ dZ)
+                        T *__restrict__ dZ)
 {
     const RowWalk w(C);
     if (!w.active) return;
@@ -526,24 +573,24 @@ bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
             const int4 a = *reinterpret_cast<const int4 *>(arg + g * C + c0), b = *reinterpret_cast<const int4 *>(arg + g * C + c0 + 4);
             am[0] = a.x, am[1] = a.y, am[2] = a.z, am[3] = a.w, am[4] = b.x, am[5] = b.y, am[6] = b.z, am[7] = b.w;
         }
-        const __nv_bfloat16 *zp = Z + (g * K) * C + c0;
-        __nv_bfloat16 *dp = dZ + (g * K) * C + c0;
+        const T *zp = Z + (g * K) * C + c0;
+        T *dp = dZ + (g * K) * C + c0;
         for (int kk = kb; kk < ke; kk += kRowUnroll) {
-            uint4 raw[kRowUnroll];
+            typename Act<T>::raw_t raw[kRowUnroll];
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u)
-                if (kk + u < ke) raw[u] = ld16(zp + (int64_t)(kk + u) * C);
+                if (kk + u < ke) raw[u] = Act<T>::ld(zp + (int64_t)(kk + u) * C);
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u)
                 if (kk + u < ke) {
                     float z[8], d[8];
-                    unpack8(raw[u], z);
+                    Act<T>::unpack(raw[u], z);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float dy = (am[i] == kk + u && fmaf(z[i], k.sc[i], k.sh[i]) > 0.f) ? go[i] : 0.f;
                         d[i] = fmaf(k.p[i], dy, fmaf(-k.w[i], z[i], k.e[i]));
                     }
-                    *reinterpret_cast<uint4 *>(dp + (int64_t)(kk + u) * C) = pack8(d);
+                    Act<T>::st(dp + (int64_t)(kk + u) * C, Act<T>::pack(d));
                 }
         }
     }
@@ -566,7 +613,7 @@ struct NarrowRows {   // element strides are validated to fit 31 bits on the hos
     int N, S, K, D;
 };
 
-template <int CIN>
+template <class T, int CIN>
 __device__ __forceinline__ void gather_narrow_row(const NarrowRows &g, uint32_t row, float (&a)[CIN])
 {
 #pragma unroll
@@ -582,7 +629,7 @@ __device__ __forceinline__ void gather_narrow_row(const NarrowRows &g, uint32_t 
             v = g.feats[b * g.fsb + i * g.fsn + k * g.fsc];
         else if (k < g.D + 3)
             v = __fsub_rn(g.xyz[b * g.xsb + i * g.xsn + (k - g.D) * g.xsc], g.new_xyz[(int64_t)bs * 3 + (k - g.D)]);
-        a[k] = __bfloat162float(__float2bfloat16_rn(v));
+        a[k] = Act<T>::round(v);
     }
 }
 
@@ -612,6 +659,7 @@ struct RowCursor {
 // The gather is split into phases so that the loads of the kRowUnroll rows in flight are independent of each other
 // (index loads, then coordinate loads, then the exchange): one dependent chain per row made the first version
 // latency-bound at 2 CTAs/SM.
+template <class T>
 __device__ __forceinline__ float narrow_component(const NarrowRows &g, int64_t i, uint32_t b, uint32_t bs, int sub)
 {
     float v = 0.f;
@@ -621,7 +669,7 @@ __device__ __forceinline__ float narrow_component(const NarrowRows &g, int64_t i
             v = g.feats[(int64_t)(int32_t)b * g.fsb + (int64_t)i32 * g.fsn + sub * g.fsc];
         else
             v = __fsub_rn(g.xyz[(int64_t)(int32_t)b * g.xsb + (int64_t)i32 * g.xsn + (sub - g.D) * g.xsc], g.new_xyz[bs * 3u + (uint32_t)(sub - g.D)]);
-        v = __bfloat162float(__float2bfloat16_rn(v));
+        v = Act<T>::round(v);
     }
     return v;
 }
@@ -633,9 +681,9 @@ __device__ __forceinline__ void narrow_exchange(float v, unsigned gmask, int gba
 }
 
 // SHARE: C/8 divides the warp, the cooperative gather above applies; otherwise every thread gathers for itself.
-template <int CIN, bool SHARE>
+template <class T, int CIN, bool SHARE>
 __global__ void __launch_bounds__(kEwThreads)
-narrow_first_layer_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ W, int ldw, int64_t M, int C, __nv_bfloat16 *__restrict__ Z,
+narrow_first_layer_kernel(NarrowRows g, const T *__restrict__ W, int ldw, int64_t M, int C, T *__restrict__ Z,
                           float *__restrict__ partials)
 {
     const int cg = C >> 3;
@@ -647,7 +695,7 @@ narrow_first_layer_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ W, int
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < CIN; ++k)
-            w2[j][k] = make_float2(__bfloat162float(W[(size_t)(c00 + 2 * j) * ldw + k]), __bfloat162float(W[(size_t)(c00 + 2 * j + 1) * ldw + k]));
+            w2[j][k] = make_float2(Act<T>::to_float(W[(size_t)(c00 + 2 * j) * ldw + k]), Act<T>::to_float(W[(size_t)(c00 + 2 * j + 1) * ldw + k]));
     RowCursor cur;
     bool started = false;
     column_sums(M, C, partials, [&](int64_t r, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
@@ -665,7 +713,7 @@ narrow_first_layer_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ W, int
                 }
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u)
-                if (u < nr) comp[u] = narrow_component(g, ii[u], cb[u], cbs[u], sub);
+                if (u < nr) comp[u] = narrow_component<T>(g, ii[u], cb[u], cbs[u], sub);
         }
 #pragma unroll
         for (int u = 0; u < kRowUnroll; ++u)
@@ -675,31 +723,29 @@ narrow_first_layer_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ W, int
                 if (SHARE)
                     narrow_exchange<CIN>(comp[u], gmask, gbase, a);
                 else
-                    gather_narrow_row<CIN>(g, (uint32_t)row, a);
-                uint4 pk;
-                __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                    gather_narrow_row<T, CIN>(g, (uint32_t)row, a);
+                float zf[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float2 acc = __fmul2_rn(make_float2(a[0], a[0]), w2[j][0]);
 #pragma unroll
                     for (int k = 1; k < CIN; ++k) acc = __ffma2_rn(make_float2(a[k], a[k]), w2[j][k], acc);
-                    pp[j] = __floats2bfloat162_rn(acc.x, acc.y);
+                    zf[2 * j] = Act<T>::round(acc.x), zf[2 * j + 1] = Act<T>::round(acc.y);
                 }
-                *reinterpret_cast<uint4 *>(Z + row * C + c0) = pk;
+                Act<T>::st(Z + row * C + c0, Act<T>::pack(zf));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {   // statistics of the STORED (bf16) values, like the fused GEMM epilogue
-                    const float2 z = __bfloat1622float2(pp[j]);
-                    s0[2 * j] += z.x, s0[2 * j + 1] += z.y;
-                    s1[2 * j] = fmaf(z.x, z.x, s1[2 * j]), s1[2 * j + 1] = fmaf(z.y, z.y, s1[2 * j + 1]);
+                for (int i = 0; i < 8; ++i) {   // statistics of the STORED values, like the fused GEMM epilogue
+                    s0[i] += zf[i];
+                    s1[i] = fmaf(zf[i], zf[i], s1[i]);
                 }
             }
     });
 }
 
 constexpr int kNarrowBwdUnroll = 2;   // 4 rows in flight spill at 128 registers (2 CTAs/SM)
-template <int CIN, bool SHARE>
+template <class T, int CIN, bool SHARE>
 __global__ void __launch_bounds__(kEwThreads, 2)
-narrow_first_layer_bwd_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ dA, const __nv_bfloat16 *__restrict__ Z,
+narrow_first_layer_bwd_kernel(NarrowRows g, const T *__restrict__ dA, const T *__restrict__ Z,
                               const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                               const float *__restrict__ rstd, const float *__restrict__ coef, int64_t M, int C, float *__restrict__ dW,
                               int ldw)
@@ -724,15 +770,15 @@ narrow_first_layer_bwd_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ dA
         RowCursor cur;
         if (SHARE && r < r_end) cur.init(g, (uint32_t)r);
         for (; r < r_end; r += kNarrowBwdUnroll * stride) {
-            uint4 rz[kNarrowBwdUnroll], rd[kNarrowBwdUnroll];
+            typename Act<T>::raw_t rz[kNarrowBwdUnroll], rd[kNarrowBwdUnroll];
             int64_t ii[kNarrowBwdUnroll];
             uint32_t cb[kNarrowBwdUnroll], cbs[kNarrowBwdUnroll];
             float comp[kNarrowBwdUnroll];
 #pragma unroll
             for (int u = 0; u < kNarrowBwdUnroll; ++u)
                 if (r + u * stride < r_end) {
-                    rz[u] = ld16(Z + (r + u * stride) * C + c0);
-                    rd[u] = ld16(dA + (r + u * stride) * C + c0);
+                    rz[u] = Act<T>::ld(Z + (r + u * stride) * C + c0);
+                    rd[u] = Act<T>::ld(dA + (r + u * stride) * C + c0);
                     if (SHARE) {
                         ii[u] = g.idx[r + u * stride];
                         cb[u] = cur.b, cbs[u] = cur.bs;
@@ -742,18 +788,18 @@ narrow_first_layer_bwd_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ dA
             if (SHARE) {
 #pragma unroll
                 for (int u = 0; u < kNarrowBwdUnroll; ++u)
-                    if (r + u * stride < r_end) comp[u] = narrow_component(g, ii[u], cb[u], cbs[u], sub);
+                    if (r + u * stride < r_end) comp[u] = narrow_component<T>(g, ii[u], cb[u], cbs[u], sub);
             }
 #pragma unroll
             for (int u = 0; u < kNarrowBwdUnroll; ++u)
                 if (r + u * stride < r_end) {
                     float z[8], d[8], a[CIN];
-                    unpack8(rz[u], z);
-                    unpack8(rd[u], d);
+                    Act<T>::unpack(rz[u], z);
+                    Act<T>::unpack(rd[u], d);
                     if (SHARE)
                         narrow_exchange<CIN>(comp[u], gmask, gbase, a);
                     else
-                        gather_narrow_row<CIN>(g, (uint32_t)(r + u * stride), a);
+                        gather_narrow_row<T, CIN>(g, (uint32_t)(r + u * stride), a);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float dy = fmaf(z[i], k.sc[i], k.sh[i]) > 0.f ? d[i] : 0.f;
@@ -761,8 +807,8 @@ narrow_first_layer_bwd_kernel(NarrowRows g, const __nv_bfloat16 *__restrict__ dA
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        // the tensor-core path feeds dZ to its weight-gradient GEMM in bf16: same rounding here
-                        const float2 dz = __bfloat1622float2(__floats2bfloat162_rn(d[2 * j], d[2 * j + 1]));
+                        // the tensor-core path feeds dZ to its weight-gradient GEMM in the storage type: same rounding here
+                        const float2 dz = make_float2(Act<T>::round(d[2 * j]), Act<T>::round(d[2 * j + 1]));
 #pragma unroll
                         for (int q = 0; q < CIN; ++q) acc[j][q] = __ffma2_rn(dz, make_float2(a[q], a[q]), acc[j][q]);
                     }
@@ -791,29 +837,31 @@ static inline int stat_parts(int64_t rows, int C) { return row_blocks(rows, C, k
 // dynamic shared memory of a column_sums kernel: one [2][C] slot per row lane of the CTA (16 KB when C/8 divides 256)
 static inline size_t stat_smem(int C) { return (size_t)(kEwThreads / (C >> 3)) * 2 * C * sizeof(float); }
 
-// Resident CTAs per SM of an elementwise kernel (cached per call site; a host-side query, legal during graph capture).
-#define MPB_RESIDENT_PER_SM(kernel)                                                       \
-    ([&]() -> int {                                                                       \
-        static int n_ = 0;                                                                \
-        if (!n_) {                                                                        \
-            int q_ = 0;                                                                   \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q_, kernel, kEwThreads, 0) != cudaSuccess) q_ = 1; \
-            n_ = q_ < 1 ? 1 : q_;                                                         \
-        }                                                                                 \
-        return n_;                                                                        \
-    }())
-
 }  // namespace mpb
 
 #define MPB_CHECK_C(C) MPB_REQUIRE((C) > 0 && (C) % 8 == 0 && (C) <= 2048, "C must be a positive multiple of 8, at most 2048")
+#define MPB_CHECK_DT(dt) MPB_REQUIRE((dt) == 0 || (dt) == 1, "dtype must be 0 (bf16 activations) or 1 (fp32 activations)")
+// Run the statement(s) with T bound to the activation storage type selected by `dt`.
+#define MPB_DISPATCH_ACT(dt, ...)    \
+    do {                             \
+        if ((dt) == 0) {             \
+            typedef __nv_bfloat16 T; \
+            __VA_ARGS__;             \
+        } else {                     \
+            typedef float T;         \
+            __VA_ARGS__;             \
+        }                            \
+    } while (0)
 
 namespace mpb {
-// conv weight fp32 [Cout, Cin] -> bf16 W [cout_p, cin_p] (zero padded; xyz_last: the 3 leading input channels move
+// conv weight fp32 [Cout, Cin] -> packed operand W [cout_p, cin_p] (zero padded; xyz_last: the 3 leading input channels move
 // behind the feature channels, matching mpb_group_points_bf16's row layout) and its transpose Wt [cin_p, cout_p].
+// MODE 0: bf16.  MODE 1: fp32 split for the 3xTF32 GEMMs: hi = tf32(w) into (Wp, Wt), lo = w - hi into (Wp_lo, Wt_lo).
 // First half of the grid writes W, second half Wt; both with coalesced stores (the fp32 source is L2-resident).
+template <int MODE>
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(const float *__restrict__ W, int cout, int cin, int cout_p, int cin_p, int xyz_last,
-                   __nv_bfloat16 *__restrict__ Wp, __nv_bfloat16 *__restrict__ Wt)
+pack_weight_kernel(const float *__restrict__ W, int cout, int cin, int cout_p, int cin_p, int xyz_last, void *__restrict__ Wp,
+                   void *__restrict__ Wt, float *__restrict__ Wp_lo, float *__restrict__ Wt_lo)
 {
     const int total = cout_p * cin_p;
     const int half = (total + 255) / 256;
@@ -827,7 +875,24 @@ pack_weight_kernel(const float *__restrict__ W, int cout, int cin, int cout_p, i
         const int src = (xyz_last && cin > 3) ? (c < cin - 3 ? c + 3 : c - (cin - 3)) : c;
         v = W[(size_t)r * cin + src];
     }
-    (transposed ? Wt : Wp)[e] = __float2bfloat16_rn(v);
+    if (MODE == 0) {
+        static_cast<__nv_bfloat16 *>(transposed ? Wt : Wp)[e] = __float2bfloat16_rn(v);
+    } else {
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        const float hi = __uint_as_float(hb);
+        float *lo = transposed ? Wt_lo : Wp_lo;
+        static_cast<float *>(transposed ? Wt : Wp)[e] = lo ? hi : v;      // no low-part buffer: the weight stays unsplit
+        if (lo) lo[e] = v - hi;
+    }
+}
+
+template <class T>
+static int resident_per_sm(const void *kernel)
+{
+    int q = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kernel, kEwThreads, 0) != cudaSuccess) q = 1;
+    return q < 1 ? 1 : q;
 }
 }  // namespace mpb
 
@@ -837,8 +902,20 @@ extern "C" int mpb_pack_weight_bf16(const float *W, int cout, int cin, int cout_
     using namespace mpb;
     MPB_REQUIRE(W && Wp && Wt && cout > 0 && cin > 0 && cout_p >= cout && cin_p >= cin, "bad argument");
     const int total = cout_p * cin_p;
-    pack_weight_kernel<<<2 * ((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, cout, cin, cout_p, cin_p, xyz_last,
-                                                                                  (__nv_bfloat16 *)Wp, (__nv_bfloat16 *)Wt);
+    pack_weight_kernel<0><<<2 * ((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, cout, cin, cout_p, cin_p, xyz_last, Wp, Wt,
+                                                                                     nullptr, nullptr);
+    return check_launch("pack_weight_kernel");
+}
+
+extern "C" int mpb_pack_weight_tf32(const float *W, int cout, int cin, int cout_p, int cin_p, int xyz_last, float *Wp_hi, float *Wp_lo,
+                                    float *Wt_hi, float *Wt_lo, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(W && Wp_hi && Wt_hi && cout > 0 && cin > 0 && cout_p >= cout && cin_p >= cin, "bad argument");
+    MPB_REQUIRE((Wp_lo != nullptr) == (Wt_lo != nullptr), "Wp_lo / Wt_lo must come together (both null: unsplit fp32 copy)");
+    const int total = cout_p * cin_p;
+    pack_weight_kernel<1><<<2 * ((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, cout, cin, cout_p, cin_p, xyz_last, Wp_hi, Wt_hi,
+                                                                                     Wp_lo, Wt_lo);
     return check_launch("pack_weight_kernel");
 }
 
@@ -848,12 +925,13 @@ extern "C" int mpb_bn_stat_partials(int64_t rows, int C)
     return mpb::stat_parts(rows, C);
 }
 
-extern "C" int mpb_bn_colstats_bf16(const void *Z, int64_t M, int C, float *partials, int nparts, void *stream)
+extern "C" int mpb_bn_colstats(int dtype, const void *Z, int64_t M, int C, float *partials, int nparts, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
+    MPB_CHECK_DT(dtype);
     MPB_REQUIRE(M > 0 && Z && partials && nparts == stat_parts(M, C), "bad argument");
-    colstats_kernel<<<nparts, kEwThreads, stat_smem(C), (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, M, C, partials);
+    MPB_DISPATCH_ACT(dtype, colstats_kernel<T><<<nparts, kEwThreads, stat_smem(C), (cudaStream_t)stream>>>((const T *)Z, M, C, partials));
     return check_launch("colstats_kernel");
 }
 
@@ -870,55 +948,63 @@ extern "C" int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int
     return check_launch("bn_finalize_kernel");
 }
 
-extern "C" int mpb_bn_relu_bf16(const void *Z, const float *scale, const float *shift, int64_t M, int C, void *A, void *stream)
+extern "C" int mpb_bn_relu(int dtype, const void *Z, const float *scale, const float *shift, int64_t M, int C, void *A, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
+    MPB_CHECK_DT(dtype);
     MPB_REQUIRE(M >= 0 && Z && scale && shift && A, "bad argument");
     if (M == 0) return MPB_OK;
-    bn_relu_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, MPB_RESIDENT_PER_SM(bn_relu_kernel)), kEwThreads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)Z, scale, shift, M, C, (__nv_bfloat16 *)A);
+    MPB_DISPATCH_ACT(dtype, {
+        static const int occ = resident_per_sm<T>((const void *)bn_relu_kernel<T>);
+        bn_relu_kernel<T><<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, occ), kEwThreads, 0, (cudaStream_t)stream>>>((const T *)Z, scale, shift, M, C,
+                                                                                                                     (T *)A);
+    });
     return check_launch("bn_relu_kernel");
 }
 
-extern "C" int mpb_bn_relu_max_bf16(const void *Z, const float *scale, const float *shift, int64_t G, int K, int C, float *out,
-                                    int32_t *argmax, float *zmax, void *stream)
+extern "C" int mpb_bn_relu_max(int dtype, const void *Z, const float *scale, const float *shift, int64_t G, int K, int C, float *out,
+                               int32_t *argmax, float *zmax, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
+    MPB_CHECK_DT(dtype);
     MPB_REQUIRE(G >= 0 && K > 0 && Z && scale && shift && out && argmax, "bad argument");
     if (G == 0) return MPB_OK;
     const int nseg = kWideThreads / (C >> 3);
     if (G <= 2 * sm_count() && nseg >= 2 && K >= 4 * nseg) {
         const size_t smem = (size_t)3 * nseg * C * sizeof(float);
-        MPB_ENSURE_DYN_SMEM(bn_relu_max_wide_kernel, smem);
-        bn_relu_max_wide_kernel<<<(unsigned)G, kWideThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
-                                                                                          argmax, zmax);
+        MPB_DISPATCH_ACT(dtype, {
+            MPB_ENSURE_DYN_SMEM(bn_relu_max_wide_kernel<T>, smem);
+            bn_relu_max_wide_kernel<T><<<(unsigned)G, kWideThreads, smem, (cudaStream_t)stream>>>((const T *)Z, scale, shift, G, K, C, out, argmax, zmax);
+        });
         return check_launch("bn_relu_max_wide_kernel");
     }
-    bn_relu_max_kernel<<<row_blocks(G, C, MPB_RESIDENT_PER_SM(bn_relu_max_kernel)), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Z, scale, shift, G, K, C, out,
-                                                                                    argmax, zmax);
+    MPB_DISPATCH_ACT(dtype, {
+        static const int occ = resident_per_sm<T>((const void *)bn_relu_max_kernel<T>);
+        bn_relu_max_kernel<T><<<row_blocks(G, C, occ), kEwThreads, 0, (cudaStream_t)stream>>>((const T *)Z, scale, shift, G, K, C, out, argmax, zmax);
+    });
     return check_launch("bn_relu_max_kernel");
 }
 
-extern "C" int mpb_bn_bwd_stats_bf16(const void *dA, const float *dOut, const int32_t *argmax, const float *zmax, int K, const void *Z,
-                                     const float *scale,
-                                     const float *shift, const float *mean, const float *rstd, int64_t M, int C, float *partials,
-                                     int nparts, void *stream)
+extern "C" int mpb_bn_bwd_stats(int dtype, const void *dA, const float *dOut, const int32_t *argmax, const float *zmax, int K, const void *Z,
+                                const float *scale, const float *shift, const float *mean, const float *rstd, int64_t M, int C,
+                                float *partials, int nparts, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
+    MPB_CHECK_DT(dtype);
     MPB_REQUIRE(M > 0 && Z && scale && shift && mean && rstd && partials, "bad argument");
     MPB_REQUIRE((dA != nullptr) != (dOut != nullptr), "exactly one of dA (dense) / dOut (pooled) must be given");
     cudaStream_t st = (cudaStream_t)stream;
     if (dA) {
         MPB_REQUIRE(nparts == stat_parts(M, C), "nparts mismatch");
-        bwd_stats_dense_kernel<<<nparts, kEwThreads, stat_smem(C), st>>>((const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale,
-                                                                                 shift, mean, rstd, M, C, partials);
+        MPB_DISPATCH_ACT(dtype, bwd_stats_dense_kernel<T><<<nparts, kEwThreads, stat_smem(C), st>>>((const T *)dA, (const T *)Z, scale, shift, mean, rstd, M,
+                                                                                                  C, partials));
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0 && nparts == stat_parts(M / K, C), "pooled: bad argmax/K/nparts");
-        bwd_stats_pooled_kernel<<<nparts, kEwThreads, stat_smem(C), st>>>(dOut, argmax, (const __nv_bfloat16 *)Z, zmax, scale, shift, mean,
-                                                                                  rstd, M / K, K, C, partials);
+        MPB_DISPATCH_ACT(dtype, bwd_stats_pooled_kernel<T><<<nparts, kEwThreads, stat_smem(C), st>>>(dOut, argmax, (const T *)Z, zmax, scale, shift, mean,
+                                                                                                   rstd, M / K, K, C, partials));
     }
     return check_launch("bwd_stats kernel");
 }
@@ -938,26 +1024,32 @@ extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C,
     return check_launch("bwd_finalize_kernel");
 }
 
-extern "C" int mpb_bn_bwd_apply_bf16(const void *dA, const float *dOut, const int32_t *argmax, int K, const void *Z, const float *scale,
-                                     const float *shift, const float *mean, const float *rstd, const float *coef, int64_t M, int C,
-                                     void *dZ, void *stream)
+extern "C" int mpb_bn_bwd_apply(int dtype, const void *dA, const float *dOut, const int32_t *argmax, int K, const void *Z, const float *scale,
+                                const float *shift, const float *mean, const float *rstd, const float *coef, int64_t M, int C,
+                                void *dZ, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
+    MPB_CHECK_DT(dtype);
     MPB_REQUIRE(M > 0 && Z && scale && shift && mean && rstd && coef && dZ, "bad argument");
     MPB_REQUIRE((dA != nullptr) != (dOut != nullptr), "exactly one of dA (dense) / dOut (pooled) must be given");
     cudaStream_t st = (cudaStream_t)stream;
     if (dA) {
-        bwd_apply_dense_kernel<<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, MPB_RESIDENT_PER_SM(bwd_apply_dense_kernel)), kEwThreads, 0, st>>>(
-            (const __nv_bfloat16 *)dA, (const __nv_bfloat16 *)Z, scale, shift, mean, rstd, coef, M, C, (__nv_bfloat16 *)dZ);
+        MPB_DISPATCH_ACT(dtype, {
+            static const int occ = resident_per_sm<T>((const void *)bwd_apply_dense_kernel<T>);
+            bwd_apply_dense_kernel<T><<<row_blocks((M + kRowUnroll - 1) / kRowUnroll, C, occ), kEwThreads, 0, st>>>((const T *)dA, (const T *)Z, scale, shift,
+                                                                                                               mean, rstd, coef, M, C, (T *)dZ);
+        });
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0, "pooled: bad argmax/K");
-        const int occ = MPB_RESIDENT_PER_SM(bwd_apply_pooled_kernel);
-        const int bx = row_blocks(M / K, C, occ), cap = occ * sm_count();
-        int ks = (cap + bx - 1) / bx;                       // segments needed to fill one wave ...
-        ks = ks > K / 8 ? K / 8 : ks;                       // ... of at least 8 rows each
-        bwd_apply_pooled_kernel<<<dim3(bx, ks < 1 ? 1 : ks), kEwThreads, 0, st>>>(dOut, argmax, K, (const __nv_bfloat16 *)Z, scale, shift,
-                                                                                  mean, rstd, coef, M / K, C, (__nv_bfloat16 *)dZ);
+        MPB_DISPATCH_ACT(dtype, {
+            static const int occ = resident_per_sm<T>((const void *)bwd_apply_pooled_kernel<T>);
+            const int bx = row_blocks(M / K, C, occ), cap = occ * sm_count();
+            int ks = (cap + bx - 1) / bx;                       // segments needed to fill one wave ...
+            ks = ks > K / 8 ? K / 8 : ks;                       // ... of at least 8 rows each
+            bwd_apply_pooled_kernel<T><<<dim3(bx, ks < 1 ? 1 : ks), kEwThreads, 0, st>>>(dOut, argmax, K, (const T *)Z, scale, shift, mean, rstd, coef,
+                                                                                         M / K, C, (T *)dZ);
+        });
     }
     return check_launch("bwd_apply kernel");
 }
@@ -973,10 +1065,40 @@ static inline NarrowRows narrow_rows(const float *xyz, int64_t xsb, int64_t xsn,
     g.new_xyz = new_xyz, g.idx = idx, g.N = N, g.S = S, g.K = K, g.D = D;
     return g;
 }
+
+template <class T, int CIN>
+static void launch_narrow_fwd(bool share, const NarrowRows &g, const void *W, int ldw, int64_t M, int C, void *Z, float *partials, int nparts,
+                              cudaStream_t st)
+{
+    const size_t smem = stat_smem(C);
+    if (share)
+        narrow_first_layer_kernel<T, CIN, true><<<nparts, kEwThreads, smem, st>>>(g, (const T *)W, ldw, M, C, (T *)Z, partials);
+    else
+        narrow_first_layer_kernel<T, CIN, false><<<nparts, kEwThreads, smem, st>>>(g, (const T *)W, ldw, M, C, (T *)Z, partials);
+}
+template <class T, int CIN, bool SHARE>
+static void launch_narrow_bwd2(const NarrowRows &g, const void *dA, const void *Z, const float *scale, const float *shift, const float *mean,
+                               const float *rstd, const float *coef, int64_t M, int C, float *dW, int ldw, cudaStream_t st)
+{
+    static const int occ = resident_per_sm<T>((const void *)narrow_first_layer_bwd_kernel<T, CIN, SHARE>);
+    narrow_first_layer_bwd_kernel<T, CIN, SHARE><<<row_blocks((M + kNarrowBwdUnroll - 1) / kNarrowBwdUnroll, C, occ), kEwThreads,
+                                                   (size_t)C * CIN * sizeof(float), st>>>(g, (const T *)dA, (const T *)Z, scale, shift, mean, rstd,
+                                                                                          coef, M, C, dW, ldw);
+}
+template <class T, int CIN>
+static void launch_narrow_bwd(bool share, const NarrowRows &g, const void *dA, const void *Z, const float *scale, const float *shift,
+                              const float *mean, const float *rstd, const float *coef, int64_t M, int C, float *dW, int ldw, cudaStream_t st)
+{
+    if (share)
+        launch_narrow_bwd2<T, CIN, true>(g, dA, Z, scale, shift, mean, rstd, coef, M, C, dW, ldw, st);
+    else
+        launch_narrow_bwd2<T, CIN, false>(g, dA, Z, scale, shift, mean, rstd, coef, M, C, dW, ldw, st);
+}
 }  // namespace mpb
 
 #define MPB_NARROW_CHECKS()                                                                                    \
     MPB_CHECK_C(C);                                                                                            \
+    MPB_CHECK_DT(dtype);                                                                                       \
     MPB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0 && D + 3 <= 8, "bad size (needs 3 + D <= 8)");       \
     MPB_REQUIRE(xyz && new_xyz && idx && (D == 0 || feats), "null pointer");                                   \
     MPB_REQUIRE(ldw >= D + 3, "ldw must cover the 3 + D input channels");                                      \
@@ -985,9 +1107,11 @@ static inline NarrowRows narrow_rows(const float *xyz, int64_t xsb, int64_t xsn,
                 "strides must fit 31 bits");                                                                   \
     MPB_REQUIRE((int64_t)B * S * K < ((int64_t)1 << 31), "row count exceeds 32-bit indexing")
 
-extern "C" int mpb_sa_first_layer_bf16(const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats, int64_t fsb,
-                                       int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx, int B, int N, int S, int K,
-                                       int D, const void *W, int ldw, int C, void *Z, float *partials, int nparts, void *stream)
+// W: the first layer's packed weight [C, ldw] in the activation storage type (bf16, or fp32 = the UNSPLIT weight: the
+// CUDA-core FMAs of this kernel are exact fp32, there is no tensor-core rounding to compensate).
+extern "C" int mpb_sa_first_layer(int dtype, const float *xyz, int64_t xsb, int64_t xsn, int64_t xsc, const float *feats, int64_t fsb,
+                                  int64_t fsn, int64_t fsc, const float *new_xyz, const int64_t *idx, int B, int N, int S, int K,
+                                  int D, const void *W, int ldw, int C, void *Z, float *partials, int nparts, void *stream)
 {
     using namespace mpb;
     MPB_NARROW_CHECKS();
@@ -995,32 +1119,22 @@ extern "C" int mpb_sa_first_layer_bf16(const float *xyz, int64_t xsb, int64_t xs
     MPB_REQUIRE(W && Z && partials && nparts == stat_parts(M, C), "bad argument");
     const NarrowRows g = narrow_rows(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = stat_smem(C);
     const bool share = (32 % (C >> 3)) == 0;
-#define MPB_LAUNCH_NARROW(CIN)                                                                                                     \
-    do {                                                                                                                           \
-        if (share)                                                                                                                 \
-            narrow_first_layer_kernel<CIN, true><<<nparts, kEwThreads, smem, st>>>(g, (const __nv_bfloat16 *)W, ldw, M, C,        \
-                                                                                  (__nv_bfloat16 *)Z, partials);                  \
-        else                                                                                                                       \
-            narrow_first_layer_kernel<CIN, false><<<nparts, kEwThreads, smem, st>>>(g, (const __nv_bfloat16 *)W, ldw, M, C,       \
-                                                                                   (__nv_bfloat16 *)Z, partials);                 \
-    } while (0)
     if (D + 3 <= 3)
-        MPB_LAUNCH_NARROW(3);
+        MPB_DISPATCH_ACT(dtype, (launch_narrow_fwd<T, 3>(share, g, W, ldw, M, C, Z, partials, nparts, st)));
     else if (D + 3 <= 6)
-        MPB_LAUNCH_NARROW(6);
+        MPB_DISPATCH_ACT(dtype, (launch_narrow_fwd<T, 6>(share, g, W, ldw, M, C, Z, partials, nparts, st)));
     else
-        MPB_LAUNCH_NARROW(8);
-#undef MPB_LAUNCH_NARROW
+        MPB_DISPATCH_ACT(dtype, (launch_narrow_fwd<T, 8>(share, g, W, ldw, M, C, Z, partials, nparts, st)));
     return check_launch("narrow_first_layer_kernel");
 }
 
-extern "C" int mpb_sa_first_layer_bwd_bf16(const void *dA, const void *Z, const float *scale, const float *shift, const float *mean,
-                                           const float *rstd, const float *coef, const float *xyz, int64_t xsb, int64_t xsn,
-                                           int64_t xsc, const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
-                                           const float *new_xyz, const int64_t *idx, int B, int N, int S, int K, int D, int C,
-                                           float *dW, int ldw, void *stream)
+// dW [C, ldw] fp32 is ACCUMULATED into (caller zero-fills; mpb_bn_bwd_finalize_f32 does it as its side job).
+extern "C" int mpb_sa_first_layer_bwd(int dtype, const void *dA, const void *Z, const float *scale, const float *shift, const float *mean,
+                                      const float *rstd, const float *coef, const float *xyz, int64_t xsb, int64_t xsn,
+                                      int64_t xsc, const float *feats, int64_t fsb, int64_t fsn, int64_t fsc,
+                                      const float *new_xyz, const int64_t *idx, int B, int N, int S, int K, int D, int C,
+                                      float *dW, int ldw, void *stream)
 {
     using namespace mpb;
     MPB_NARROW_CHECKS();
@@ -1028,27 +1142,12 @@ extern "C" int mpb_sa_first_layer_bwd_bf16(const void *dA, const void *Z, const 
     const int64_t M = (int64_t)B * S * K;
     const NarrowRows g = narrow_rows(xyz, xsb, xsn, xsc, feats, fsb, fsn, fsc, new_xyz, idx, N, S, K, D);
     cudaStream_t st = (cudaStream_t)stream;
-    const __nv_bfloat16 *dA_ = (const __nv_bfloat16 *)dA, *Z_ = (const __nv_bfloat16 *)Z;
     const bool share = (32 % (C >> 3)) == 0;
-#define MPB_LAUNCH_NARROW_BWD2(CIN, SH)                                                                                     \
-    narrow_first_layer_bwd_kernel<CIN, SH><<<row_blocks((M + kNarrowBwdUnroll - 1) / kNarrowBwdUnroll, C,                               \
-                                                        MPB_RESIDENT_PER_SM((narrow_first_layer_bwd_kernel<CIN, SH>))),     \
-                                             kEwThreads, (size_t)C * CIN * sizeof(float), st>>>(g, dA_, Z_, scale, shift, mean, rstd, \
-                                                                                                coef, M, C, dW, ldw)
-#define MPB_LAUNCH_NARROW_BWD(CIN)            \
-    do {                                      \
-        if (share)                            \
-            MPB_LAUNCH_NARROW_BWD2(CIN, true); \
-        else                                  \
-            MPB_LAUNCH_NARROW_BWD2(CIN, false); \
-    } while (0)
     if (D + 3 <= 3)
-        MPB_LAUNCH_NARROW_BWD(3);
+        MPB_DISPATCH_ACT(dtype, (launch_narrow_bwd<T, 3>(share, g, dA, Z, scale, shift, mean, rstd, coef, M, C, dW, ldw, st)));
     else if (D + 3 <= 6)
-        MPB_LAUNCH_NARROW_BWD(6);
+        MPB_DISPATCH_ACT(dtype, (launch_narrow_bwd<T, 6>(share, g, dA, Z, scale, shift, mean, rstd, coef, M, C, dW, ldw, st)));
     else
-        MPB_LAUNCH_NARROW_BWD(8);
-#undef MPB_LAUNCH_NARROW_BWD
-#undef MPB_LAUNCH_NARROW_BWD2
+        MPB_DISPATCH_ACT(dtype, (launch_narrow_bwd<T, 8>(share, g, dA, Z, scale, shift, mean, rstd, coef, M, C, dW, ldw, st)));
     return check_launch("narrow_first_layer_bwd_kernel");
 }

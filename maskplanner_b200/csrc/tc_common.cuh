@@ -105,15 +105,21 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // ---- UMMA descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1
 // | [49,52) base offset=0 | [61,64) layout type (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks XOR row & 7), 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row & 3: the only
+// swizzled layout the tensor core accepts for MN-major 32-bit operands; TMA name CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
 }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32, M = 128:
 // [4,6) D fmt (1 = F32) | [7,10) A fmt (1 = BF16) | [10,13) B fmt | [15] A major (1 = MN) | [16] B major | [17,23) N>>3 | [24,29) M>>4

@@ -223,17 +223,22 @@ class _GroupPointsBF16(torch.autograd.Function):
         return None, gf, None, None, None
 
 
-# Arithmetic of the shared MLP (reference :210-212).  "bf16": tensor-core path (tcgen05 GEMMs, bf16
-# activations, fp32 accumulation and statistics; tolerance rel 1e-2).  "fp32": strict-fp32 library GEMMs
-# (tolerance rel 1e-4; what the parity fixtures frozen from the CPU reference are checked with).
+# Arithmetic of the shared MLP (reference :210-212); every mode runs the hand-written tcgen05 GEMMs + BatchNorm
+# kernels of maskplanner_b200.shared_mlp:
+#   "bf16"  bf16 activations/operands, fp32 accumulation and statistics                      tolerance rel 1e-2
+#   "tf32"  fp32 activations, one TF32 pass per product (what cuDNN does for the reference
+#           on a GPU with torch's default allow_tf32)                                         tolerance ~1e-3
+#   "fp32"  fp32 activations, 3xTF32 (hi/lo split of both operands): the reference-precision
+#           mode, what the parity fixtures frozen from the CPU reference are checked with     tolerance rel 1e-4
 _MLP_PRECISION = "bf16"
+PRECISIONS = ("bf16", "tf32", "fp32")
 
 
 def set_mlp_precision(mode):
     """Select the shared-MLP arithmetic for PointNetSetAbstraction modules that do not override it."""
     global _MLP_PRECISION
-    if mode not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if mode not in PRECISIONS:
+        raise ValueError("precision must be one of %s" % (PRECISIONS,))
     _MLP_PRECISION = mode
 
 
@@ -299,7 +304,7 @@ class PointNetSetAbstraction(nn.Module):
         # position-major ([B,S,C']); a caller that immediately feeds the next SA layer (which
         # permutes back, reference :196-198) can set this to False and skip the transpose copy.
         self.contiguous_output = True
-        self.precision = None   # None -> module-level default (set_mlp_precision); or "bf16" / "fp32"
+        self.precision = None   # None -> module-level default (set_mlp_precision); or "bf16" / "tf32" / "fp32"
 
     def forward(self, xyz, points, full_points=None, seed_idx=None):
         xyz = xyz.permute(0, 2, 1)                                                      # :196
@@ -307,8 +312,9 @@ class PointNetSetAbstraction(nn.Module):
             points = points.permute(0, 2, 1)
         if full_points is not None:
             full_points = full_points.permute(0, 2, 1)
-        if (self.precision or _MLP_PRECISION) == "bf16" and (self.training or not torch.is_grad_enabled()):
+        if self.training or not torch.is_grad_enabled():
             return self._forward_tensor_core(xyz, points, full_points, seed_idx)
+        # eval mode WITH autograd (not on the training or inference path): stock torch ops below
         if self.group_all:
             new_xyz, new_points = sample_and_group_all(xyz, points)                     # :203
         else:
@@ -330,10 +336,12 @@ class PointNetSetAbstraction(nn.Module):
         return out.contiguous() if self.contiguous_output else out
 
     def _forward_tensor_core(self, xyz, points, full_points, seed_idx):
-        """Reference :203-215 with the grouped tensor produced directly as bf16 GEMM rows and the MLP on
-        tcgen05 (maskplanner_b200.shared_mlp).  xyz [B,N,3], points [B,N,D]|None (already position-major)."""
-        from .shared_mlp import narrow_rows_supported, pad64, shared_mlp_max
+        """Reference :203-215 with the grouped tensor produced directly as GEMM rows (bf16 or fp32, by precision)
+        and the MLP on tcgen05 (maskplanner_b200.shared_mlp).  xyz [B,N,3], points [B,N,D]|None (position-major)."""
+        from .shared_mlp import MODES, narrow_rows_supported, pad64, shared_mlp_max
         require_cuda(xyz)
+        mode = self.precision or _MLP_PRECISION
+        row_dtype = MODES[mode][2]
         B, N, C = xyz.shape
         if self.group_all:                                                              # :151-168
             new_xyz = torch.zeros(B, 1, C, device=xyz.device)
@@ -345,16 +353,22 @@ class PointNetSetAbstraction(nn.Module):
             new_xyz = index_points(xyz, fps_idx)                                        # :131
             idx = query_ball_point(self.radius, K, xyz, new_xyz)                        # :132
             rows = index_points(full_points, idx) if (points is None and full_points is not None) else None
-        if rows is not None:   # group-all / full_points: plain rows, padded and rounded to bf16
+        xyz_last = False
+        if rows is not None:   # group-all / full_points: plain rows, padded (and rounded to bf16 in that mode)
             w = rows.shape[-1]
-            a0 = F.pad(rows.reshape(B * S * K, w), (0, pad64(w) - w)).to(torch.bfloat16)
+            a0 = F.pad(rows.reshape(B * S * K, w), (0, pad64(w) - w)).to(row_dtype)
         elif narrow_rows_supported(points, K) and len(self.mlp_convs) >= 2:
             # <= 8 channels per grouped row (SA1): the first layer gathers its rows on the fly, nothing is materialised
             a0 = (xyz, points, new_xyz.contiguous(), idx.contiguous())                  # :133-138 fused into :210
+            xyz_last = True
         else:
             D = 0 if points is None else points.shape[2]
-            a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))        # :133-138
-        pooled = shared_mlp_max(a0, K, self.mlp_convs, self.mlp_bns, self.training, xyz_last=rows is None)   # :208-214
+            if mode == "bf16":   # features first, centred xyz last: aligned 16-byte feature copies
+                a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))    # :133-138
+                xyz_last = True
+            else:                # fp32 rows in the reference's own column order (xyz first), zero padded
+                a0 = group_points(xyz, points, new_xyz, idx, ldo=pad64(3 + D)).view(B * S * K, pad64(3 + D))
+        pooled = shared_mlp_max(a0, K, self.mlp_convs, self.mlp_bns, self.training, xyz_last=xyz_last, mode=mode)   # :208-214
         out = pooled.view(B, S, -1).permute(0, 2, 1)
         return new_xyz.permute(0, 2, 1), (out.contiguous() if self.contiguous_output else out)
 
@@ -403,7 +417,8 @@ class PointNetSetAbstractionMsg(nn.Module):
         B, N, C = xyz.shape
         S = self.npoint
         new_xyz = index_points(xyz, farthest_point_sample(xyz, S, seed_idx))          # :253
-        tensor_core = (self.precision or _MLP_PRECISION) == "bf16" and (self.training or not torch.is_grad_enabled())
+        tensor_core = self.training or not torch.is_grad_enabled()
+        mode = self.precision or _MLP_PRECISION
         D = 0 if points is None else points.shape[2]
         outs = []
         for i, radius in enumerate(self.radius_list):
@@ -411,8 +426,13 @@ class PointNetSetAbstractionMsg(nn.Module):
             idx = query_ball_point(radius, K, xyz, new_xyz)                           # :257
             if tensor_core:
                 # the reference concatenates [feats, centred xyz] here (:262-263): exactly the bf16 row layout
-                a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))
-                pooled = shared_mlp_max(a0, K, self.conv_blocks[i], self.bn_blocks[i], self.training, xyz_last=False)
+                if mode == "bf16":
+                    a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, idx, pad64(3 + D))
+                else:   # fp32 rows [feats | centred xyz | 0] in the reference's order
+                    centred = group_points(xyz, None, new_xyz, idx)
+                    rows = centred if points is None else torch.cat([index_points(points, idx), centred], dim=-1)
+                    a0 = F.pad(rows.reshape(B * S * K, 3 + D), (0, pad64(3 + D) - (3 + D)))
+                pooled = shared_mlp_max(a0, K, self.conv_blocks[i], self.bn_blocks[i], self.training, xyz_last=False, mode=mode)
                 outs.append(pooled.view(B, S, -1).permute(0, 2, 1))
             else:
                 centred = group_points(xyz, None, new_xyz, idx)                       # :258-259

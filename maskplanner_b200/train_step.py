@@ -104,7 +104,7 @@ class Trainer:
         # encoder they run on TF32 tensor cores (10-bit mantissa, finer than the encoder's bf16 activations);
         # with the strict-fp32 encoder they stay strict fp32 so that mode keeps the reference's arithmetic.
         from .pointnet2_utils import get_mlp_precision
-        self.heads_tf32 = get_mlp_precision() == "bf16" if heads_tf32 is None else bool(heads_tf32)
+        self.heads_tf32 = get_mlp_precision() in ("bf16", "tf32") if heads_tf32 is None else bool(heads_tf32)
         # The heads' M = batch GEMMs are library calls either way; cuBLASLt's heuristics are preferred for them (measured
         # 3.95 vs 3.97 ms per step; a single run showed 3.87 and was not reproduced).  MPB_BLAS=cublas|cublaslt|default
         # overrides.  This is a process-wide torch setting (torch.backends.cuda.preferred_blas_library), applied once.

@@ -107,10 +107,9 @@ def test_flat_bucket_views_are_16_byte_aligned_and_disjoint():
 
 def test_narrow_first_layer_eligibility(monkeypatch):
     """Host-side switch of the on-the-fly first SA layer: <= 8 channels per grouped row, no gradient into the point
-    features, not under L2 chunking, and the MPB_NARROW_FIRST escape hatch."""
+    features, and the MPB_NARROW_FIRST escape hatch."""
     from maskplanner_b200 import shared_mlp as SM
     monkeypatch.delenv("MPB_NARROW_FIRST", raising=False)
-    monkeypatch.setattr(SM, "L2_CHUNK_BYTES", 0)
     assert SM.narrow_rows_supported(None, 32)
     assert SM.narrow_rows_supported(torch.zeros(2, 10, 3), 32)
     assert SM.narrow_rows_supported(torch.zeros(2, 10, 5), 32)
@@ -119,5 +118,4 @@ def test_narrow_first_layer_eligibility(monkeypatch):
     monkeypatch.setenv("MPB_NARROW_FIRST", "0")
     assert not SM.narrow_rows_supported(None, 32)
     monkeypatch.delenv("MPB_NARROW_FIRST")
-    monkeypatch.setattr(SM, "L2_CHUNK_BYTES", 1 << 20)
-    assert not SM.narrow_rows_supported(None, 32)
+    assert SM.narrow_rows_supported(None, 32)
