@@ -429,7 +429,7 @@ def run_ours(args, ws, rank, local):
     torch.cuda.synchronize()
     timeline, shared_mlp.GEMM_TIMELINE = shared_mlp.GEMM_TIMELINE, None
     per_kernel = {}
-    for name, nbytes, flops, e0, e1 in timeline:
+    for name, nbytes, flops, e0, e1, _tag in timeline:
         d = per_kernel.setdefault(name, {"launches": 0, "bytes": 0, "flops": 0, "ms": 0.0})
         d["launches"] += 1
         d["bytes"] += nbytes

@@ -88,6 +88,7 @@ struct GemmSmemTail {
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint64_t zfull[2][2];   // [epilogue warpgroup][z staging buffer]
+    uint64_t sdone[2][2];   // [epilogue warpgroup][staging buffer]: statistic MMAs that read the buffer have completed
     uint32_t tmem_base;
 };
 
@@ -124,10 +125,12 @@ __device__ __forceinline__ float warp_column_sum_32x32(float (&v)[32], int lane)
 // `r7` = row index & 7 (the swizzle key), `ch0` = channel of the row's first element, `lo` = where the low part of the
 // TF32 split goes (same swizzled offsets in a second tile).  sc/sh: per-channel scale / shift in shared memory.
 template <int DT, bool XFORM, bool ATOM32 = false>
-__device__ __forceinline__ void transform_row(uint8_t *row, uint8_t *row_lo, int r7, const float *sc, const float *sh, bool valid)
+__device__ __forceinline__ void transform_row(uint8_t *row, uint8_t *row_lo, int r7, const float *sc, const float *sh, bool valid,
+                                              int c_begin = 0, int c_end = 8)
 {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
+        if (c < c_begin || c >= c_end) continue;
         // SWIZZLE_128B: logical 16-byte chunk c sits at physical chunk c ^ (row & 7);
         // 32-byte-atom variant: logical 32-byte chunk c >> 1 sits at (c >> 1) ^ (row & 3), its two halves stay in order
         const int off = ATOM32 ? (((((c >> 1) ^ (r7 & 3)) << 1) | (c & 1)) << 4) : ((c ^ r7) << 4);
@@ -177,32 +180,47 @@ struct GemmTnArgs {
     int M, N, K, BN, stages, out_bufs;
     const float *a_scale, *a_shift;    // XFORM: A' = relu(a_scale[k] * A + a_shift[k])
     const float *z_scale, *z_shift;    // EPI 2: relu mask of the layer below
-    float *partials;                   // EPI 1/2: [8 * gridDim.x][2][N]
+    float *partials;                   // EPI 1/2: [nparts][2][N]; nparts = 8 * grid (CUDA-core statistics) or 2 * grid (tensor-core)
 };
 
 constexpr int kGemmTnThreads = 384;    // producer, MMA, allocator, spare + two epilogue warpgroups
-constexpr int kGemmTnThreadsXf = 512;  // + the transform warpgroup
+constexpr int kGemmTnThreadsXf = 640;  // + two transform warpgroups (each thread rewrites half a row of the landed A tile)
 
-// EPI: 0 = store only; 1 = + column sum / sum of squares of the stored values (forward BatchNorm statistics);
-//      2 = + column sum dY / sum dY*z, dY = C * [z_scale*z + z_shift > 0], z = tmZ tile (BatchNorm-backward statistics)
+// Statistics on the tensor core (bf16 kernels, TCS): the 128-row x 64-column tile the epilogue has just staged in shared
+// memory (swizzled, exactly a wgrad-style MN-major operand) is multiplied with itself,
+//     D[128 x 64] (+)= [ X | E ]^T [128 rows -> M = 64 + 64]  *  Y [128 rows x 64]      (8 MMAs of K = 16 rows)
+// where E is a constant box whose column 0 is all ones.  Rows 0..63 of D accumulate the Gram block X^T Y -- its DIAGONAL is
+// the per-column sum of x*y -- and row 64 accumulates 1^T Y, the per-column sum of y.  bf16 x bf16 products are exact in the
+// fp32 accumulator, so these are the same sums the CUDA-core butterfly produced, for 8 issued instructions per block instead
+// of ~250 shuffle/select/add instructions per warp (ncu: the statistics epilogue made the kernel issue-bound, 30 M warp
+// instructions against 7 M for the plain store).  EPI 1: X = Y = stored output -> (sum z, sum z^2).  EPI 2: X = z tile of the
+// layer below (TMA-loaded), Y = dY = C * [z_scale*z + z_shift > 0] -> (sum dY, sum dY*z).  The accumulators live in TMEM for
+// the whole kernel (one set per epilogue warpgroup) and are read once at the end.
+// EPI: 0 = store only; 1 = + forward BatchNorm statistics of the stored values; 2 = + BatchNorm-backward statistics.
 template <int DT, bool XFORM, int EPI>
 __global__ void __launch_bounds__((XFORM || DT == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const GemmTnArgs p)
 {
     constexpr bool kXf = XFORM || DT == DT_TF32X3;
+    constexpr bool TCS = DT == DT_BF16 && EPI != 0;       // statistics on the tensor core
     constexpr int EPR = DT == DT_BF16 ? 64 : 32;          // elements per 128-byte row = columns per k-block and per output block
     constexpr int NA = DT == DT_TF32X3 ? 2 : 1;           // operand copies per stage (hi, lo)
+    constexpr uint32_t kAccStride = TCS ? 128u : 256u;    // TMEM columns between the two accumulators (TCS: BN <= 128)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.M, N = p.N, K = p.K, BN = p.BN, stages = p.stages;
     const uint32_t b_bytes = (uint32_t)BN * 128u;
     const uint32_t stage_bytes = NA * (kABytes + b_bytes);   // [A | A_lo | B | B_lo]
-    uint8_t *staging = smem + (size_t)stages * stage_bytes;                                   // [2 warpgroups][out_bufs] output tiles
-    uint8_t *zstage = staging + (size_t)2 * p.out_bufs * kABytes;                             // EPI 2: [2 warpgroups][2] z tiles
-    float *stat_acc = reinterpret_cast<float *>(zstage + (EPI == 2 ? 4 * kABytes : 0));       // EPI != 0: [8 warps][2][BN]
-    float *vec = stat_acc + (EPI != 0 ? 8 * 2 * 256 : 0);                                     // [a_scale K][a_shift K][z_scale N][z_shift N]
+    // carve-up (every tile 1024-byte aligned): ring | output staging [2 wg][out_bufs] | z tiles [2 wg][2] (EPI 2) |
+    // dY tiles [2 wg] (TCS, EPI 2) | ones box (TCS) | CUDA-core statistic slots [8 warps][2][256] (!TCS) | vectors | barriers
+    uint8_t *staging = smem + (size_t)stages * stage_bytes;
+    uint8_t *zstage = staging + (size_t)2 * p.out_bufs * kABytes;
+    uint8_t *dystage = zstage + (EPI == 2 ? 4 * kABytes : 0);
+    uint8_t *ones = dystage + ((TCS && EPI == 2) ? 2 * kABytes : 0);
+    float *stat_acc = reinterpret_cast<float *>(ones + (TCS ? kABytes : 0));
+    float *vec = stat_acc + ((EPI != 0 && !TCS) ? 8 * 2 * 256 : 0);                           // [a_scale K][a_shift K][z_scale N][z_shift N]
     float *s_ascale = vec, *s_ashift = vec + (XFORM ? K : 0);
     float *s_zscale = s_ashift + (XFORM ? K : 0), *s_zshift = s_zscale + (EPI == 2 ? N : 0);
     GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(s_zshift + (EPI == 2 ? N : 0));
@@ -214,6 +232,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = threadIdx.x; i < K; i += blockDim.x) s_ascale[i] = p.a_scale[i], s_ashift[i] = p.a_shift[i];
     if (EPI == 2)
         for (int i = threadIdx.x; i < N; i += blockDim.x) s_zscale[i] = p.z_scale[i], s_zshift[i] = p.z_shift[i];
+    if (TCS) {   // E: 128 rows x 64 bf16 columns, column 0 = 1 (chunk 0 of row r sits at physical chunk r & 7), everything else 0
+        for (int i = threadIdx.x; i < kABytes / 16; i += blockDim.x) {
+            const int r = i >> 3, pc = i & 7;
+            reinterpret_cast<uint4 *>(ones)[i] = make_uint4(pc == (r & 7) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+    }
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmA);
         prefetch_tensormap(&tmB);
@@ -223,13 +248,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < stages; ++s) {
             mbar_init(&tail->full[s], 1);
             mbar_init(&tail->empty[s], 1);
-            mbar_init(&tail->ready[s], 4);
+            mbar_init(&tail->ready[s], 8);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tail->tfull[a], 1);
             mbar_init(&tail->tempty[a], 4);
             mbar_init(&tail->zfull[a][0], 1);
             mbar_init(&tail->zfull[a][1], 1);
+            mbar_init(&tail->sdone[a][0], 1);
+            mbar_init(&tail->sdone[a][1], 1);
         }
         fence_barrier_init();
     }
@@ -264,7 +291,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 mbar_wait(&tail->tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&tail->full[stage], phase);              // B (and the raw A) have landed
                     if (kXf) mbar_wait(&tail->ready[stage], phase);    // A has been rewritten by the transform warps
@@ -295,18 +322,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (kXf && warp >= 12) {
-        // transform warpgroup: thread t owns row t of the landed A tile
+        // two transform warpgroups: thread t owns half (four 16-byte chunks) of row t & 127 of the landed A tile
         const int t = threadIdx.x - 384;
-        const int r7 = t & 7;
+        const int row_i = t & 127, half = t >> 7;
+        const int r7 = row_i & 7;
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * kTileM;
-            const bool valid = m0 + t < M;
+            const bool valid = m0 + row_i < M;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&tail->full[stage], phase);
-                uint8_t *row = smem + (size_t)stage * stage_bytes + t * 128;
-                transform_row<DT, XFORM>(row, row + kABytes, r7, s_ascale + kb * EPR, s_ashift + kb * EPR, valid);
+                uint8_t *row = smem + (size_t)stage * stage_bytes + row_i * 128;
+                transform_row<DT, XFORM>(row, row + kABytes, r7, s_ascale + kb * EPR, s_ashift + kb * EPR, valid, 4 * half, 4 * half + 4);
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tail->ready[stage]);
@@ -320,15 +348,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int acc = (warp - 4) >> 2;   // accumulator buffer owned by this warpgroup
         uint32_t acc_phase = 0;
         int nblk = 0;                                   // 128-byte column blocks processed so far by this warpgroup
-        const bool issuer = ew == 0 && lane == 0;       // the one thread of the warpgroup that owns its bulk-store groups / z loads
+        const bool issuer = ew == 0 && lane == 0;       // the one thread of the warpgroup that owns its bulk-store groups / z loads / statistic MMAs
         const int r_in_tile = ew * 32 + lane;
         const int r7 = r_in_tile & 7;
         float *my_stat = stat_acc + (size_t)(warp - 4) * 2 * 256;
-        if (EPI != 0)
+        if (EPI != 0 && !TCS)
             for (int c = lane; c < 2 * BN; c += 32) my_stat[c] = 0.f;
         uint8_t *my_staging = staging + (size_t)acc * p.out_bufs * kABytes;
         uint8_t *my_z = zstage + (size_t)acc * 2 * kABytes;
-        // z-tile prefetch ring (EPI 2): the issuer keeps two blocks in flight ahead of the warpgroup
+        uint8_t *my_dy = dystage + (size_t)acc * kABytes;
+        const uint32_t stat_tmem = tmem_base + 256u + (uint32_t)acc * 128u;     // TCS: [128 lanes x 64 columns] per column block
+        const uint32_t sidesc = make_idesc_bf16(64u, true, true);
+        uint32_t stat_used = 0;                                                  // bit j: column block j's accumulator has been started
+        // z-tile prefetch (EPI 2): CUDA-core statistics keep two blocks in flight; the tensor-core variant refills a z buffer
+        // only once the statistic MMA that read it has completed, i.e. one block ahead
         int z_tile = blockIdx.x + acc * (int)gridDim.x, z_c0 = 0, z_issued = 0;
         auto issue_z = [&]() {
             if (z_tile >= total) return;
@@ -342,7 +375,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (EPI == 2 && issuer) {
             issue_z();
-            issue_z();
+            if (!TCS) issue_z();
         }
         int t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
@@ -350,16 +383,30 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tail->tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(ew * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(ew * 32) << 16);
             for (int c0 = 0; c0 < BN; c0 += EPR, ++nblk) {
-                uint8_t *buf = my_staging + (size_t)(p.out_bufs == 2 ? (nblk & 1) : 0) * kABytes;
-                if (issuer) {                                        // the store that used this buffer has drained its reads
+                const int ob = p.out_bufs == 2 ? (nblk & 1) : 0;
+                uint8_t *buf = my_staging + (size_t)ob * kABytes;
+                if (issuer) {
+                    // the TMA store that last used this staging buffer has drained its reads ...
                     if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                    if (TCS) {
+                        // ... and so has the statistic MMA that read it (EPI 1) / that read the dY tile and the z buffer about to
+                        // be refilled (EPI 2: one dY tile, so the previous block's MMA must be complete)
+                        if (EPI == 1) {
+                            const int uses = p.out_bufs == 2 ? (nblk >> 1) : nblk;       // earlier uses of this buffer
+                            if (uses > 0) mbar_wait(&tail->sdone[acc][ob], (uint32_t)(uses - 1) & 1u);
+                        } else {
+                            if (nblk > 0) mbar_wait(&tail->sdone[acc][0], (uint32_t)(nblk - 1) & 1u);
+                            issue_z();                                                     // z tile of block nblk + 1
+                        }
+                    }
                 }
                 const uint8_t *zrow = my_z + (size_t)(nblk & 1) * kABytes + r_in_tile * 128;
                 if (EPI == 2) mbar_wait(&tail->zfull[acc][nblk & 1], (uint32_t)(nblk >> 1) & 1u);
                 named_bar_sync(1 + acc, 128);
                 uint8_t *rowp = buf + r_in_tile * 128;
+                uint8_t *dyrow = my_dy + r_in_tile * 128;
 #pragma unroll
                 for (int h = 0; h < EPR / 32; ++h) {                 // 32 accumulator columns per TMEM load
                     if (c0 + 32 * h < BN) {
@@ -375,7 +422,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int chunk = (4 * h + v) ^ r7;   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
                                 *reinterpret_cast<uint4 *>(rowp + chunk * 16) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
                             }
-                            if (EPI != 0) {   // statistics of exactly what was stored
+                            if (TCS && EPI == 2) {
+                                // dY tile for the statistic MMA: the stored (bf16) gradient where the layer below was active, else 0
+                                const float *zs = s_zscale + n0 + c0 + 32 * h, *zh = s_zshift + n0 + c0 + 32 * h;
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) {
+                                    const int chunk = (4 * h + v) ^ r7;
+                                    const uint4 zr = *reinterpret_cast<const uint4 *>(zrow + (chunk << 4));
+                                    const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
+                                    const float4 s0 = *reinterpret_cast<const float4 *>(zs + 8 * v), s1 = *reinterpret_cast<const float4 *>(zs + 8 * v + 4);
+                                    const float4 h0 = *reinterpret_cast<const float4 *>(zh + 8 * v), h1 = *reinterpret_cast<const float4 *>(zh + 8 * v + 4);
+                                    const float sc8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                                    const float sh8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                                    uint32_t dw[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float2 z2 = unpack_bf16(zw[u]);
+                                        const uint32_t c2 = pk[4 * v + u];
+                                        const uint32_t lo = fmaf(z2.x, sc8[2 * u], sh8[2 * u]) > 0.f ? (c2 & 0x0000FFFFu) : 0u;
+                                        const uint32_t hi = fmaf(z2.y, sc8[2 * u + 1], sh8[2 * u + 1]) > 0.f ? (c2 & 0xFFFF0000u) : 0u;
+                                        dw[u] = lo | hi;
+                                    }
+                                    *reinterpret_cast<uint4 *>(dyrow + (chunk << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                                }
+                            }
+                            if (EPI != 0 && !TCS) {   // statistics of exactly what was stored
 #pragma unroll
                                 for (int v = 0; v < 16; ++v) {
                                     const float2 f = unpack_bf16(pk[v]);
@@ -393,43 +464,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 for (int v = 0; v < 32; ++v) zv[v] = __uint_as_float(r[v]);
                             }
                         }
-                        if (EPI == 1) {
+                        if (EPI == 1 && !TCS) {
 #pragma unroll
                             for (int v = 0; v < 32; ++v) zq[v] = zv[v] * zv[v];
                         }
-                        if (EPI == 2) {   // dY = C * [relu mask of the layer below]; second moment against the raw pre-activation z
+                        if (EPI == 2 && !TCS) {   // dY = C * [relu mask of the layer below]; second moment against the raw pre-activation z
                             const float *zs = s_zscale + n0 + c0 + 32 * h, *zh = s_zshift + n0 + c0 + 32 * h;
-                            if (DT == DT_BF16) {
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) {
-                                    const uint4 zr = *reinterpret_cast<const uint4 *>(zrow + (((4 * h + v) ^ r7) << 4));
-                                    const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
+                            for (int v = 0; v < 8; ++v) {
+                                const float4 z4 = *reinterpret_cast<const float4 *>(zrow + ((v ^ r7) << 4));
+                                const float4 s4 = *reinterpret_cast<const float4 *>(zs + 4 * v), h4 = *reinterpret_cast<const float4 *>(zh + 4 * v);
+                                const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        const float2 z2 = unpack_bf16(zw[u]);
-                                        const int j = 8 * v + 2 * u;
-                                        const float d0 = fmaf(z2.x, zs[j], zh[j]) > 0.f ? zv[j] : 0.f;
-                                        const float d1 = fmaf(z2.y, zs[j + 1], zh[j + 1]) > 0.f ? zv[j + 1] : 0.f;
-                                        zv[j] = d0, zv[j + 1] = d1;
-                                        zq[j] = d0 * z2.x, zq[j + 1] = d1 * z2.y;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int v = 0; v < 8; ++v) {
-                                    const float4 z4 = *reinterpret_cast<const float4 *>(zrow + ((v ^ r7) << 4));
-                                    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        const int j = 4 * v + u;
-                                        const float d0 = fmaf(zz[u], zs[j], zh[j]) > 0.f ? zv[j] : 0.f;
-                                        zv[j] = d0;
-                                        zq[j] = d0 * zz[u];
-                                    }
+                                for (int u = 0; u < 4; ++u) {
+                                    const int j = 4 * v + u;
+                                    const float d0 = fmaf(zz[u], ss[u], hh[u]) > 0.f ? zv[j] : 0.f;
+                                    zv[j] = d0;
+                                    zq[j] = d0 * zz[u];
                                 }
                             }
                         }
-                        if (EPI != 0) {
+                        if (EPI != 0 && !TCS) {
                             const float cs = warp_column_sum_32x32(zv, lane), cq = warp_column_sum_32x32(zq, lane);
                             my_stat[c0 + 32 * h + lane] += cs;
                             my_stat[BN + c0 + 32 * h + lane] += cq;
@@ -442,17 +497,32 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(&tail->tempty[acc]);
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1 + acc, 128);                      // staging tile complete, z tile fully read
+                named_bar_sync(1 + acc, 128);                      // staging (and dY) tile complete, z tile fully read
                 if (issuer) {
                     tma_store_2d(&tmC, buf, n0 + c0, m0);
                     bulk_commit();
-                    if (EPI == 2) issue_z();                        // refill the z buffer this block just released
+                    if (EPI == 2 && !TCS) issue_z();               // refill the z buffer this block just released
+                    if (TCS) {
+                        // D[acc, block j] (+)= [X | E]^T * Y over the tile's 128 rows
+                        const int j = c0 / EPR;
+                        const uint32_t x_addr = smem_u32(EPI == 1 ? buf : my_z + (size_t)(nblk & 1) * kABytes);
+                        const uint32_t y_addr = smem_u32(EPI == 1 ? buf : my_dy);
+                        const uint64_t adesc = make_smem_desc_sw128(x_addr, smem_u32(ones) - x_addr, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(y_addr, kABytes, 1024);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)   // 16 rows per MMA = two 8-row groups = 2048 B
+                            umma_bf16(stat_tmem + (uint32_t)j * 64u, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), sidesc,
+                                      (k > 0 || ((stat_used >> j) & 1u)) ? 1u : 0u);
+                        stat_used |= 1u << j;
+                        umma_commit(&tail->sdone[acc][EPI == 1 ? ob : 0]);
+                    }
                 }
             }
             acc_phase ^= 1;
         }
         if (issuer) bulk_wait<0>();          // all stores complete before the CTA (and its shared memory) goes away
-        if (EPI != 0) {
+        if (EPI != 0 && !TCS) {
             // one partial row per epilogue warp; a CTA always owns the same column tile (gridDim.x % tiles_n == 0)
             const int n0 = ((int)blockIdx.x % tiles_n) * BN;
             float *dst = p.partials + ((size_t)blockIdx.x * 8 + (warp - 4)) * 2 * N;
@@ -460,6 +530,53 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const bool mine = c >= n0 && c < n0 + BN;
                 dst[c] = mine ? my_stat[c - n0] : 0.f;
                 dst[N + c] = mine ? my_stat[BN + c - n0] : 0.f;
+            }
+        }
+        if (TCS) {
+            // one partial row per warpgroup: wait for its last statistic MMA, then read row 64 (sums) and the Gram diagonal
+            const int n0 = ((int)blockIdx.x % tiles_n) * BN;
+            float *dst = p.partials + ((size_t)blockIdx.x * 2 + acc) * 2 * N;
+            for (int c = r_in_tile; c < 2 * N; c += 128) dst[c] = 0.f;       // columns of other tiles / no tile processed at all
+            named_bar_sync(1 + acc, 128);
+            if (nblk > 0) {
+                if (EPI == 1) {
+                    const int last = nblk - 1, ob = p.out_bufs == 2 ? (last & 1) : 0;
+                    const int uses = p.out_bufs == 2 ? (last >> 1) : last;
+                    mbar_wait(&tail->sdone[acc][ob], (uint32_t)uses & 1u);
+                    if (p.out_bufs == 2 && nblk > 1) {
+                        const int prev = nblk - 2;
+                        mbar_wait(&tail->sdone[acc][prev & 1], (uint32_t)(prev >> 1) & 1u);
+                    }
+                } else {
+                    mbar_wait(&tail->sdone[acc][0], (uint32_t)(nblk - 1) & 1u);
+                }
+                tc_fence_after();
+                const int nb = BN / EPR > 0 ? (BN + EPR - 1) / EPR : 1;
+                for (int j = 0; j < nb; ++j) {
+                    const uint32_t base = stat_tmem + (uint32_t)j * 64u + ((uint32_t)(ew * 32) << 16);
+                    if (ew < 2) {            // rows 32*ew + lane of the Gram block: the diagonal element sits in column 32*ew + lane
+                        uint32_t r[32];
+                        tmem_ld_32x32(base + (uint32_t)(32 * ew), r);
+                        float d = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) d = lane == k ? __uint_as_float(r[k]) : d;
+                        const int c = j * EPR + 32 * ew + lane;
+                        if (c < BN) dst[N + n0 + c] = d;
+                    } else if (ew == 2) {    // row 64 (lane 0 of this warp): the 64 column sums
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(base + (uint32_t)(32 * hh), r);
+                            if (lane == 0) {
+#pragma unroll
+                                for (int k = 0; k < 32; ++k) {
+                                    const int c = j * EPR + 32 * hh + k;
+                                    if (c < BN) dst[n0 + c] = __uint_as_float(r[k]);
+                                }
+                            }
+                        }
+                    }
+                }
             }
         }
     }
@@ -623,19 +740,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
         const int ew = warp - 4;
         const int row = n0 + ew * 32 + lane;
         float *dst_row = p.partials + ((size_t)ms * p.n_pad + row) * K + k0;
+        const bool real_row = row < N;            // rows >= N: channel padding of the 128-row tile, never read by the reduction
         if (num_rb > 0) {
             mbar_wait(&tail->tfull[0], 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
             for (int c0 = 0; c0 < NU; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);      // warp-collective: every lane takes part, only real rows store
+                if (real_row) {
 #pragma unroll
-                for (int v = 0; v < 32; v += 4)
-                    *reinterpret_cast<float4 *>(dst_row + c0 + v) = make_float4(__uint_as_float(r[v]), __uint_as_float(r[v + 1]),
-                                                                                __uint_as_float(r[v + 2]), __uint_as_float(r[v + 3]));
+                    for (int v = 0; v < 32; v += 4)
+                        *reinterpret_cast<float4 *>(dst_row + c0 + v) = make_float4(__uint_as_float(r[v]), __uint_as_float(r[v + 1]),
+                                                                                    __uint_as_float(r[v + 2]), __uint_as_float(r[v + 3]));
+                }
             }
-        } else {
+        } else if (real_row) {
             for (int c0 = 0; c0 < NU; c0 += 4) *reinterpret_cast<float4 *>(dst_row + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -646,25 +766,38 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
 
 // dW[r, c] = sum over splits (fixed order) of the partial tiles, cropped to the real [cout, cin] and with the packed
 // column order undone (xyz_last: the three coordinate channels were moved behind the features by the weight packing).
-__global__ void __launch_bounds__(256)
+// A block = G warps x 32 consecutive outputs: warp g sums the splits i = g, g + G, ... (coalesced 128-byte rows of the
+// partial slabs, four loads in flight), the G per-warp sums meet in shared memory and are added in warp order --
+// the same order on every run, so the result is bitwise reproducible.  (The first version walked all splits from
+// one thread per output: 74 dependent rounds of L2 latency on 16 CTAs.)
+constexpr int kReduceMaxWarps = 32;
+__global__ void __launch_bounds__(32 * kReduceMaxWarps)
 wgrad_reduce_kernel(const float *__restrict__ partials, int m_splits, int n_pad, int K, int cout, int cin, int xyz_last, float *__restrict__ dW)
 {
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    if (e >= cout * cin) return;
-    const int r = e / cin, c = e - r * cin;
-    const int pc = (xyz_last && cin > 3) ? (c < 3 ? cin - 3 + c : c - 3) : c;
-    const float *src = partials + (size_t)r * K + pc;
-    const size_t stride = (size_t)n_pad * K;
+    __shared__ float red[kReduceMaxWarps][32];
+    const int G = blockDim.x >> 5, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 32 + lane;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int i = 0;
-    for (; i + 4 <= m_splits; i += 4) {        // four interleaved chains (loads in flight), combined in a fixed order
-        s0 += src[(size_t)i * stride];
-        s1 += src[(size_t)(i + 1) * stride];
-        s2 += src[(size_t)(i + 2) * stride];
-        s3 += src[(size_t)(i + 3) * stride];
+    if (e < cout * cin) {
+        const int r = e / cin, c = e - r * cin;
+        const int pc = (xyz_last && cin > 3) ? (c < 3 ? cin - 3 + c : c - 3) : c;
+        const float *src = partials + (size_t)r * K + pc;
+        const size_t stride = (size_t)n_pad * K;
+        int i = g;
+        for (; i + 3 * G < m_splits; i += 4 * G) {
+            const float a0 = src[(size_t)i * stride], a1 = src[(size_t)(i + G) * stride];
+            const float a2 = src[(size_t)(i + 2 * G) * stride], a3 = src[(size_t)(i + 3 * G) * stride];
+            s0 += a0, s1 += a1, s2 += a2, s3 += a3;
+        }
+        for (; i < m_splits; i += G) s0 += src[(size_t)i * stride];
     }
-    for (; i < m_splits; ++i) s0 += src[(size_t)i * stride];
-    dW[e] = (s0 + s1) + (s2 + s3);
+    red[g][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (g == 0 && e < cout * cin) {
+        float t = 0.f;
+        for (int w = 0; w < G; ++w) t += red[w][lane];
+        dW[e] = t;
+    }
 }
 
 // Columns per tile: the whole N when it fits one UMMA (N <= cap, multiple of 32); otherwise the largest multiple of
@@ -678,7 +811,7 @@ static int pick_bn(int N, int cap, int blk)
 }
 
 struct TnPlan {
-    int BN, stages, out_bufs, grid, threads;
+    int BN, stages, out_bufs, grid, threads, parts_per_cta;
     size_t smem;
 };
 
@@ -687,11 +820,13 @@ static bool plan_gemm_tn(int dt, bool xform, int epi, int M, int N, int K, TnPla
     const int epr = dt == DT_BF16 ? 64 : 32;
     const int na = dt == DT_TF32X3 ? 2 : 1;
     if (M <= 0 || N <= 0 || K <= 0 || K % epr || N % 32 || (xform && K > kMaxVec) || (epi == 2 && N > kMaxVec)) return false;
-    const int bn = pick_bn(N, dt == DT_TF32X3 ? 128 : 256, epr);
+    const bool tcs = dt == DT_BF16 && epi != 0;            // statistics on the tensor core: accumulators share TMEM, so BN <= 128
+    const int bn = pick_bn(N, (dt == DT_TF32X3 || tcs) ? 128 : 256, epr);
     if (bn <= 0 || (bn != N && bn % epr)) return false;
     if (dt != DT_BF16 && bn % 32) return false;
     const int stage_bytes = na * (kABytes + bn * 128);
-    const int fixed0 = (epi == 2 ? 4 * kABytes : 0) + (epi != 0 ? 8 * 2 * 256 * 4 : 0) + (xform ? 2 * K * 4 : 0) + (epi == 2 ? 2 * N * 4 : 0) +
+    const int fixed0 = (epi == 2 ? 4 * kABytes : 0) + ((tcs && epi == 2) ? 2 * kABytes : 0) + (tcs ? kABytes : 0) +
+                       ((epi != 0 && !tcs) ? 8 * 2 * 256 * 4 : 0) + (xform ? 2 * K * 4 : 0) + (epi == 2 ? 2 * N * 4 : 0) +
                        (int)sizeof(GemmSmemTail) + 1024;
     int out_bufs = 2;
     int stages = (227 * 1024 - fixed0 - 2 * out_bufs * kABytes) / stage_bytes;
@@ -707,6 +842,7 @@ static bool plan_gemm_tn(int dt, bool xform, int epi, int M, int N, int K, TnPla
     grid = grid / tiles_n * tiles_n;       // a CTA always owns the same column tile (statistics partial rows)
     if (grid < tiles_n) return false;
     pl->BN = bn, pl->stages = stages, pl->out_bufs = out_bufs, pl->grid = grid;
+    pl->parts_per_cta = tcs ? 2 : 8;
     pl->threads = (xform || dt == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads;
     pl->smem = (size_t)stages * stage_bytes + 2 * out_bufs * kABytes + fixed0;
     return true;
@@ -729,7 +865,7 @@ extern "C" int mpb_sa_gemm_stat_partials(int dtype, int M, int N, int K, int xfo
 {
     mpb::TnPlan pl;
     if (epi == 0 || !mpb::plan_gemm_tn(dtype, xform != 0, epi, M, N, K, &pl)) return 0;
-    return 8 * pl.grid;
+    return pl.parts_per_cta * pl.grid;
 }
 
 extern "C" int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const void *B_lo, void *C, int M, int N, int K,
@@ -750,7 +886,7 @@ extern "C" int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const voi
     const bool xform = a_scale != nullptr;
     TnPlan pl;
     MPB_REQUIRE(plan_gemm_tn(dtype, xform, epi, M, N, K, &pl), "unsupported shape (K multiple of 64 bf16 / 32 tf32, N multiple of 32, tiles must fit)");
-    MPB_REQUIRE(epi == 0 || nparts == 8 * pl.grid, "nparts mismatch (ask mpb_sa_gemm_stat_partials)");
+    MPB_REQUIRE(epi == 0 || nparts == pl.parts_per_cta * pl.grid, "nparts mismatch (ask mpb_sa_gemm_stat_partials)");
     const int esz = dtype == DT_BF16 ? 2 : 4;
     CUtensorMap tmA, tmB, tmBlo, tmC, tmZ;
     int rc = make_map(&tmA, esz, A, M, K, K, kTileM);
@@ -877,7 +1013,9 @@ extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M
     MPB_WG_CASE(DT_TF32X3, true);
 #undef MPB_WG_CASE
     if (rc) return rc;
-    wgrad_reduce_kernel<<<(cout * cin + 255) / 256, 256, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, dW);
+    int G = 1;                                           // warps per block: ~4 splits per thread, at most 32 warps
+    while (G < kReduceMaxWarps && G * 4 < pl.m_splits) G <<= 1;
+    wgrad_reduce_kernel<<<(cout * cin + 31) / 32, 32 * G, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, dW);
     return check_launch("wgrad_reduce_kernel");
 }
 

@@ -52,10 +52,10 @@ FUSE_BWD_STATS = os.environ.get("MPB_FUSE_BWD_STATS", "1") == "1"  # BatchNorm-b
 
 
 class _Timed:
-    def __init__(self, name, nbytes, flops):
+    def __init__(self, name, nbytes, flops, tag=""):
         self.rec = None
         if GEMM_TIMELINE is not None:
-            self.rec = (name, nbytes, flops, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.rec = (name, nbytes, flops, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), tag)
 
     def __enter__(self):
         if self.rec:
@@ -73,7 +73,7 @@ def _gemm_tn(lib, gd, esz, a, b, b_lo, c, M, N, K, st, real, a_affine=None, epi=
     A and B read once, C written once (+ Z read once for epi 2)."""
     rk, rn = real
     nbytes = esz * (M * rk + rn * rk + M * rn + (M * rn if epi == 2 else 0))
-    with _Timed("gemm_tn_kernel", nbytes, 2 * M * rn * rk):
+    with _Timed("gemm_tn_kernel", nbytes, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d epi=%d" % (M, N, K, 1 if a_affine else 0, epi)):
         check(lib.mpb_sa_gemm_tn(gd, ptr(a), ptr(b), ptr(b_lo), ptr(c), M, N, K,
                                  ptr(a_affine[0]) if a_affine else None, ptr(a_affine[1]) if a_affine else None,
                                  epi, ptr(partials), nparts, ptr(z), ptr(z_affine[0]) if z_affine else None,
@@ -87,7 +87,7 @@ def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz
     if ws_bytes < 0:
         raise _cabi.MpbError("mpb_sa_gemm_wgrad: unsupported shape M=%d N=%d K=%d" % (M, N, K))
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dw.device)
-    with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk):
+    with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d" % (M, N, K, 1 if a_affine else 0)):
         check(lib.mpb_sa_gemm_wgrad(gd, ptr(dz), ptr(a), M, N, K, ptr(a_affine[0]) if a_affine else None,
                                     ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, ptr(dw), st),
               "mpb_sa_gemm_wgrad", launches=2)

@@ -78,7 +78,7 @@ def _rel_l2(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
 
 
-@pytest.mark.parametrize("mode,tol_out,tol_grad", [("bf16", 1e-3, 1e-2), ("tf32", 5e-3, 5e-2), ("fp32", 2e-5, 1e-4)])
+@pytest.mark.parametrize("mode,tol_out,tol_grad", [("bf16", 1e-3, 1e-2), ("tf32", 5e-3, 0.15), ("fp32", 2e-5, 1e-4)])
 @pytest.mark.parametrize("G,K,cin,mlp", [(64, 12, 9, [16, 24, 32]), (2, 40, 35, [32, 48]), (512, 32, 3, [64, 64, 128]),
                                           (256, 64, 131, [128, 128, 256]), (4, 128, 259, [256, 512, 1024])])
 def test_fused_stack_forward_backward_matches_emulation(G, K, cin, mlp, mode, tol_out, tol_grad):
