@@ -167,7 +167,7 @@ MPB_API int mpb_knn_points_bwd_f32(const float *p1, const float *p2, int N, int 
  *                      both operands read as MN-major straight from their row-major layout; the contraction
  *                      rows are split over CTAs whose partial tiles go to `workspace`
  *                      (mpb_sa_gemm_wgrad_workspace bytes) and are summed in a fixed order: bitwise reproducible.
- *                      xyz_last undoes mpb_pack_weight_*'s column permutation.
+ *                      xyz_last undoes mpb_pack_weight_*'s column permutation; accumulate != 0 adds to dW instead.
  * mpb_bn_*:            training-mode BatchNorm2d statistics, normalise + ReLU (+ max-pool with arg-max),
  *                      and the matching backward; `partials` is a [nparts, 2, C] fp32 workspace with
  *                      nparts = mpb_bn_stat_partials(rows, C).  running_mean / running_var are updated in
@@ -187,7 +187,7 @@ MPB_API int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const void *
 MPB_API int64_t mpb_sa_gemm_wgrad_workspace(int dtype, int M, int N, int K, int xform);
 MPB_API int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K,
                               const float *a_scale, const float *a_shift, float *workspace, int cout,
-                              int cin, int xyz_last, float *dW, void *stream);
+                              int cin, int xyz_last, int accumulate, float *dW, void *stream);
 MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
 /* dtype of the mpb_bn_* / mpb_sa_first_layer* calls: storage type of the activations, 0 = bf16, 1 = fp32. */
 MPB_API int mpb_bn_colstats(int dtype, const void *Z, int64_t M, int C, float *partials, int nparts,
@@ -243,6 +243,40 @@ MPB_API int mpb_sa_first_layer_bwd(int dtype, const void *dA, const void *Z, con
                                    int64_t xsc, const float *feats, int64_t fsb, int64_t fsn,
                                    int64_t fsc, const float *new_xyz, const int64_t *idx, int B, int N,
                                    int S, int K, int D, int C, float *dW, int ldw, void *stream);
+
+/* ---- f3: regression heads                             models/pointnet2_cls_ssg.py:270-295, :309-341 ----------
+ * The head GEMMs reuse mpb_sa_gemm_tn / mpb_sa_gemm_wgrad (dtype 1 = TF32, 2 = 3xTF32) with the WEIGHT as the 128-row
+ * operand, so head activations are FEATURE-MAJOR [F, Bp], Bp = batch padded to a multiple of 32 (<= 128):
+ *   forward  Yt[Nout,Bp] = W[Nout,Kin] * X[Bp,Kin]^T      mpb_sa_gemm_tn(dtype, A=W, B=X, C=Yt, M=Nout, N=Bp, K=Kin)
+ *   dW       dW[Nout,Kin] = dYt[Nout,Bp] * Xt[Kin,Bp]^T   mpb_sa_gemm_tn(dtype, A=dYt, B=Xt, C=dW, M=Nout, N=Kin, K=Bp)
+ *   dX       dXt[Kin,Bp] = W^T * dYt                       mpb_sa_gemm_wgrad(dtype, dZ=W, A=dYt, M=Nout, N=Kin, K=Bp)
+ * mpb_head_act_fwd:  bias + BatchNorm1d (training: batch statistics over the B real columns, running stats updated;
+ *                    eval: running stats) + ReLU + dropout(p), one warp per feature.  Outputs the activation in both
+ *                    layouts: Xt [F,Bp] and X [Bp,F] (padding rows/columns zero); Xt_lo/X_lo non-NULL: hi/lo TF32 split.
+ *                    Dropout keeps element (f,b) iff hash(seed, *step, layer, f, b) >= p: nothing is stored.
+ * mpb_head_act_bwd:  dXt [F,Bp] -> dYt [F,Bp], dgamma, dbeta, dbias [F] (mask regenerated from the same hash).
+ * mpb_rng_advance:   *counter += 1 on the stream (once per forward; a captured step advances it on replay).
+ * mpb_head_to_feature_major / _to_batch_major: [B,F] <-> [F,Bp] (+ bias on the way out, + column sums on the way in).
+ * mpb_head_pose_out_*: out[b,j,:] = [fc3[3j..3j+2], w * normalize(tanh(fc_normals[3j..3j+2]))]  (:332-339) and its backward. */
+MPB_API int mpb_rng_advance(int64_t *counter, void *stream);
+MPB_API int mpb_head_act_fwd(const float *Yt, int F, int B, int Bp, const float *bias, const float *gamma,
+                             const float *beta, float *running_mean, float *running_var, float momentum,
+                             float eps, int training, float drop_p, uint64_t seed, const int64_t *step,
+                             int layer, float *Xt, float *Xt_lo, float *X, float *X_lo, float *mean,
+                             float *rstd, void *stream);
+MPB_API int mpb_head_act_bwd(const float *dXt, const float *Yt, int F, int B, int Bp, const float *bias,
+                             const float *gamma, const float *beta, const float *mean, const float *rstd,
+                             int training, float drop_p, uint64_t seed, const int64_t *step, int layer,
+                             float *dYt, float *dgamma, float *dbeta, float *dbias, void *stream);
+MPB_API int mpb_head_to_feature_major(const float *X, int B, int Bp, int F, float *Xt, float *Xt_lo,
+                                      float *colsum, void *stream);
+MPB_API int mpb_head_to_batch_major(const float *Yt, const float *bias, int B, int Bp, int F, float *Y,
+                                    void *stream);
+MPB_API int mpb_head_pose_out_fwd(const float *Yt3, const float *b3, const float *Ytn, const float *bn,
+                                  int B, int Bp, int P, float weight_orient, float *out, void *stream);
+MPB_API int mpb_head_pose_out_bwd(const float *d_out, const float *Ytn, const float *bn, int B, int Bp, int P,
+                                  float weight_orient, float *dYt3, float *dYtn, float *db3, float *dbn,
+                                  void *stream);
 
 /* `padded=True` length scan                             pytorch3d_chamfer.py:138-149 ----------
  * first[n] = first j with y[n,j,0] == sentinel, else P2; *any_flag (int32, caller zero-fills) is

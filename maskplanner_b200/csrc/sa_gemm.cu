@@ -772,7 +772,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
 // one thread per output: 74 dependent rounds of L2 latency on 16 CTAs.)
 constexpr int kReduceMaxWarps = 32;
 __global__ void __launch_bounds__(32 * kReduceMaxWarps)
-wgrad_reduce_kernel(const float *__restrict__ partials, int m_splits, int n_pad, int K, int cout, int cin, int xyz_last, float *__restrict__ dW)
+wgrad_reduce_kernel(const float *__restrict__ partials, int m_splits, int n_pad, int K, int cout, int cin, int xyz_last, int accumulate,
+                    float *__restrict__ dW)
 {
     __shared__ float red[kReduceMaxWarps][32];
     const int G = blockDim.x >> 5, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -796,7 +797,7 @@ wgrad_reduce_kernel(const float *__restrict__ partials, int m_splits, int n_pad,
     if (g == 0 && e < cout * cin) {
         float t = 0.f;
         for (int w = 0; w < G; ++w) t += red[w][lane];
-        dW[e] = t;
+        dW[e] = accumulate ? dW[e] + t : t;
     }
 }
 
@@ -979,7 +980,8 @@ extern "C" int64_t mpb_sa_gemm_wgrad_workspace(int dtype, int M, int N, int K, i
 }
 
 extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K, const float *a_scale,
-                                 const float *a_shift, float *workspace, int cout, int cin, int xyz_last, float *dW, void *stream)
+                                 const float *a_shift, float *workspace, int cout, int cin, int xyz_last, int accumulate, float *dW,
+                                 void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(dtype >= DT_BF16 && dtype <= DT_TF32X3, "dtype must be 0 (bf16), 1 (tf32) or 2 (tf32x3)");
@@ -1015,7 +1017,7 @@ extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M
     if (rc) return rc;
     int G = 1;                                           // warps per block: ~4 splits per thread, at most 32 warps
     while (G < kReduceMaxWarps && G * 4 < pl.m_splits) G <<= 1;
-    wgrad_reduce_kernel<<<(cout * cin + 31) / 32, 32 * G, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, dW);
+    wgrad_reduce_kernel<<<(cout * cin + 31) / 32, 32 * G, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, accumulate, dW);
     return check_launch("wgrad_reduce_kernel");
 }
 

@@ -4,8 +4,10 @@ Mirror of the reference's ``PointNet2Regressor_StrokeMasks`` (models/pointnet2_c
 same constructor arguments, same sub-module / parameter names (``sa1..sa3``, ``fc1..fc3``, ``bn1``,
 ``bn2``, ``fc_normals``, ``sm_fc1..3``, ``sm_bn1..2``, ``mask_conf_out``, ``seg_conf_*``) so reference
 state_dicts load unchanged, same output tuple.  The three set-abstraction layers are the B200
-drop-ins from ``maskplanner_b200.pointnet2_utils``; the heads stay stock torch modules
-(``nn.Linear`` / ``BatchNorm1d`` / ``Dropout``: library GEMMs with M = batch size).
+drop-ins from ``maskplanner_b200.pointnet2_utils``; the heads keep their stock ``nn.Linear`` / ``BatchNorm1d`` modules as
+parameter containers, but in the MaskPlanner configuration their arithmetic runs as one autograd node over hand-written
+kernels (``maskplanner_b200.heads``: weight-streaming tcgen05 GEMMs + row-local BatchNorm1d/ReLU/dropout kernels,
+SURVEY.md 8f-3).
 """
 import torch
 import torch.nn as nn
@@ -60,6 +62,9 @@ class PointNet2Regressor_StrokeMasks(nn.Module):
             self.sm_bn2 = nn.BatchNorm1d(h1)
             if mask_confidence_scores:
                 self.mask_conf_out = nn.Linear(h1, n_stroke_masks)
+        import os
+        self.fused_heads = os.environ.get("MPB_FUSED_HEADS", "1") == "1"
+        self._heads = None
 
     def encode(self, xyz, fps_seeds=None):
         """xyz [B,3,N] -> global feature [B,1024] (pointnet2_cls_ssg.py:297-309)."""
@@ -76,6 +81,22 @@ class PointNet2Regressor_StrokeMasks(nn.Module):
     def forward(self, xyz, fps_seeds=None):
         B = xyz.shape[0]
         feat = self.encode(xyz, fps_seeds)
+        if self.fused_heads and feat.is_cuda and B <= 128:
+            # MaskPlanner configuration: both heads as one autograd node over hand-written kernels (maskplanner_b200.heads)
+            from .heads import FusedHeads
+            from .pointnet2_utils import get_mlp_precision
+            if self._heads is None:
+                if not FusedHeads.supported(self):
+                    self.fused_heads = False
+                    return self._forward_heads_torch(feat, B)
+                self._heads = FusedHeads(self)
+            out, masks, mask_scores = self._heads(feat, self.sa1.precision or get_mlp_precision())
+            return out, masks, mask_scores, None
+        return self._forward_heads_torch(feat, B)
+
+    def _forward_heads_torch(self, feat, B):
+        """The heads as stock torch modules (library GEMMs): configurations the fused path does not cover
+        (per-segment confidence scores, no stroke masks, batches above 128) and A/B comparisons in the tests."""
         h = self.dropout(F.relu(self.bn1(self.fc1(feat))))                       # :310
         h = self.dropout(F.relu(self.bn2(self.fc2(h))))                          # :311
         seg = self.fc3(h)                                                        # :312

@@ -89,7 +89,7 @@ def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dw.device)
     with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d" % (M, N, K, 1 if a_affine else 0)):
         check(lib.mpb_sa_gemm_wgrad(gd, ptr(dz), ptr(a), M, N, K, ptr(a_affine[0]) if a_affine else None,
-                                    ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, ptr(dw), st),
+                                    ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, 0, ptr(dw), st),
               "mpb_sa_gemm_wgrad", launches=2)
 
 

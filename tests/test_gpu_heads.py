@@ -1,0 +1,152 @@
+"""Fused regression heads (maskplanner_b200.heads: weight-streaming tcgen05 GEMMs + row-local BatchNorm1d/ReLU/dropout
+kernels) against the same modules run as stock torch ops (`_forward_heads_torch`, the reference's op sequence,
+models/pointnet2_cls_ssg.py:309-341).  Dropout is switched off for the element-wise comparisons (the fused path draws its
+masks from a counter-based hash, not torch's Philox stream) and checked statistically on its own.
+Tolerances: TF32 head GEMMs (bf16/tf32 encoder modes) rel 3e-3 outputs / 6e-2 gradients (single-pass TF32 through three layers and two BatchNorm backward passes); 3xTF32 (fp32 mode) 3e-5 / 1e-3 (BatchNorm1d over 5..64 samples is poorly conditioned)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+def _models(category, seed=0):
+    from maskplanner_b200 import regressor
+    torch.manual_seed(seed)
+    m = regressor.maskplanner_model(category).cuda()
+    for bn in (m.bn1, m.bn2, m.sm_bn1, m.sm_bn2):
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.uniform_(-0.3, 0.3)
+    m.dropout.p = 0.0
+    ref = copy.deepcopy(m)
+    ref.fused_heads = False
+    return m, ref
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("bf16", 3e-3, 6e-2), ("fp32", 3e-5, 2e-4)])
+@pytest.mark.parametrize("category,B,training", [("windows_v2", 64, True), ("cuboids_v2", 16, True), ("windows_v2", 5, True),
+                                                  ("windows_v2", 8, False)])
+def test_fused_heads_match_torch_modules(category, B, training, precision, tol_out, tol_grad):
+    from maskplanner_b200.heads import FusedHeads
+    m, ref = _models(category)
+    m.train(training), ref.train(training)
+    g = torch.Generator(device="cuda").manual_seed(B)
+    feat = torch.randn(B, 1024, device="cuda", generator=g)
+    f1 = feat.clone().requires_grad_(True)
+    f2 = feat.clone().requires_grad_(True)
+    heads = FusedHeads(m)
+    # float64 truth: the same modules in double precision; the strict-fp32 torch run measures how far plain fp32 is from it
+    ref64 = copy.deepcopy(ref).double()
+    f3 = feat.clone().double().requires_grad_(True)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        o1 = heads(f1, precision)
+        o2 = ref._forward_heads_torch(f2, B)[:3]
+        o3 = ref64._forward_heads_torch(f3, B)[:3]
+        ws = [torch.randn(o.shape, device="cuda", generator=g) for o in o2]
+        sum((a * w).sum() for a, w in zip(o1, ws)).backward()
+        sum((a * w).sum() for a, w in zip(o2, ws)).backward()
+        sum((a * w.double()).sum() for a, w in zip(o3, ws)).backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+    def check(name, mine, fp32, truth, tol):
+        """within `tol` of the float64 truth, or within 3x of what torch's own fp32 run achieves (ill-conditioned
+        BatchNorm1d backward over a handful of samples)"""
+        e_mine, e_fp32 = _rel(mine, truth), _rel(fp32, truth)
+        assert e_mine < max(tol, 3 * e_fp32), (name, e_mine, e_fp32)
+
+    for i, (a, b, c) in enumerate(zip(o1, o2, o3)):
+        assert tuple(a.shape) == tuple(b.shape)
+        check("out%d" % i, a, b, c, tol_out)
+    check("d_feat", f1.grad, f2.grad, f3.grad, tol_grad)
+    for (n, p1), (_, p2), (_, p3) in zip(m.named_parameters(), ref.named_parameters(), ref64.named_parameters()):
+        if n.startswith("sa"):
+            continue
+        assert p1.grad is not None, n
+        if n.split(".")[0] in ("fc1", "fc2", "sm_fc1", "sm_fc2") and n.endswith("bias") and training:
+            # BatchNorm removes the bias: the true gradient is 0, both sides hold rounding noise
+            assert float(p1.grad.abs().max()) < 1e-3 * max(1.0, float(getattr(m, n.split(".")[0]).weight.grad.abs().max())), n
+            continue
+        check(n, p1.grad, p2.grad, p3.grad, tol_grad)
+    if training:
+        for b1, b2 in zip((m.bn1, m.bn2, m.sm_bn1, m.sm_bn2), (ref.bn1, ref.bn2, ref.sm_bn1, ref.sm_bn2)):
+            assert torch.allclose(b1.running_mean, b2.running_mean, rtol=2e-3, atol=1e-4)
+            assert torch.allclose(b1.running_var, b2.running_var, rtol=5e-3, atol=1e-5)
+            assert int(b1.num_batches_tracked) == 1
+
+
+def test_head_dropout_hash_statistics_and_backward_consistency():
+    """mpb_head_act_fwd / _bwd with p = 0.3: the kept fraction among positive activations is 0.7 +- 1 %, kept values are
+    scaled by 1/(1-p), a new step counter draws a new mask, the same counter regenerates the same mask, and the backward
+    pass sends zero gradient exactly through the dropped (or ReLU-killed) elements."""
+    from maskplanner_b200 import _cabi as c
+    lib = c.load()
+    F, B, Bp, p = 1024, 64, 64, 0.3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Yt = torch.randn(F, Bp, device="cuda", generator=g)
+    ones, zeros = torch.ones(F, device="cuda"), torch.zeros(F, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def fwd(drop):
+        Xt, X = torch.empty(F, Bp, device="cuda"), torch.empty(Bp, F, device="cuda")
+        mean, rstd = torch.empty(F, device="cuda"), torch.empty(F, device="cuda")
+        c.check(lib.mpb_head_act_fwd(c.ptr(Yt), F, B, Bp, c.ptr(zeros), c.ptr(ones), c.ptr(zeros), None, None, 0.1, 1e-5, 1, drop, 1234,
+                                     c.ptr(step), 7, c.ptr(Xt), None, c.ptr(X), None, c.ptr(mean), c.ptr(rstd), c.stream_ptr()), "act_fwd")
+        return Xt, X, mean, rstd
+
+    base, _, mean, rstd = fwd(0.0)
+    a1, x1, _, _ = fwd(p)
+    a1b, _, _, _ = fwd(p)
+    assert torch.equal(a1, a1b)                                   # same counter -> same mask
+    assert torch.equal(x1, a1.t().contiguous())                   # the two layouts agree
+    pos = base > 0
+    kept = (a1 != 0) & pos
+    frac = float(kept.sum()) / float(pos.sum())
+    assert abs(frac - (1 - p)) < 0.01, frac
+    assert torch.allclose(a1[kept], base[kept] / (1 - p), rtol=1e-6)
+    c.check(lib.mpb_rng_advance(c.ptr(step), c.stream_ptr()), "rng")
+    a2, _, _, _ = fwd(p)
+    assert int(step) == 1 and not torch.equal(a1, a2)
+    # backward with the counter of a2
+    dXt = torch.randn(F, Bp, device="cuda", generator=g)
+    dYt = torch.empty(F, Bp, device="cuda")
+    dg, db, dbias = (torch.empty(F, device="cuda") for _ in range(3))
+    c.check(lib.mpb_head_act_bwd(c.ptr(dXt), c.ptr(Yt), F, B, Bp, c.ptr(zeros), c.ptr(ones), c.ptr(zeros), c.ptr(mean), c.ptr(rstd), 1, p, 1234,
+                                 c.ptr(step), 7, c.ptr(dYt), c.ptr(dg), c.ptr(db), c.ptr(dbias), c.stream_ptr()), "act_bwd")
+    yhat = ((Yt - mean[:, None]) * rstd[:, None]).double()
+    dy = torch.where(a2 != 0, dXt.double() / (1 - p), torch.zeros_like(dXt, dtype=torch.float64))
+    want = rstd[:, None].double() * (dy - dy.mean(1, keepdim=True) - yhat * (dy * yhat).mean(1, keepdim=True))
+    assert _rel(dYt, want) < 1e-5
+    assert _rel(db, dy.sum(1)) < 1e-5 and _rel(dg, (dy * yhat).sum(1)) < 1e-5
+
+
+def test_training_step_with_fused_heads_tracks_torch_heads(monkeypatch):
+    """Whole step: fused heads vs torch heads from identical weights, dropout off, 6 optimisation steps (TF32 head GEMMs on both sides)."""
+    from maskplanner_b200 import synthetic
+    from maskplanner_b200.train_step import Trainer
+    curves = []
+    batch = synthetic.make_batch(8, "windows_v2", seed0=5)
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MPB_FUSED_HEADS", fused)
+        tr = Trainer("windows_v2", torch.device("cuda", 0), seed=11)
+        tr.model.dropout.p = 0.0
+        dev_batch = tr.to_device(batch)
+        gen = torch.Generator().manual_seed(3)
+        losses = []
+        for _ in range(6):
+            seeds = (torch.randint(0, 5120, (8,), generator=gen), torch.randint(0, 512, (8,), generator=gen))
+            losses.append(float(tr.step(dev_batch, seeds).item()))
+        curves.append(losses)
+    # identical first step; afterwards Adam's sign-like first updates amplify last-bit differences, so the trajectories
+    # are only required to optimise alike
+    assert np.allclose(curves[0][:2], curves[1][:2], rtol=5e-3), curves
+    assert curves[0][-1] < 0.5 * curves[0][0] and curves[1][-1] < 0.5 * curves[1][0]
+    assert abs(curves[0][-1] - curves[1][-1]) < 0.25 * curves[1][-1], curves

@@ -81,7 +81,7 @@ def run_wg(dt, M, N, K, xform, cout=None, cin=None, xyz_last=False, seed=0):
         return "skip (unsupported)"
     ws = torch.empty(ws_bytes // 4, device=dev)
     dW = torch.full((cout, cin), float("nan"), device=dev)
-    check(lib.mpb_sa_gemm_wgrad(dt, ptr(dZ), ptr(A), M, N, K, ptr(sc), ptr(sh), ptr(ws), cout, cin, int(xyz_last), ptr(dW), stream_ptr()),
+    check(lib.mpb_sa_gemm_wgrad(dt, ptr(dZ), ptr(A), M, N, K, ptr(sc), ptr(sh), ptr(ws), cout, cin, int(xyz_last), 0, ptr(dW), stream_ptr()),
           "wgrad")
     torch.cuda.synchronize()
     Af = A.double()
@@ -97,7 +97,7 @@ def run_wg(dt, M, N, K, xform, cout=None, cin=None, xyz_last=False, seed=0):
     err = rel(dW, want)
     # determinism: a second run must be bit-identical
     dW2 = torch.empty_like(dW)
-    check(lib.mpb_sa_gemm_wgrad(dt, ptr(dZ), ptr(A), M, N, K, ptr(sc), ptr(sh), ptr(ws), cout, cin, int(xyz_last), ptr(dW2), stream_ptr()),
+    check(lib.mpb_sa_gemm_wgrad(dt, ptr(dZ), ptr(A), M, N, K, ptr(sc), ptr(sh), ptr(ws), cout, cin, int(xyz_last), 0, ptr(dW2), stream_ptr()),
           "wgrad")
     torch.cuda.synchronize()
     same = bool(torch.equal(dW, dW2))
