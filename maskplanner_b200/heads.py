@@ -19,7 +19,7 @@ reference on CUDA vs CPU, runs are reproducible per seed but not bit-identical a
 """
 import torch
 
-from . import _cabi, streams
+from . import _cabi, gradsink, streams
 from ._cabi import check, ptr, stream_ptr
 
 GEMM_DTYPE = {"bf16": 1, "tf32": 1, "fp32": 2}     # encoder precision mode -> head GEMM arithmetic (TF32 / 3xTF32)
@@ -49,9 +49,9 @@ class _Ctx:
         return Yt
 
     # dW [Nout, Kin] = dYt [Nout, Bp] @ Xt [Kin, Bp]^T
-    def linear_dw(self, dYt, Xt, Xt_lo, Kin):
+    def linear_dw(self, dYt, Xt, Xt_lo, Kin, out=None):
         Nout = dYt.shape[0]
-        dW = self.empty(Nout, Kin)
+        dW = out.view(Nout, Kin) if out is not None else self.empty(Nout, Kin)
         check(self.lib.mpb_sa_gemm_tn(self.gd, ptr(dYt), ptr(Xt), ptr(Xt_lo), ptr(dW), Nout, Kin, self.Bp, None, None, 0, None, 0, None, None, None,
                                       stream_ptr()), "mpb_sa_gemm_tn(head dW)")
         return dW
@@ -145,6 +145,7 @@ class HeadsFunction(torch.autograd.Function):
 
         ctx.cfg, ctx.B = cfg, B
         ctx.names = HeadsFunction.param_names()
+        ctx.sinks = {n: gradsink.lookup(t) for n, t in P.items()} if gradsink.active() else {}
         keep = [Ft, Ft_lo, h1[2], h1[3], h2[2], h2[3], m1[2], m1[3], m2[2], m2[3], Ytn]
         for n in ("fc1", "fc2", "sm_fc1", "sm_fc2"):
             keep += list(saved[n])
@@ -166,20 +167,26 @@ class HeadsFunction(torch.autograd.Function):
         training, drop_p = cfg["training"], cfg["drop_p"] if cfg["training"] else 0.0
         seed, step = cfg["seed"], cfg["step"]
         G = {}
+        S = ctx.sinks
+
+        def vec(name, n):
+            """gradient vector of a small parameter: its view of the flat buffer when one is registered"""
+            t = S.get(name)
+            return t if t is not None else k.empty(n)
 
         def act_bwd(name_fc, name_bn, layer, dXt):
             Yt, mean, rstd = pre[name_fc]
             F = Yt.shape[0]
             dYt = k.empty(F, Bp)
-            dg, db, dbias = k.empty(F), k.empty(F), k.empty(F)
+            dg, db, dbias = vec(name_bn + ".weight", F), vec(name_bn + ".bias", F), vec(name_fc + ".bias", F)
             check(lib.mpb_head_act_bwd(ptr(dXt), ptr(Yt), F, B, Bp, ptr(P[name_fc + ".bias"]), ptr(P[name_bn + ".weight"]), ptr(P[name_bn + ".bias"]),
                                        ptr(mean), ptr(rstd), 1 if training else 0, drop_p, seed, ptr(step), layer, ptr(dYt), ptr(dg), ptr(db), ptr(dbias),
                                        stream_ptr()), "mpb_head_act_bwd")
             G[name_bn + ".weight"], G[name_bn + ".bias"], G[name_fc + ".bias"] = dg, db, dbias
             return dYt
 
-        def to_feature_major(dY, F):
-            dYt, dbias = k.empty(F, Bp), k.empty(F)
+        def to_feature_major(dY, F, bias_name):
+            dYt, dbias = k.empty(F, Bp), vec(bias_name, F)
             check(lib.mpb_head_to_feature_major(ptr(dY), B, Bp, F, ptr(dYt), None, ptr(dbias), stream_ptr()), "mpb_head_to_feature_major")
             return dYt, dbias
 
@@ -190,38 +197,41 @@ class HeadsFunction(torch.autograd.Function):
         # stroke-mask head backward on the side stream
         with streams.Fork(d_masks, d_scores, M2t, M1t, Ft) as fork:
             n3, nc = P["sm_fc3.weight"].shape[0], P["mask_conf_out.weight"].shape[0]
-            dYs3, G["sm_fc3.bias"] = to_feature_major(d_masks, n3)
-            dYc, G["mask_conf_out.bias"] = to_feature_major(d_scores, nc)
-            G["sm_fc3.weight"] = k.linear_dw(dYs3, M2t, M2t_lo, M2t.shape[0])
-            G["mask_conf_out.weight"] = k.linear_dw(dYc, M2t, M2t_lo, M2t.shape[0])
+            dYs3, G["sm_fc3.bias"] = to_feature_major(d_masks, n3, "sm_fc3.bias")
+            dYc, G["mask_conf_out.bias"] = to_feature_major(d_scores, nc, "mask_conf_out.bias")
+            G["sm_fc3.weight"] = k.linear_dw(dYs3, M2t, M2t_lo, M2t.shape[0], out=S.get("sm_fc3.weight"))
+            G["mask_conf_out.weight"] = k.linear_dw(dYc, M2t, M2t_lo, M2t.shape[0], out=S.get("mask_conf_out.weight"))
             dM2t = k.linear_dx(P["sm_fc3.weight"], dYs3)
             k.linear_dx(P["mask_conf_out.weight"], dYc, out=dM2t)
             dYs2 = act_bwd("sm_fc2", "sm_bn2", 3, dM2t)
-            G["sm_fc2.weight"] = k.linear_dw(dYs2, M1t, M1t_lo, M1t.shape[0])
+            G["sm_fc2.weight"] = k.linear_dw(dYs2, M1t, M1t_lo, M1t.shape[0], out=S.get("sm_fc2.weight"))
             dM1t = k.linear_dx(P["sm_fc2.weight"], dYs2)
             dYs1 = act_bwd("sm_fc1", "sm_bn1", 2, dM1t)
-            G["sm_fc1.weight"] = k.linear_dw(dYs1, Ft, Ft_lo, Kf)
+            G["sm_fc1.weight"] = k.linear_dw(dYs1, Ft, Ft_lo, Kf, out=S.get("sm_fc1.weight"))
             dF_mask = k.linear_dx(P["sm_fc1.weight"], dYs1)
         n_pose = P["fc3.weight"].shape[0] // 3
         dYt3, dYtn = k.empty(3 * n_pose, Bp), k.empty(3 * n_pose, Bp)
-        G["fc3.bias"], G["fc_normals.bias"] = k.empty(3 * n_pose), k.empty(3 * n_pose)
+        G["fc3.bias"], G["fc_normals.bias"] = vec("fc3.bias", 3 * n_pose), vec("fc_normals.bias", 3 * n_pose)
         check(lib.mpb_head_pose_out_bwd(ptr(d_out), ptr(Ytn), ptr(P["fc_normals.bias"]), B, Bp, n_pose, cfg["weight_orient"], ptr(dYt3), ptr(dYtn),
                                         ptr(G["fc3.bias"]), ptr(G["fc_normals.bias"]), stream_ptr()), "mpb_head_pose_out_bwd")
-        G["fc3.weight"] = k.linear_dw(dYt3, H2t, H2t_lo, H2t.shape[0])
-        G["fc_normals.weight"] = k.linear_dw(dYtn, H2t, H2t_lo, H2t.shape[0])
+        G["fc3.weight"] = k.linear_dw(dYt3, H2t, H2t_lo, H2t.shape[0], out=S.get("fc3.weight"))
+        G["fc_normals.weight"] = k.linear_dw(dYtn, H2t, H2t_lo, H2t.shape[0], out=S.get("fc_normals.weight"))
         dH2t = k.linear_dx(P["fc3.weight"], dYt3)
         k.linear_dx(P["fc_normals.weight"], dYtn, out=dH2t)
         dYt2 = act_bwd("fc2", "bn2", 1, dH2t)
-        G["fc2.weight"] = k.linear_dw(dYt2, H1t, H1t_lo, H1t.shape[0])
+        G["fc2.weight"] = k.linear_dw(dYt2, H1t, H1t_lo, H1t.shape[0], out=S.get("fc2.weight"))
         dH1t = k.linear_dx(P["fc2.weight"], dYt2)
         dYt1 = act_bwd("fc1", "bn1", 0, dH1t)
-        G["fc1.weight"] = k.linear_dw(dYt1, Ft, Ft_lo, Kf)
+        G["fc1.weight"] = k.linear_dw(dYt1, Ft, Ft_lo, Kf, out=S.get("fc1.weight"))
         dFt = k.linear_dx(P["fc1.weight"], dYt1)
         fork.join(dF_mask, *[G[n] for n in G if n.startswith(("sm_", "mask_conf"))])
         dFt += dF_mask
         d_feat = k.empty(B, Kf)
         check(lib.mpb_head_to_batch_major(ptr(dFt), None, B, Bp, Kf, ptr(d_feat), stream_ptr()), "mpb_head_to_batch_major")
-        grads = [G.get(n) for n in ctx.names]      # running statistics: None
+        # running statistics: None; parameters whose gradient went straight into the flat buffer: None as well
+        grads = [None if S.get(n) is not None else G.get(n) for n in ctx.names]
+        if gradsink.HOOKS["heads_done"] is not None:
+            gradsink.HOOKS["heads_done"]()
         return (d_feat, None, *grads)
 
     @staticmethod

@@ -39,6 +39,10 @@ class LossConfig:
     explicit_weight_stroke_masks_confidence: float = 100.0
     explicit_no_stroke_weight: float = 1.0
     pose_dim: int = 6                                    # get_dim_traj_points(['orientnorm'])
+    # Data parallel only: normalise the matched-pair BCE (:906, `.mean()` over all matched pairs of the batch) by the
+    # GLOBAL pair count (one scalar all-reduce) so that the rank-averaged gradient equals the single-process one;
+    # False = each rank takes the mean over its own shard (plain DDP behaviour).
+    mask_loss_global_mean: bool = False
 
 
 def chamfer_terms_13(y_pred, y, cfg, fused=True):
@@ -153,7 +157,13 @@ def stroke_masks_loss(pred_to_gt_match, pred_stroke_masks, scores, stroke_ids, c
         # matched pairs as dense [B, T] slots, absent strokes masked out (the reference stacks them, :886-902)
         sel = pred_stroke_masks.gather(1, row_c[:, :, None].expand(B, n_ids, out_segments))          # pred mask matched to stroke t
         bce = F.binary_cross_entropy_with_logits(sel, onehot.transpose(1, 2), reduction="none").sum(-1)   # [B, T]
-        mask_loss = (bce * pres_f).sum() / pres_f.sum()                          # :906  mean over all matched pairs in the batch
+        n_pairs = pres_f.sum()
+        if cfg.mask_loss_global_mean and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            n_glob = n_pairs.detach().clone()
+            torch.distributed.all_reduce(n_glob)
+            n_pairs = n_glob / torch.distributed.get_world_size()                # rank-mean of (sum_r / this) = global sum / global count
+        mask_loss = (bce * pres_f).sum() / n_pairs                               # :906  mean over all matched pairs in the batch
         target_scores = torch.zeros_like(scores).scatter_add_(1, row_c, pres_f)  # :920-921 (each mask matched at most once)
         weights = cfg.explicit_no_stroke_weight + (1.0 - cfg.explicit_no_stroke_weight) * target_scores   # :924-925
         conf_loss = F.binary_cross_entropy_with_logits(scores, target_scores, reduction="none", weight=weights).mean()   # :930

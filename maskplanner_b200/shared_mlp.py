@@ -30,7 +30,7 @@ import os
 
 import torch
 
-from . import _cabi
+from . import _cabi, gradsink
 from ._cabi import check, ptr, stream_ptr
 
 # precision -> (GEMM dtype code of mpb_sa_gemm_*, activation dtype code of mpb_bn_*, torch storage dtype)
@@ -269,6 +269,7 @@ class SharedMLPMax(torch.autograd.Function):
         flat_w = []
         for wt, wt_lo in wts:
             flat_w += [wt, wt_lo]
+        ctx.sinks = [tuple(gradsink.lookup(flat[6 * l + j]) for j in range(4)) for l in range(L)] if gradsink.active() else None
         ctx.save_for_backward(argmax, *zs, *stats, *flat_w, *[flat[6 * l + 2] for l in range(L)], zmax, a0,
                               *(narrow if narrow is not None else ()))
         c_last = dims[-1][0]
@@ -314,8 +315,12 @@ class SharedMLPMax(torch.autograd.Function):
             pooled = l == L - 1
             is_narrow = l == 0 and narrow is not None
             coef = torch.empty(3, cout_p, dtype=torch.float32, device=dev)
-            dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
-            dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+            # data-parallel runs: the kernels write straight into the parameter's view of the flat gradient buffer and
+            # autograd gets None for it (maskplanner_b200.gradsink); the conv bias view is never written -- its gradient
+            # is exactly zero and the buffer starts zeroed
+            sink_w, sink_b, sink_g, sink_be = ctx.sinks[l] if ctx.sinks else (None, None, None, None)
+            dgamma = sink_g if sink_g is not None else torch.empty(cout, dtype=torch.float32, device=dev)
+            dbeta = sink_be if sink_be is not None else torch.empty(cout, dtype=torch.float32, device=dev)
             # zero-filled by the finalize launch: the (exactly zero) conv-bias gradient and, for the narrow first layer,
             # the weight-gradient accumulator of its fused backward kernel
             nw = cout_p * NARROW_LDW if is_narrow else 0
@@ -328,8 +333,13 @@ class SharedMLPMax(torch.autograd.Function):
                 dw = wbuf[:nw].view(cout_p, NARROW_LDW)
                 check(lib.mpb_sa_first_layer_bwd(ad, ptr(d_a), ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), ptr(coef),
                                                  *_narrow_args(narrow), cout_p, ptr(dw), NARROW_LDW, st), "mpb_sa_first_layer_bwd")
-                grads[0] = _unpermute_narrow_wgrad(dw, cout, cin)
-                grads[1], grads[2], grads[3] = dbias, dgamma, dbeta
+                g0 = _unpermute_narrow_wgrad(dw, cout, cin)
+                if sink_w is not None:
+                    sink_w.copy_(g0)
+                grads[0] = g0 if sink_w is None else None
+                grads[1] = dbias if sink_b is None else None
+                grads[2] = dgamma if sink_g is None else None
+                grads[3] = dbeta if sink_be is None else None
                 d_a = None
                 break
             dz = torch.empty(M, cout_p, dtype=tdt, device=dev)
@@ -342,7 +352,7 @@ class SharedMLPMax(torch.autograd.Function):
             # weight gradient against the layer's input f_{l-1}(Z_{l-1}) (or the stored first-layer rows)
             ps = stats[l - 1] if l > 0 else None
             real = (cin if l == 0 else dims[l - 1][0], cout)
-            dw = torch.empty(cout, cin, dtype=torch.float32, device=dev)
+            dw = sink_w.view(cout, cin) if sink_w is not None else torch.empty(cout, cin, dtype=torch.float32, device=dev)
             if l > 0 and not FUSE_APPLY:
                 a_prev = torch.empty(M, cin_p, dtype=tdt, device=dev)
                 check(lib.mpb_bn_relu(ad, ptr(zs[l - 1]), ptr(ps[0]), ptr(ps[1]), M, cin_p, ptr(a_prev), st), "mpb_bn_relu")
@@ -350,10 +360,10 @@ class SharedMLPMax(torch.autograd.Function):
             else:
                 _gemm_wgrad(lib, gd, esz, dz, zs[l - 1] if l > 0 else a0, M, cout_p, cin_p, st, real, (ps[0], ps[1]) if l > 0 else None,
                             cout, cin, ctx.xyz_last and l == 0, dw)
-            grads[6 * l] = dw.view(cout, cin, 1, 1)
-            grads[6 * l + 1] = dbias                                                   # exact zeros: BN removes the conv bias
-            grads[6 * l + 2] = dgamma
-            grads[6 * l + 3] = dbeta
+            grads[6 * l] = dw.view(cout, cin, 1, 1) if sink_w is None else None
+            grads[6 * l + 1] = dbias if sink_b is None else None                       # exact zeros: BN removes the conv bias
+            grads[6 * l + 2] = dgamma if sink_g is None else None
+            grads[6 * l + 3] = dbeta if sink_be is None else None
             need_da = l > 0 or (ctx.has_a0 and ctx.needs_input_grad[0])
             d_prev = None
             if need_da:

@@ -15,13 +15,16 @@ loss, backward, all-reduce, Adam -- is captured once into a CUDA graph and repla
 step instead of ~600, which is what makes a ~5 ms step possible at all from Python.
 
 BatchNorm semantics: replica semantics (each rank normalises over its own samples), the standard DDP
-behaviour; single-process-equivalent statistics would need SyncBN and are out of scope for round 1.
+behaviour; single-process-equivalent statistics would need SyncBN (not built).  `Trainer.sync_bn_buffers()` averages
+the running statistics over the ranks before a checkpoint; `LossConfig.mask_loss_global_mean` makes the stroke-mask
+loss's mean over matched pairs (loss_handler.py:906) a mean over the GLOBAL batch instead of a mean of per-rank means.
 """
 import os
 
 import torch
 import torch.distributed as dist
 
+from . import gradsink
 from . import loss as L
 from . import optim, regressor, streams, synthetic
 from .pointnet2_utils import draw_fps_seed
@@ -44,13 +47,22 @@ class FlatGradBuckets:
         self.heads = self.flat[:n_heads]
         self.encoder = self.flat[n_heads:]
         off = 0
+        self.views = []
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(p.grad)
             off += pad4(p.numel())
         self.head_params = heads
 
     def zero(self):
         self.flat.zero_()
+
+    def register_sinks(self):
+        """Let the library's backward kernels write each gradient straight into its view (maskplanner_b200.gradsink):
+        no per-step memset, no AccumulateGrad read-modify-write passes."""
+        gradsink.clear()
+        for p, v in zip(self.params, self.views):
+            gradsink.register(p, v)
 
 
 def shard_range(global_batch, rank, world_size):
@@ -65,6 +77,13 @@ def all_reduce_mean_(flat, world_size, group=None):
     if world_size > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.mul_(1.0 / world_size)
+    return flat
+
+
+def all_reduce_sum_(flat, world_size, group=None):
+    """In-place SUM over ranks; the 1/world_size of the average is folded into the optimizer kernel (grad_scale)."""
+    if world_size > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
 
 
@@ -118,6 +137,16 @@ class Trainer:
         # gradients are left unset between steps and autograd hands its freshly computed tensors over as .grad -- this
         # saves one read-modify-write accumulation kernel per parameter (~80 launches) and the flat-buffer memset.
         self.buckets = FlatGradBuckets(self.model) if world_size > 1 else None
+        # Direct gradient placement (DP): every gradient is written by its producing kernel into the flat buffer, the
+        # collective sums it and the 1/W of the average rides in the Adam kernel.  Needs the fused heads (all parameters
+        # then come from this library's autograd nodes) and this library's Adam; MPB_DIRECT_GRADS=0 restores the round-1
+        # plumbing (memset + AccumulateGrad + scaling passes) for A/B runs.
+        self.direct_grads = (world_size > 1 and self.model.fused_heads and os.environ.get("MPB_DIRECT_GRADS", "1") == "1"
+                             and os.environ.get("MPB_TORCH_ADAM", "0") != "1")
+        if self.direct_grads:
+            self.buckets.register_sinks()
+        else:
+            gradsink.clear()
         # one-launch Adam (csrc/adam.cu); MPB_TORCH_ADAM=1 swaps torch's fused implementation back in for A/B runs
         if os.environ.get("MPB_TORCH_ADAM", "0") == "1":
             self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True, capturable=use_graph)
@@ -138,7 +167,22 @@ class Trainer:
         self._static_loss = None
         self._calls = 0
         self._graph_warmup_steps = graph_warmup_steps
-        if world_size > 1:
+        if self.direct_grads:
+            def heads_done():
+                # called at the end of the heads' backward node: every head gradient has been ENQUEUED (on the step's
+                # stream or on the side stream the stroke-mask head runs on); the collective waits for both
+                producers = {torch.cuda.current_stream(), self._step_stream}
+                if streams.enabled():
+                    producers.add(streams.side_stream(self.device))
+                for s in producers:
+                    if s is not None:
+                        self.comm_stream.wait_stream(s)
+                with torch.cuda.stream(self.comm_stream):
+                    all_reduce_sum_(self.buckets.heads, self.world_size)
+                self._heads_ready = torch.cuda.Event()
+                self._heads_ready.record(self.comm_stream)
+            gradsink.HOOKS["heads_done"] = heads_done
+        elif world_size > 1:
             # launch the head-bucket all-reduce on the side stream as soon as backward has produced the
             # LAST head gradient (counted, so no assumption about autograd's execution order)
             n_heads = len(self.buckets.head_params)
@@ -160,6 +204,16 @@ class Trainer:
             for p in self.buckets.head_params:
                 p.register_post_accumulate_grad_hook(hook)
 
+    def sync_bn_buffers(self):
+        """Average the BatchNorm running statistics over the ranks (replica semantics lets them drift apart; call before
+        saving a checkpoint so the result does not depend on which rank writes it)."""
+        if self.world_size <= 1:
+            return
+        for name, buf in self.model.named_buffers():
+            if name.endswith(("running_mean", "running_var")):
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                buf.div_(self.world_size)
+
     def to_device(self, host_batch):
         """The step's H2D boundary (train_maskplanner.py:207-208, loss_handler.py:628-629): pinned -> device, async."""
         if not host_batch["stroke_ids"].is_cuda:
@@ -178,7 +232,8 @@ class Trainer:
     def _step_body(self, batch, fps_seeds):
         self._step_stream = torch.cuda.current_stream()
         if self.buckets is not None:                                              # model.zero_grad()  (:184)
-            self.buckets.zero()
+            if not self.direct_grads:
+                self.buckets.zero()       # direct placement overwrites every gradient each step: nothing to clear
         else:
             for p in self.model.parameters():
                 p.grad = None
@@ -190,13 +245,17 @@ class Trainer:
         self._heads_pending = 0
         loss.backward()                                                           # :220
         if self.world_size > 1:
-            all_reduce_mean_(self.buckets.encoder, self.world_size)
+            reduce_ = all_reduce_sum_ if self.direct_grads else all_reduce_mean_
+            reduce_(self.buckets.encoder, self.world_size)
             if self._heads_ready is not None:
                 torch.cuda.current_stream().wait_event(self._heads_ready)
                 self._heads_ready = None
             else:  # hooks did not all fire (a head without gradient): reduce the bucket here
-                all_reduce_mean_(self.buckets.heads, self.world_size)
-        self.opt.step()                                                           # :221
+                reduce_(self.buckets.heads, self.world_size)
+        if self.direct_grads:
+            self.opt.step(grad_scale=1.0 / self.world_size)                       # :221 (the buffer holds the SUM over ranks)
+        else:
+            self.opt.step()                                                       # :221
         return loss.detach()
 
     def step(self, batch, fps_seeds=None):

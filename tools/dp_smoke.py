@@ -28,6 +28,7 @@ flat = torch.cat([p.detach().flatten() for p in tr.model.parameters()])
 other = flat.clone()
 dist.broadcast(other, src=0)
 log("param max diff vs rank0", float((flat - other).abs().max()))
+log("direct_grads", tr.direct_grads, "param checksum %.9e %.9e" % (float(flat.double().sum()), float(flat.double().abs().sum())))
 dist.barrier()
 torch.cuda.synchronize()
 log("done")
