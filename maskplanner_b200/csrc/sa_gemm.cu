@@ -121,56 +121,73 @@ __device__ __forceinline__ float warp_column_sum_32x32(float (&v)[32], int lane)
     return v[0];
 }
 
-// In-place transform of one 128-byte row chunk set: `row` points at a 128-byte swizzled row (8 chunks of 16 bytes),
-// `r7` = row index & 7 (the swizzle key), `ch0` = channel of the row's first element, `lo` = where the low part of the
-// TF32 split goes (same swizzled offsets in a second tile).  sc/sh: per-channel scale / shift in shared memory.
-template <int DT, bool XFORM, bool ATOM32 = false>
-__device__ __forceinline__ void transform_row(uint8_t *row, uint8_t *row_lo, int r7, const float *sc, const float *sh, bool valid,
-                                              int c_begin = 0, int c_end = 8)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
 {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // max(x, 0) folded into the rounding conversion
+    return d;
+}
+
+// Column-owner form of the same transform: the thread owns ONE logical 16-byte chunk `c` (8 bf16 / 4 fp32 channels) of
+// the rows r0, r0 + RSTEP, ... (NR of them) of a box of 128-byte swizzled rows, so its per-channel scale / shift sit in
+// registers for the whole box (the row-owner form re-read them from shared memory for every chunk: four uniform
+// 16-byte loads per data load, 3/4 of the kernel's shared-memory wavefronts in the ncu capture) and, RSTEP being a
+// multiple of 8, the swizzled chunk position is a per-thread constant.  A quarter warp (8 lanes = the 8 chunks of one
+// row) touches one whole 128-byte row per access: conflict-free.  Rows >= rows_valid (TMA zero fill past M) stay zero.
+template <int DT, bool XFORM, bool ATOM32, int NR, int RSTEP>
+__device__ __forceinline__ void transform_cols(uint8_t *box, uint8_t *box_lo, int c, int r0, const float *sc, const float *sh, int rows_valid)
+{
+    static_assert(RSTEP % 8 == 0, "the swizzle key must not change along the thread's rows");
+    const int r7 = r0 & 7;
+    const int off = ATOM32 ? (((((c >> 1) ^ (r7 & 3)) << 1) | (c & 1)) << 4) : ((c ^ r7) << 4);
+    uint8_t *p0 = box + r0 * 128 + off;
+    uint4 raw[NR];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        if (c < c_begin || c >= c_end) continue;
-        // SWIZZLE_128B: logical 16-byte chunk c sits at physical chunk c ^ (row & 7);
-        // 32-byte-atom variant: logical 32-byte chunk c >> 1 sits at (c >> 1) ^ (row & 3), its two halves stay in order
-        const int off = ATOM32 ? (((((c >> 1) ^ (r7 & 3)) << 1) | (c & 1)) << 4) : ((c ^ r7) << 4);
-        uint4 raw = *reinterpret_cast<const uint4 *>(row + off);
-        if (DT == DT_BF16) {
-            float f[8];
-            float2 t;
-            t = unpack_bf16(raw.x), f[0] = t.x, f[1] = t.y;
-            t = unpack_bf16(raw.y), f[2] = t.x, f[3] = t.y;
-            t = unpack_bf16(raw.z), f[4] = t.x, f[5] = t.y;
-            t = unpack_bf16(raw.w), f[6] = t.x, f[7] = t.y;
-            if (XFORM) {
-                const float4 s0 = *reinterpret_cast<const float4 *>(sc + c * 8), s1 = *reinterpret_cast<const float4 *>(sc + c * 8 + 4);
-                const float4 h0 = *reinterpret_cast<const float4 *>(sh + c * 8), h1 = *reinterpret_cast<const float4 *>(sh + c * 8 + 4);
-                f[0] = fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), f[1] = fmaxf(fmaf(f[1], s0.y, h0.y), 0.f);
-                f[2] = fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), f[3] = fmaxf(fmaf(f[3], s0.w, h0.w), 0.f);
-                f[4] = fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), f[5] = fmaxf(fmaf(f[5], s1.y, h1.y), 0.f);
-                f[6] = fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), f[7] = fmaxf(fmaf(f[7], s1.w, h1.w), 0.f);
-            }
-            if (!valid) {
+    for (int j = 0; j < NR; ++j) raw[j] = *reinterpret_cast<const uint4 *>(p0 + j * RSTEP * 128);
+    if (DT == DT_BF16) {
+        float2 s2[4], h2[4];
+        if (XFORM) {
+            const float4 s0 = *reinterpret_cast<const float4 *>(sc + c * 8), s1 = *reinterpret_cast<const float4 *>(sc + c * 8 + 4);
+            const float4 h0 = *reinterpret_cast<const float4 *>(sh + c * 8), h1 = *reinterpret_cast<const float4 *>(sh + c * 8 + 4);
+            s2[0] = make_float2(s0.x, s0.y), s2[1] = make_float2(s0.z, s0.w), s2[2] = make_float2(s1.x, s1.y), s2[3] = make_float2(s1.z, s1.w);
+            h2[0] = make_float2(h0.x, h0.y), h2[1] = make_float2(h0.z, h0.w), h2[2] = make_float2(h1.x, h1.y), h2[3] = make_float2(h1.z, h1.w);
+        }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = 0.f;
+        for (int j = 0; j < NR; ++j) {
+            const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float2 x = unpack_bf16(w[u]);
+                if (XFORM) {
+                    x = __ffma2_rn(x, s2[u], h2[u]);
+                    o[u] = pack_bf16_relu(x.x, x.y);
+                } else {
+                    o[u] = w[u];
+                }
             }
-            *reinterpret_cast<uint4 *>(row + off) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        } else {
-            float f[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+            const bool valid = r0 + j * RSTEP < rows_valid;
+            *reinterpret_cast<uint4 *>(p0 + j * RSTEP * 128) = valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (XFORM) s4 = *reinterpret_cast<const float4 *>(sc + c * 4), h4 = *reinterpret_cast<const float4 *>(sh + c * 4);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            float f[4] = {__uint_as_float(raw[j].x), __uint_as_float(raw[j].y), __uint_as_float(raw[j].z), __uint_as_float(raw[j].w)};
             if (XFORM) {
-                const float4 s0 = *reinterpret_cast<const float4 *>(sc + c * 4), h0 = *reinterpret_cast<const float4 *>(sh + c * 4);
-                f[0] = fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), f[1] = fmaxf(fmaf(f[1], s0.y, h0.y), 0.f);
-                f[2] = fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), f[3] = fmaxf(fmaf(f[3], s0.w, h0.w), 0.f);
+                f[0] = fmaxf(fmaf(f[0], s4.x, h4.x), 0.f), f[1] = fmaxf(fmaf(f[1], s4.y, h4.y), 0.f);
+                f[2] = fmaxf(fmaf(f[2], s4.z, h4.z), 0.f), f[3] = fmaxf(fmaf(f[3], s4.w, h4.w), 0.f);
             }
-            if (!valid) f[0] = f[1] = f[2] = f[3] = 0.f;
+            if (!(r0 + j * RSTEP < rows_valid)) f[0] = f[1] = f[2] = f[3] = 0.f;
             if (DT == DT_TF32X3) {
                 float hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) hi[i] = to_tf32(f[i]), lo[i] = f[i] - hi[i];   // exact difference; the MMA truncates lo to TF32
-                *reinterpret_cast<float4 *>(row + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(row_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4 *>(p0 + j * RSTEP * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(box_lo + r0 * 128 + off + j * RSTEP * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             } else {
-                *reinterpret_cast<float4 *>(row + off) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4 *>(p0 + j * RSTEP * 128) = make_float4(f[0], f[1], f[2], f[3]);
             }
         }
     }
@@ -248,7 +265,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < stages; ++s) {
             mbar_init(&tail->full[s], 1);
             mbar_init(&tail->empty[s], 1);
-            mbar_init(&tail->ready[s], 8);
+            mbar_init(&tail->ready[s], 4);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tail->tfull[a], 1);
@@ -322,22 +339,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (kXf && warp >= 12) {
-        // two transform warpgroups: thread t owns half (four 16-byte chunks) of row t & 127 of the landed A tile
-        const int t = threadIdx.x - 384;
-        const int row_i = t & 127, half = t >> 7;
-        const int r7 = row_i & 7;
-        int stage = 0;
+        // two transform warpgroups work on ALTERNATE k-blocks (two stages in flight: the wake-up, shared-memory and proxy-fence
+        // latencies of one overlap the other's); inside a warpgroup thread t owns chunk t & 7 of the rows (t >> 3) + 16 j
+        const int wg = (warp - 12) >> 2;
+        const int t = (threadIdx.x - 384) & 127;
+        const int c = t & 7, r0 = t >> 3;
+        int stage = 0, it = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * kTileM;
-            const bool valid = m0 + row_i < M;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&tail->full[stage], phase);
-                uint8_t *row = smem + (size_t)stage * stage_bytes + row_i * 128;
-                transform_row<DT, XFORM>(row, row + kABytes, r7, s_ascale + kb * EPR, s_ashift + kb * EPR, valid, 4 * half, 4 * half + 4);
-                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tail->ready[stage]);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                if ((it & 1) == wg) {
+                    mbar_wait(&tail->full[stage], phase);
+                    uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                    transform_cols<DT, XFORM, false, 8, 16>(sa, sa + kABytes, c, r0, s_ascale + kb * EPR, s_ashift + kb * EPR, M - m0);
+                    fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                }
                 if (++stage == stages) stage = 0, phase ^= 1;
             }
         }
@@ -706,28 +725,25 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
                 umma_commit(&tail->tfull[0]);
             }
         } else if (kXf && warp >= 8) {
-            // transform warpgroup: 128 threads walk the (box, row) pairs of the stage that need rewriting
+            // transform warpgroup: thread t owns chunk t & 7 of the rows (t >> 3) + 16 j of every box that needs rewriting
             const int t = threadIdx.x - 256;
+            const int c = t & 7, r0 = t >> 3;
             int stage = 0;
             uint32_t phase = 0;
             const int first_box = DT == DT_TF32X3 ? 0 : ZB;            // bf16 / single-pass tf32: only the A boxes change
             for (int rb = 0; rb < num_rb; ++rb) {
                 mbar_wait(&tail->full[stage], phase);
                 uint8_t *s = smem + (size_t)stage * stage_bytes;
-                const int r0 = m_begin + rb * RB;
-                for (int item = t; item < (ZB + AB) * RB; item += 128) {
-                    const int box = item / RB, r = item - box * RB;
-                    if (box < first_box) continue;
+                // rows past M were zero-filled by the TMA; they must stay zero through relu(shift)
+                const int rows_valid = M - (m_begin + rb * RB);
+                for (int box = first_box; box < ZB + AB; ++box) {
                     if (box < ZB ? (box >= a_boxes) : (box - ZB >= b_boxes)) continue;
-                    uint8_t *row = s + (size_t)box * kBox + r * 128;
-                    const bool is_a = box >= ZB;
-                    const float *sc = s_ascale + (is_a ? (box - ZB) * EPR : 0), *sh = s_ashift + (is_a ? (box - ZB) * EPR : 0);
-                    // rows past M were zero-filled by the TMA; they must stay zero through relu(shift)
-                    const bool valid = r0 + r < M;
-                    if (XFORM && is_a)
-                        transform_row<DT, true, DT != DT_BF16>(row, row + half_bytes, r & 7, sc, sh, valid);
+                    uint8_t *bp = s + (size_t)box * kBox;
+                    if (XFORM && box >= ZB)
+                        transform_cols<DT, true, DT != DT_BF16, RB / 16, 16>(bp, bp + half_bytes, c, r0, s_ascale + (box - ZB) * EPR,
+                                                                             s_ashift + (box - ZB) * EPR, rows_valid);
                     else
-                        transform_row<DT, false, DT != DT_BF16>(row, row + half_bytes, r & 7, sc, sh, valid);
+                        transform_cols<DT, false, DT != DT_BF16, RB / 16, 16>(bp, bp + half_bytes, c, r0, s_ascale, s_ashift, rows_valid);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();

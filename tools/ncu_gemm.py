@@ -13,6 +13,16 @@ CASES = {
     "dgrad_epi2": lambda: cg.run_tn(0, 524288, 128, 256, False, 2),
     "wgrad": lambda: cg.run_wg(0, 524288, 256, 128, False),
     "wgrad_xf": lambda: cg.run_wg(0, 524288, 256, 128, True),
+    "sa1_fwd_l1": lambda: cg.run_tn(0, 1048576, 64, 64, True, 1),
+    "sa1_fwd_l2": lambda: cg.run_tn(0, 1048576, 128, 64, True, 1),
+    "sa1_dgrad_l2": lambda: cg.run_tn(0, 1048576, 64, 128, False, 2),
+    "sa1_dgrad_l1": lambda: cg.run_tn(0, 1048576, 64, 64, False, 2),
+    "sa1_wgrad_l2": lambda: cg.run_wg(0, 1048576, 128, 64, True),
+    "sa1_wgrad_l1": lambda: cg.run_wg(0, 1048576, 64, 64, True),
+    "sa2_fwd_l0": lambda: cg.run_tn(0, 524288, 128, 192, False, 1),
+    "sa2_fwd_l2": lambda: cg.run_tn(0, 524288, 256, 128, True, 1),
+    "sa2_dgrad_l0": lambda: cg.run_tn(0, 524288, 192, 128, False, 0),
+    "sa2_wgrad_l0": lambda: cg.run_wg(0, 524288, 128, 192, False),
     "fwd_x3": lambda: cg.run_tn(2, 524288, 128, 128, True, 1),
     "wgrad_x3": lambda: cg.run_wg(2, 524288, 256, 128, True),
 }
