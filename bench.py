@@ -336,14 +336,15 @@ def timed_steps(trainer, resident, steps, warmup, ws, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # every call announces the batch of the next call: its sampling plan (FPS / ball query) is computed inside this step
     for i in range(warmup):
-        trainer.step(resident[i % 3])
+        trainer.step(resident[i % 3], next_batch=resident[(i + 1) % 3])
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.monotonic()
     a.record()
     for i in range(steps):
-        trainer.step(resident[i % 3])
+        trainer.step(resident[i % 3], next_batch=resident[(i + 1) % 3])
     b.record()
     barrier()
     t1 = time.monotonic()
@@ -398,11 +399,12 @@ def run_ours(args, ws, rank, local):
     # end to end through the public step API: pinned host batch -> H2D -> step -> loss.item() (D2H); every step's batch is
     # copied inside the timed region (the copy of batch i+1 is issued while step i runs, like a prefetching loader)
     for i in range(3):          # warm the end-to-end path (side-stream allocator pool, pinned-copy plumbing) before timing it
-        trainer.step_from_host(host[i % 3], next_host_batch=host[(i + 1) % 3])
+        trainer.step_from_host(host[i % 3], next_host_batch=host[(i + 1) % 3], after_next_host_batch=host[(i + 2) % 3])
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        lv = trainer.step_from_host(host[i % 3], next_host_batch=host[(i + 1) % 3])   # next batch's H2D overlaps this step
+        # the H2D copies of the next two batches overlap this step (the next batch's cloud feeds this step's side branch)
+        lv = trainer.step_from_host(host[i % 3], next_host_batch=host[(i + 1) % 3], after_next_host_batch=host[(i + 2) % 3])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev)

@@ -246,6 +246,35 @@ def get_mlp_precision():
     return _MLP_PRECISION
 
 
+def sampling_plan(xyz, specs, seeds=None, out=None):
+    """The index half of a chain of set-abstraction layers, which depends on the cloud alone (reference :130-132 of
+    every layer: FPS -> centroid gather -> ball query; the next layer samples the previous layer's centroids).
+
+    xyz [B,N,3]; specs = [(npoint, radius, nsample), ...]; seeds = per-layer FPS seed indices (None: drawn like the
+    reference).  Returns [(fps_idx [B,S] i64, new_xyz [B,S,3], idx [B,S,K] i64), ...].  Nothing here needs the features,
+    so a training loop can compute the plan of batch i+1 while batch i is still in flight (Trainer, pipeline_sampling).
+    `out`: optional preallocated plan (same shapes) to write into (fixed addresses for CUDA-graph replay)."""
+    plan = []
+    cur = xyz
+    for l, (npoint, radius, nsample) in enumerate(specs):
+        fps_idx = farthest_point_sample(cur, npoint, None if seeds is None else seeds[l])
+        new_xyz = index_points(cur, fps_idx)
+        idx = query_ball_point(radius, nsample, cur, new_xyz)
+        if out is not None:
+            for dst, src in zip(out[l], (fps_idx, new_xyz, idx)):
+                dst.copy_(src)
+            fps_idx, new_xyz, idx = out[l]
+        plan.append((fps_idx, new_xyz, idx))
+        cur = new_xyz
+    return plan
+
+
+def empty_sampling_plan(B, specs, device):
+    """Preallocated buffers with the shapes sampling_plan() returns."""
+    return [(torch.zeros(B, S, dtype=torch.long, device=device), torch.zeros(B, S, 3, dtype=torch.float32, device=device),
+             torch.zeros(B, S, K, dtype=torch.long, device=device)) for (S, _r, K) in specs]
+
+
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, full_points=None, seed_idx=None):
     """Reference :112-148.  xyz [B,N,3], points [B,N,D]|None -> new_xyz [B,S,3], new_points [B,S,K,3+D]
     (or [B,S,K,C_full] with `full_points`; 4-tuple with `returnfps`)."""
@@ -306,14 +335,16 @@ class PointNetSetAbstraction(nn.Module):
         self.contiguous_output = True
         self.precision = None   # None -> module-level default (set_mlp_precision); or "bf16" / "tf32" / "fp32"
 
-    def forward(self, xyz, points, full_points=None, seed_idx=None):
+    def forward(self, xyz, points, full_points=None, seed_idx=None, sampling=None):
+        """`sampling` (extension): a precomputed (fps_idx, new_xyz, idx) triple of this layer from sampling_plan()."""
         xyz = xyz.permute(0, 2, 1)                                                      # :196
         if points is not None:
             points = points.permute(0, 2, 1)
         if full_points is not None:
             full_points = full_points.permute(0, 2, 1)
         if self.training or not torch.is_grad_enabled():
-            return self._forward_tensor_core(xyz, points, full_points, seed_idx)
+            return self._forward_tensor_core(xyz, points, full_points, seed_idx, sampling)
+        assert sampling is None, "precomputed sampling is only wired into the tensor-core path"
         # eval mode WITH autograd (not on the training or inference path): stock torch ops below
         if self.group_all:
             new_xyz, new_points = sample_and_group_all(xyz, points)                     # :203
@@ -335,7 +366,7 @@ class PointNetSetAbstraction(nn.Module):
         out = torch.max(x, 2)[0].permute(0, 2, 1)                                    # [B,S,C'] -> [B,C',S]
         return out.contiguous() if self.contiguous_output else out
 
-    def _forward_tensor_core(self, xyz, points, full_points, seed_idx):
+    def _forward_tensor_core(self, xyz, points, full_points, seed_idx, sampling=None):
         """Reference :203-215 with the grouped tensor produced directly as GEMM rows (bf16 or fp32, by precision)
         and the MLP on tcgen05 (maskplanner_b200.shared_mlp).  xyz [B,N,3], points [B,N,D]|None (position-major)."""
         from .shared_mlp import MODES, narrow_rows_supported, pad64, shared_mlp_max
@@ -349,9 +380,13 @@ class PointNetSetAbstraction(nn.Module):
             S, K = 1, N
         else:
             S, K = self.npoint, self.nsample
-            fps_idx = farthest_point_sample(xyz, S, seed_idx)                           # :130
-            new_xyz = index_points(xyz, fps_idx)                                        # :131
-            idx = query_ball_point(self.radius, K, xyz, new_xyz)                        # :132
+            if sampling is not None:
+                fps_idx, new_xyz, idx = sampling
+                assert tuple(idx.shape) == (B, S, K), "sampling plan does not match this layer"
+            else:
+                fps_idx = farthest_point_sample(xyz, S, seed_idx)                       # :130
+                new_xyz = index_points(xyz, fps_idx)                                    # :131
+                idx = query_ball_point(self.radius, K, xyz, new_xyz)                    # :132
             rows = index_points(full_points, idx) if (points is None and full_points is not None) else None
         xyz_last = False
         if rows is not None:   # group-all / full_points: plain rows, padded (and rounded to bf16 in that mode)

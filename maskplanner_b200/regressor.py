@@ -66,21 +66,34 @@ class PointNet2Regressor_StrokeMasks(nn.Module):
         self.fused_heads = os.environ.get("MPB_FUSED_HEADS", "1") == "1"
         self._heads = None
 
-    def encode(self, xyz, fps_seeds=None):
+    def sampling_specs(self):
+        return [(self.sa1.npoint, self.sa1.radius, self.sa1.nsample), (self.sa2.npoint, self.sa2.radius, self.sa2.nsample)]
+
+    def sampling_plan(self, xyz, fps_seeds=None, out=None):
+        """FPS / centroid / ball-query indices of sa1 and sa2 for a cloud xyz [B,3,N] (they depend on the coordinates only)."""
+        from .pointnet2_utils import sampling_plan
+        return sampling_plan(xyz[:, :3, :].permute(0, 2, 1), self.sampling_specs(), fps_seeds, out=out)
+
+    def encode(self, xyz, fps_seeds=None, plan=None):
         """xyz [B,3,N] -> global feature [B,1024] (pointnet2_cls_ssg.py:297-309)."""
         B = xyz.shape[0]
         norm = xyz[:, 3:, :] if self.normal_channel else None
         if self.normal_channel:
             xyz = xyz[:, :3, :]
         s1, s2 = fps_seeds if fps_seeds is not None else (None, None)
-        l1_xyz, l1_points = self.sa1(xyz, norm, seed_idx=s1)
-        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, seed_idx=s2)
+        p1, p2 = plan if plan is not None else (None, None)
+        l1_xyz, l1_points = self.sa1(xyz, norm, seed_idx=s1, sampling=p1)
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, seed_idx=s2, sampling=p2)
         _, l3_points = self.sa3(l2_xyz, l2_points)
         return l3_points.reshape(B, 1024)
 
-    def forward(self, xyz, fps_seeds=None):
+    def forward(self, xyz, fps_seeds=None, plan=None, after_encode=None):
+        """plan: precomputed sampling_plan() of this cloud; after_encode: optional callable run between the encoder and
+        the heads (the Trainer forks the NEXT batch's sampling plan onto a side stream there)."""
         B = xyz.shape[0]
-        feat = self.encode(xyz, fps_seeds)
+        feat = self.encode(xyz, fps_seeds, plan)
+        if after_encode is not None:
+            after_encode()
         if self.fused_heads and feat.is_cuda and B <= 128:
             # MaskPlanner configuration: both heads as one autograd node over hand-written kernels (maskplanner_b200.heads)
             from .heads import FusedHeads

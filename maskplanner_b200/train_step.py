@@ -111,7 +111,7 @@ class Trainer:
     KEYS = ("point_cloud", "traj", "traj_as_pc", "stroke_ids")
 
     def __init__(self, category="windows_v2", device=None, lr=1e-3, seed=0, loss_cfg=None, world_size=1, fused_loss=True,
-                 use_graph=False, graph_warmup_steps=2, heads_tf32=None):
+                 use_graph=False, graph_warmup_steps=2, heads_tf32=None, pipeline_sampling=None):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         torch.manual_seed(seed)                       # identical initial weights on every rank
         self.model = regressor.maskplanner_model(category).to(self.device)
@@ -162,6 +162,16 @@ class Trainer:
         self._staged = None
         self._step_stream = None
         self.use_graph = use_graph
+        # Sampling pipelined across steps: the FPS / ball-query indices of sa1 and sa2 depend on the cloud alone, so the plan
+        # of the NEXT batch (step(..., next_batch=...)) is computed on a side stream while this batch's heads, loss and head
+        # backward run (small-grid kernels that leave most SMs idle), instead of heading the next step's critical path with a
+        # 64-CTA, 0.2 ms FPS that nothing can overlap.  The same work per step, every step; MPB_PIPELINE_SAMPLING=0 disables.
+        if pipeline_sampling is None:
+            pipeline_sampling = os.environ.get("MPB_PIPELINE_SAMPLING", "1") == "1"
+        self.pipeline_sampling = bool(pipeline_sampling)
+        self._plan_cur = self._plan_next = None      # preallocated plans (fixed addresses: graph replay)
+        self._plan_for = None                        # the cloud tensor `_plan_cur` was computed for
+        self._next_static = None
         self._graph = None
         self._static = None
         self._static_loss = None
@@ -220,16 +230,18 @@ class Trainer:
             L.validate_stroke_ids(host_batch["stroke_ids"], self.n_masks)       # host-side, no synchronisation
         return {k: host_batch[k].to(self.device, dtype=torch.float32, non_blocking=True) for k in self.KEYS}
 
-    def _step_core(self, batch, fps_seeds):
+    def _step_core(self, batch, fps_seeds, plan=None, nxt=None):
         old_tf32 = torch.backends.cuda.matmul.allow_tf32
         if self.heads_tf32:
             torch.backends.cuda.matmul.allow_tf32 = True  # head GEMMs (M = batch, library calls) on TF32 tensor cores
         try:
-            return self._step_body(batch, fps_seeds)
+            return self._step_body(batch, fps_seeds, plan, nxt)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
-    def _step_body(self, batch, fps_seeds):
+    def _step_body(self, batch, fps_seeds, plan=None, nxt=None):
+        """plan: sampling plan of this batch (None: computed in line).  nxt = (next cloud [B,N,3], next seeds, plan buffers):
+        the next batch's plan is computed on a side stream between the encoder forward and the end of the step."""
         self._step_stream = torch.cuda.current_stream()
         if self.buckets is not None:                                              # model.zero_grad()  (:184)
             if not self.direct_grads:
@@ -238,7 +250,18 @@ class Trainer:
             for p in self.model.parameters():
                 p.grad = None
         cloud = batch["point_cloud"].permute(0, 2, 1)                             # :207
-        pred, masks, scores, _ = self.model(cloud, fps_seeds)                     # :210
+        fork = None
+
+        def after_encode():
+            nonlocal fork
+            if nxt is None:
+                return
+            n_cloud, n_seeds, n_out = nxt
+            with streams.Fork(n_cloud, slot=2) as fork:
+                with torch.no_grad():
+                    self.model.sampling_plan(n_cloud.permute(0, 2, 1), n_seeds, out=n_out)
+
+        pred, masks, scores, _ = self.model(cloud, fps_seeds, plan=plan, after_encode=after_encode)   # :210
         loss = L.asymm_v6_chamfer_with_stroke_masks(pred, batch["traj"], masks, scores, batch["stroke_ids"],
                                                     batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss,
                                                     weights=self.loss_weights)    # :212-218
@@ -256,74 +279,153 @@ class Trainer:
             self.opt.step(grad_scale=1.0 / self.world_size)                       # :221 (the buffer holds the SUM over ranks)
         else:
             self.opt.step()                                                       # :221
+        if fork is not None:
+            fork.join()
+            if plan is not None:          # the plan just computed becomes the current one (backward has finished reading `plan`)
+                for dst3, src3 in zip(plan, nxt[2]):
+                    for dst, src in zip(dst3, src3):
+                        dst.copy_(src)
         return loss.detach()
 
-    def step(self, batch, fps_seeds=None):
+    def _ensure_plans(self, B):
+        if self._plan_cur is None or self._plan_cur[0][0].shape[0] != B:
+            from .pointnet2_utils import empty_sampling_plan
+            specs = self.model.sampling_specs()
+            self._plan_cur = empty_sampling_plan(B, specs, self.device)
+            self._plan_next = empty_sampling_plan(B, specs, self.device)
+            self._plan_for = None
+
+    def _draw_seeds(self, B, n_points):
+        return (draw_fps_seed(B, n_points, self.device), draw_fps_seed(B, self.model.sa1.npoint, self.device))
+
+    def step(self, batch, fps_seeds=None, next_batch=None, next_fps_seeds=None):
         """One optimisation step on a device-resident batch.  Returns the loss as a 0-d device tensor.
         `fps_seeds` = (seed indices for SA1 [B], for SA2 [B]); None draws them from the CPU generator exactly
-        like the reference does (models/pointnet2_utils.py:77, one randint per SA layer)."""
-        if not self.use_graph:
+        like the reference does (models/pointnet2_utils.py:77, one randint per SA layer).
+        `next_batch` (pipeline_sampling): the batch of the FOLLOWING call; its sampling plan (FPS seeds `next_fps_seeds`, or
+        drawn the same way) is computed during this step.  A batch whose plan was not announced that way, or explicit
+        `fps_seeds`, gets its plan computed in line first -- same results either way."""
+        pipe = self.pipeline_sampling
+        if not self.use_graph and not pipe:
             return self._step_core(batch, fps_seeds)
         self._calls += 1
+        B, n_points = batch["point_cloud"].shape[0], batch["point_cloud"].shape[1]
+        to_dev = lambda seeds: tuple(s.to(self.device, dtype=torch.long) for s in seeds)
+        plan = nxt = None
+        if pipe:
+            self._ensure_plans(B)
+            if fps_seeds is not None or self._plan_for is not batch["point_cloud"]:
+                seeds = to_dev(fps_seeds) if fps_seeds is not None else self._draw_seeds(B, n_points)
+                with torch.no_grad():
+                    self.model.sampling_plan(batch["point_cloud"].permute(0, 2, 1), seeds, out=self._plan_cur)
+            plan = self._plan_cur
+            self._plan_for = None
+            if next_batch is not None:
+                n_seeds = to_dev(next_fps_seeds) if next_fps_seeds is not None else self._draw_seeds(B, n_points)
+                n_cloud = next_batch["point_cloud"]
+                assert n_cloud.shape == batch["point_cloud"].shape, "pipelined sampling needs equal batch shapes"
+        if not self.use_graph:
+            if pipe and next_batch is not None:
+                nxt = (n_cloud, n_seeds, self._plan_next)
+            out = self._step_core(batch, fps_seeds, plan, nxt)
+            if nxt is not None:
+                self._plan_for = n_cloud
+            return out
         # host-side hyper-parameters a scheduler may have changed since the last call (learning rate:
         # train_maskplanner.py:230; loss weights: :186-199) -> device scalars the captured kernels read
         if hasattr(self.opt, "sync_hyper"):
             self.opt.sync_hyper()
         self.loss_weights.sync(self.loss_cfg)
         batch = pad_batch(batch, self.max_segments, self.max_poses)
-        B = batch["point_cloud"].shape[0]
-        if fps_seeds is None:
-            fps_seeds = (draw_fps_seed(B, batch["point_cloud"].shape[1], self.device), draw_fps_seed(B, 512, self.device))
-        else:
-            fps_seeds = tuple(s.to(self.device, dtype=torch.long) for s in fps_seeds)
-        if self._calls <= self._graph_warmup_steps:      # real eager steps: lazy initialisation + Adam state
-            return self._step_core(batch, fps_seeds)
-        if self._graph is None:
-            self._static = {k: batch[k].clone() for k in self.KEYS}
-            self._static["seeds"] = tuple(s.clone() for s in fps_seeds)
-            torch.cuda.synchronize()
-            from . import _cabi
-            n0 = _cabi.KERNEL_LAUNCHES
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._static_loss = self._step_core(self._static, self._static["seeds"])
-            self.kernels_per_step = _cabi.KERNEL_LAUNCHES - n0     # libmaskplanner_b200 kernels inside one replay
-        else:
-            for k in self.KEYS:
-                self._static[k].copy_(batch[k], non_blocking=True)
-            for dst, src in zip(self._static["seeds"], fps_seeds):
+        if not pipe:
+            if fps_seeds is None:
+                fps_seeds = self._draw_seeds(B, n_points)
+            else:
+                fps_seeds = to_dev(fps_seeds)
+        if pipe and self._next_static is None:
+            self._next_static = (torch.zeros_like(batch["point_cloud"]), tuple(torch.zeros(B, dtype=torch.long, device=self.device) for _ in range(2)))
+        if pipe and next_batch is not None:
+            self._next_static[0].copy_(n_cloud, non_blocking=True)
+            for dst, src in zip(self._next_static[1], n_seeds):
                 dst.copy_(src, non_blocking=True)
-        self._graph.replay()
-        return self._static_loss
+        if pipe:
+            # the side branch is part of the captured graph: without a next batch it recomputes a plan nobody will use
+            nxt = (self._next_static[0], self._next_static[1], self._plan_next)
+        if self._calls <= self._graph_warmup_steps:      # real eager steps: lazy initialisation + Adam state
+            out = self._step_core(batch, fps_seeds, plan, nxt)
+        else:
+            if self._graph is None:
+                self._static = {k: batch[k].clone() for k in self.KEYS}
+                if not pipe:
+                    self._static["seeds"] = tuple(s.clone() for s in fps_seeds)
+                torch.cuda.synchronize()
+                from . import _cabi
+                n0 = _cabi.KERNEL_LAUNCHES
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._static_loss = self._step_core(self._static, None if pipe else self._static["seeds"], plan, nxt)
+                self.kernels_per_step = _cabi.KERNEL_LAUNCHES - n0     # libmaskplanner_b200 kernels inside one replay
+            else:
+                for k in self.KEYS:
+                    self._static[k].copy_(batch[k], non_blocking=True)
+                if not pipe:
+                    for dst, src in zip(self._static["seeds"], fps_seeds):
+                        dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            out = self._static_loss
+        if pipe:
+            self._plan_for = n_cloud if next_batch is not None else None
+        return out
 
     def prefetch(self, host_batch):
         """Start the H2D copy of a FUTURE step's pinned batch on a side stream, so it overlaps the step in flight (what
         the reference's DataLoader workers + pin_memory + non_blocking copies do, train_maskplanner.py:207-208)."""
+        if self._staged is None:
+            self._staged = {}
+        if id(host_batch) in self._staged:
+            return
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         with torch.cuda.stream(self._copy_stream):
             dev = self.to_device(host_batch)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        self._staged = (host_batch, dev, ev)
+        while len(self._staged) >= 4:                       # bounded look-ahead
+            self._staged.pop(next(iter(self._staged)))
+        self._staged[id(host_batch)] = (host_batch, dev, ev, [False])
 
-    def step_from_host(self, host_batch, fps_seeds=None, next_host_batch=None):
-        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223).
-        `next_host_batch`: the batch of the following call; its H2D copy is issued right after this step has been
-        enqueued and runs concurrently with it."""
-        staged = self._staged
-        if staged is not None and staged[0] is host_batch:
-            _, dev, ev = staged
-            self._staged = None
+    def _take_staged(self, host_batch, pop):
+        """Device copy of a host batch: the prefetched one (made visible to the current stream) or a copy issued now."""
+        entry = (self._staged or {}).get(id(host_batch))
+        if entry is None or entry[0] is not host_batch:
+            return self.to_device(host_batch)
+        _, dev, ev, seen = entry
+        if not seen[0]:
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
             for t in dev.values():
                 t.record_stream(cur)          # allocated on the copy stream, consumed here
-        else:
-            dev = self.to_device(host_batch)
-        loss = self.step(dev, fps_seeds)
-        if next_host_batch is not None:
-            self.prefetch(next_host_batch)
+            seen[0] = True
+        if pop:
+            self._staged.pop(id(host_batch))
+        return dev
+
+    def step_from_host(self, host_batch, fps_seeds=None, next_host_batch=None, after_next_host_batch=None, next_fps_seeds=None):
+        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223).
+        `next_host_batch`: the batch of the following call.  Its H2D copy is issued right after this step has been
+        enqueued and runs concurrently with it; with pipeline_sampling its sampling plan is computed during this step, which
+        needs its cloud on the device already -- pass `after_next_host_batch` (the batch after that) as well and every
+        copy is issued two calls ahead, off the critical path."""
+        dev = self._take_staged(host_batch, pop=True)
+        nxt = None
+        if self.pipeline_sampling and next_host_batch is not None:
+            if (self._staged or {}).get(id(next_host_batch)) is None:
+                self.prefetch(next_host_batch)           # first call / no look-ahead given: the copy heads this step
+            nxt = self._take_staged(next_host_batch, pop=False)
+        loss = self.step(dev, fps_seeds, next_batch=nxt, next_fps_seeds=next_fps_seeds)
+        for hb in (next_host_batch, after_next_host_batch):
+            if hb is not None:
+                self.prefetch(hb)
         return float(loss.item())
 
 

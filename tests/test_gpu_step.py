@@ -293,6 +293,41 @@ def test_prefetched_host_batches_give_the_same_losses():
         assert curves[0] == curves[1], (use_graph, curves)
 
 
+@pytest.mark.gpu
+def test_pipelined_sampling_gives_the_same_losses():
+    """Trainer(pipeline_sampling=True): the FPS / ball-query plan of the NEXT batch is computed on a side stream during the
+    current step (step(batch, next_batch=..., next_fps_seeds=...)).  Same seeds -> the same indices -> bit-identical losses
+    as the in-line order, eager and under CUDA-graph replay, through step() and through step_from_host()."""
+    from maskplanner_b200 import synthetic
+    from maskplanner_b200.train_step import Trainer, pin_batch
+    B = 4
+    host = [pin_batch(synthetic.make_batch(B, "windows_v2", seed0=170 + 10 * i)) for i in range(3)]
+    gen = torch.Generator().manual_seed(5)
+    seeds = [(torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen)) for _ in range(8)]
+    dev = torch.device("cuda", 0)
+    for use_graph in (False, True):
+        curves = []
+        for mode in ("inline", "pipelined", "pipelined_host"):
+            # lr = 0: the weights stay put, so each loss is a pure function of (batch, FPS seeds) and must match bit for bit
+            tr = Trainer("windows_v2", dev, seed=4, use_graph=use_graph, lr=0.0, pipeline_sampling=mode != "inline")
+            tr.model.dropout.p = 0.0
+            resident = [tr.to_device(h) for h in host]
+            losses = []
+            for i in range(7):
+                if mode == "inline":
+                    losses.append(float(tr.step(resident[i % 3], seeds[i]).item()))
+                elif mode == "pipelined":
+                    # the first call has no announced plan: explicit seeds compute it in line; later calls use the announced one
+                    losses.append(float(tr.step(resident[i % 3], seeds[i] if i == 0 else None, next_batch=resident[(i + 1) % 3],
+                                                next_fps_seeds=seeds[i + 1]).item()))
+                else:
+                    losses.append(tr.step_from_host(host[i % 3], seeds[i] if i == 0 else None, next_host_batch=host[(i + 1) % 3],
+                                                    after_next_host_batch=host[(i + 2) % 3], next_fps_seeds=seeds[i + 1]))
+            curves.append(losses)
+        assert curves[0] == curves[1] == curves[2], (use_graph, curves)
+        assert len({round(c, 3) for c in curves[0]}) > 3
+
+
 def test_graph_replay_follows_lr_scheduler_and_loss_weight_schedule():
     """after capture only graph.replay() runs, so host-side changes must reach the device scalars the
     captured kernels read.  (a) a torch LR scheduler accepts optim.Adam (it is a torch.optim.Optimizer) and its lr
