@@ -306,6 +306,36 @@ MPB_API int mpb_adam_step_f32(int ntensors, float *const *params, const float *c
 MPB_API int mpb_lap_f32(const float *cost, const uint8_t *present, int B, int P, int T,
                         int64_t *out_row, void *stream);
 
+/* ---- a9 / f1: the asymm_v6 training loss around the nearest-neighbour kernels   loss_handler.py:596-666, :816-935 ----
+ * The caller issues mpb_chamfer_nn_f32 twice (segments, both directions; poses, GT -> prediction) and mpb_lap_f32;
+ * these entry points replace the ~130 small torch ops between them.
+ *  mpb_loss_lengths_f32         `padded=True` length scan of traj [B,P2,D] and traj_as_pc [B,P3,D2] in one launch
+ *                               (pytorch3d_chamfer.py:138-149: first row whose channel 0 is the sentinel).
+ *  mpb_mask_cost_f32            ids_out[b,i] = (int) stroke_ids[b, match[b,i]] (:838); cost[b,p,t] = sum_i
+ *                               BCEWithLogits(masks[b,p,i], [ids == t]) for all p, t (:860-873); present[b,t].
+ *  mpb_asymm_v6_loss_value_f32  loss = w0*t1 + w1*t2 + w2*t3 + w3*mean matched BCE + w4*confidence BCE; weights5 is a
+ *                               DEVICE array (schedulable between CUDA-graph replays); n_pairs_in (optional, device)
+ *                               overrides the matched-pair normaliser (global count under data parallelism).
+ *                               terms8 = {t1, t2, t3, weighted mask term, sum matched BCE, local pairs, confidence, pairs used}.
+ *  mpb_asymm_v6_loss_bwd_f32    d loss / d y_pred [B,P1,D], d masks [B,NM,P1], d scores [B,NM], scaled by grad_loss[0]. */
+MPB_API int mpb_loss_lengths_f32(const float *traj, int P2, int D, const float *traj_as_pc, int P3, int D2, int B,
+                                 float sentinel, int64_t *len_traj, int64_t *len_pc, void *stream);
+MPB_API int mpb_mask_cost_f32(const float *masks, const float *stroke_ids, const int64_t *match, int B, int NM, int P1,
+                              int P2, float *cost, uint8_t *present, int32_t *ids_out, void *stream);
+MPB_API int mpb_asymm_v6_loss_value_f32(const float *d_x, const float *d_y, const int64_t *len_y, const float *d_y2,
+                                        const int64_t *len_y2, const float *cost, const uint8_t *present,
+                                        const int64_t *row, const float *scores, const float *weights5,
+                                        const float *n_pairs_in, float no_stroke_w, int B, int P1, int P2, int P3,
+                                        int NM, float *loss, float *terms8, void *stream);
+MPB_API int mpb_asymm_v6_loss_bwd_f32(const float *y_pred, const float *traj, const float *traj_as_pc,
+                                      const float *masks, const float *scores, const int64_t *idx_x,
+                                      const int64_t *idx_y, const int64_t *len_y, const int64_t *idx_y2,
+                                      const int64_t *len_y2, const int32_t *ids, const uint8_t *present,
+                                      const int64_t *row, const float *weights5, const float *terms8,
+                                      const float *grad_loss, float no_stroke_w, int B, int P1, int P2, int D, int P3,
+                                      int D2, int NM, float *grad_pred, float *grad_masks, float *grad_scores,
+                                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ matrices come from one batched GEMM on the device (BCE-with-logits against a bin
 softplus(x) - x*y, so cost[p,t] = sum_i softplus(x[p,i]) - sum_{i in stroke t} x[p,i]); the
 assignment itself runs on the host with scipy from ONE device->host copy per step.
 """
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -206,17 +207,125 @@ class DeviceLossWeights:
         return self.t[SCHEDULABLE.index(name)]
 
 
+class _FusedAsymmV6(torch.autograd.Function):
+    """The whole loss as one autograd node over the fused kernels of csrc/loss.cu (six launches forward, three
+    backward, no torch glue): lengths -> [segment NN -> mask costs -> Hungarian] next to [pose NN on a side stream] ->
+    loss value.  Returns (loss 0-d, terms [8]); gradients flow to y_pred, the mask logits and the mask scores."""
+
+    @staticmethod
+    def forward(ctx, y_pred, masks, scores, y, stroke_ids, traj_as_pc, w5, no_stroke_w, pose_dim, global_mean):
+        from . import _cabi
+        from ._cabi import check, ptr, stream_ptr
+        lib = _cabi.load()
+        dev = y_pred.device
+        x = y_pred.detach().float().contiguous()
+        yy = y.detach().float().contiguous()
+        pc = traj_as_pc.detach().float().contiguous()
+        mk = masks.detach().float().contiguous()
+        sc = scores.detach().float().contiguous()
+        sid = stroke_ids.detach().float().contiguous()
+        B, P1, D = x.shape
+        P2, P3, NM = yy.shape[1], pc.shape[1], mk.shape[1]
+        assert D % pose_dim == 0 and pc.shape[2] == pose_dim and mk.shape[2] == P1 and sid.shape[1] == P2
+        i64 = dict(dtype=torch.int64, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        len_y, len_y2 = torch.empty(B, **i64), torch.empty(B, **i64)
+        check(lib.mpb_loss_lengths_f32(ptr(yy), P2, D, ptr(pc), P3, pose_dim, B, CH.PAD_SENTINEL, ptr(len_y), ptr(len_y2), stream_ptr()),
+              "mpb_loss_lengths_f32")
+        d_x, idx_x = torch.empty(B, P1, **f32), torch.empty(B, P1, **i64)
+        d_y, idx_y = torch.empty(B, P2, **f32), torch.empty(B, P2, **i64)
+        d_y2, idx_y2 = torch.empty(B, P3, **f32), torch.empty(B, P3, **i64)
+        # term 2 (ground-truth poses -> predicted poses) feeds nothing but the loss value: side stream, next to the
+        # segment search -> cost matrices -> Hungarian chain
+        with Fork(x, pc, len_y2, d_y2, idx_y2) as fork:
+            check(lib.mpb_chamfer_nn_f32(ptr(x), ptr(pc), B, P1 * (D // pose_dim), P3, pose_dim, None, ptr(len_y2), None, None,
+                                         ptr(d_y2), ptr(idx_y2), stream_ptr()), "mpb_chamfer_nn_f32")
+        check(lib.mpb_chamfer_nn_f32(ptr(x), ptr(yy), B, P1, P2, D, None, ptr(len_y), ptr(d_x), ptr(idx_x), ptr(d_y), ptr(idx_y),
+                                     stream_ptr()), "mpb_chamfer_nn_f32")
+        cost = torch.empty(B, NM, NM, **f32)
+        present = torch.empty(B, NM, dtype=torch.uint8, device=dev)
+        ids = torch.empty(B, P1, dtype=torch.int32, device=dev)
+        check(lib.mpb_mask_cost_f32(ptr(mk), ptr(sid), ptr(idx_x), B, NM, P1, P2, ptr(cost), ptr(present), ptr(ids), stream_ptr()),
+              "mpb_mask_cost_f32")
+        row = torch.empty(B, NM, **i64)
+        check(lib.mpb_lap_f32(ptr(cost), ptr(present), B, NM, NM, ptr(row), stream_ptr()), "mpb_lap_f32")
+        n_pairs = None
+        if global_mean and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            n_pairs = present.sum().float().reshape(1)
+            torch.distributed.all_reduce(n_pairs)
+            n_pairs = n_pairs / torch.distributed.get_world_size()       # rank-mean of (sum_r / this) = global sum / global count
+        fork.join(d_y2, idx_y2)
+        loss = torch.empty((), **f32)
+        terms = torch.empty(8, **f32)
+        check(lib.mpb_asymm_v6_loss_value_f32(ptr(d_x), ptr(d_y), ptr(len_y), ptr(d_y2), ptr(len_y2), ptr(cost), ptr(present), ptr(row),
+                                              ptr(sc), ptr(w5), ptr(n_pairs), float(no_stroke_w), B, P1, P2, P3, NM, ptr(loss), ptr(terms),
+                                              stream_ptr()), "mpb_asymm_v6_loss_value_f32")
+        ctx.save_for_backward(x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5, terms)
+        ctx.dims = (B, P1, P2, D, P3, pose_dim, NM, float(no_stroke_w))
+        ctx.shapes = (y_pred.shape, masks.shape, scores.shape)
+        ctx.mark_non_differentiable(terms)
+        ctx.match = idx_x
+        return loss, terms
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms):
+        from . import _cabi
+        from ._cabi import check, ptr, stream_ptr
+        x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5, terms = ctx.saved_tensors
+        B, P1, P2, D, P3, D2, NM, nsw = ctx.dims
+        g = g_loss.detach().float().reshape(1).contiguous()
+        gp, gm, gs = torch.empty_like(x), torch.empty_like(mk), torch.empty_like(sc)
+        check(_cabi.load().mpb_asymm_v6_loss_bwd_f32(ptr(x), ptr(yy), ptr(pc), ptr(mk), ptr(sc), ptr(idx_x), ptr(idx_y), ptr(len_y),
+                                                     ptr(idx_y2), ptr(len_y2), ptr(ids), ptr(present), ptr(row), ptr(w5), ptr(terms), ptr(g),
+                                                     nsw, B, P1, P2, D, P3, D2, NM, ptr(gp), ptr(gm), ptr(gs), stream_ptr()),
+              "mpb_asymm_v6_loss_bwd_f32", launches=3)
+        s0, s1, s2 = ctx.shapes
+        return gp.view(s0), gm.view(s1), gs.view(s2), None, None, None, None, None, None, None
+
+
+_W5_CACHE = {}
+
+
+def _weights_tensor(cfg, weights, device):
+    """The five schedulable weights as a device array: the Trainer's DeviceLossWeights tensor, or a cached upload of the
+    host values of `cfg` (eager callers)."""
+    if weights is not None:
+        return weights.t
+    vals = tuple(float(getattr(cfg, k)) for k in SCHEDULABLE)
+    key = (vals, str(device))
+    t = _W5_CACHE.get(key)
+    if t is None:
+        if len(_W5_CACHE) > 64:
+            _W5_CACHE.clear()
+        t = _W5_CACHE[key] = torch.tensor(vals, dtype=torch.float32, device=device)
+    return t
+
+
 def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores, stroke_ids, traj_as_pc, cfg=None,
                                        fused=True, return_terms=False, matcher="device", weights=None):
     """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config.
-    weights: optional DeviceLossWeights overriding cfg's five schedulable weights (CUDA-graph replays)."""
+    weights: optional DeviceLossWeights overriding cfg's five schedulable weights (CUDA-graph replays).
+    fused=True (default): the fused kernels of csrc/loss.cu (_FusedAsymmV6) when the device matcher is used;
+    fused="nn": terms 1 + 3 share one nearest-neighbour launch, everything around it stock torch ops (the round-1 path,
+    kept for A/B runs and as a second implementation the parity tests compare against); fused=False: the reference's
+    three chamfer_distance calls literally."""
     cfg = cfg or LossConfig()
+    if fused is True and matcher == "device" and y_pred.is_cuda and pred_stroke_masks.shape[1] <= 32 \
+            and os.environ.get("MPB_FUSED_LOSS", "1") == "1":
+        # the training path: one autograd node over the fused kernels (csrc/loss.cu)
+        loss, terms = _FusedAsymmV6.apply(y_pred, pred_stroke_masks, mask_scores, y, stroke_ids.to(y_pred.device), traj_as_pc,
+                                          _weights_tensor(cfg, weights, y_pred.device), cfg.explicit_no_stroke_weight, cfg.pose_dim,
+                                          bool(cfg.mask_loss_global_mean))
+        if return_terms:
+            return loss, dict(asymm_segment=terms[0], reverse_point=terms[1], reverse_segment=terms[2], masks=terms[3])
+        return loss
     if weights is not None:
         import copy
         cfg = copy.copy(cfg)
         for k in SCHEDULABLE:
             setattr(cfg, k, weights[k])
-    t1, t3, _, match = chamfer_terms_13(y_pred, y, cfg, fused=fused)
+    t1, t3, _, match = chamfer_terms_13(y_pred, y, cfg, fused=bool(fused))
     # term 2 (a second nearest-neighbour search) does not feed the mask loss (cost matrices -> Hungarian solver ->
     # matched BCE/dice): the two run side by side (maskplanner_b200/streams.py)
     with Fork(y_pred, traj_as_pc) as fork:
