@@ -188,15 +188,21 @@ MPB_API int64_t mpb_sa_gemm_wgrad_workspace(int dtype, int M, int N, int K, int 
 MPB_API int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K,
                               const float *a_scale, const float *a_shift, float *workspace, int cout,
                               int cin, int xyz_last, int accumulate, float *dW, void *stream);
+/* accumulate = -1 in mpb_sa_gemm_wgrad writes the per-split partial tiles only; this call sums them (fixed order) into dW.
+ * Split so the caller can run the reduction on another stream: it feeds the optimizer, not the next GEMM. */
+MPB_API int mpb_sa_gemm_wgrad_reduce(int dtype, int M, int N, int K, int xform, const float *workspace, int cout,
+                                     int cin, int xyz_last, int accumulate, float *dW, void *stream);
 MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
 /* dtype of the mpb_bn_* / mpb_sa_first_layer* calls: storage type of the activations, 0 = bf16, 1 = fp32. */
 MPB_API int mpb_bn_colstats(int dtype, const void *Z, int64_t M, int C, float *partials, int nparts,
                             void *stream);
-/* C_valid <= C: channels >= C_valid are alignment padding (scale = shift = 0, no parameter access). */
+/* C_valid <= C: channels >= C_valid are alignment padding (scale = shift = 0, no parameter access).
+ * num_batches_tracked (optional, device int64): BatchNorm's batch counter, incremented by this launch. */
 MPB_API int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                 const float *bias, const float *gamma, const float *beta,
                                 float *running_mean, float *running_var, float momentum, float eps,
-                                float *scale, float *shift, float *mean, float *rstd, void *stream);
+                                float *scale, float *shift, float *mean, float *rstd,
+                                int64_t *num_batches_tracked, void *stream);
 /* A = relu(scale*Z + shift) as a separate pass (A/B switch MPB_FUSE_APPLY=0; the default path applies it inside
  * the consumer GEMM's operand path instead, mpb_sa_gemm_tn a_scale/a_shift). */
 MPB_API int mpb_bn_relu(int dtype, const void *Z, const float *scale, const float *shift, int64_t M,
@@ -317,7 +323,8 @@ MPB_API int mpb_lap_f32(const float *cost, const uint8_t *present, int B, int P,
  *                               DEVICE array (schedulable between CUDA-graph replays); n_pairs_in (optional, device)
  *                               overrides the matched-pair normaliser (global count under data parallelism).
  *                               terms8 = {t1, t2, t3, weighted mask term, sum matched BCE, local pairs, confidence, pairs used}.
- *  mpb_asymm_v6_loss_bwd_f32    d loss / d y_pred [B,P1,D], d masks [B,NM,P1], d scores [B,NM], scaled by grad_loss[0]. */
+ *  mpb_asymm_v6_loss_bwd_f32    d loss / d y_pred [B,P1,D], d masks [B,NM,P1], d scores [B,NM], scaled by grad_loss[0];
+ *                               independent of the value kernel (n_pairs_in: the same optional override). */
 MPB_API int mpb_loss_lengths_f32(const float *traj, int P2, int D, const float *traj_as_pc, int P3, int D2, int B,
                                  float sentinel, int64_t *len_traj, int64_t *len_pc, void *stream);
 MPB_API int mpb_mask_cost_f32(const float *masks, const float *stroke_ids, const int64_t *match, int B, int NM, int P1,
@@ -331,7 +338,7 @@ MPB_API int mpb_asymm_v6_loss_bwd_f32(const float *y_pred, const float *traj, co
                                       const float *masks, const float *scores, const int64_t *idx_x,
                                       const int64_t *idx_y, const int64_t *len_y, const int64_t *idx_y2,
                                       const int64_t *len_y2, const int32_t *ids, const uint8_t *present,
-                                      const int64_t *row, const float *weights5, const float *terms8,
+                                      const int64_t *row, const float *weights5, const float *n_pairs_in,
                                       const float *grad_loss, float no_stroke_w, int B, int P1, int P2, int D, int P3,
                                       int D2, int NM, float *grad_pred, float *grad_masks, float *grad_scores,
                                       void *stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mpb_sa_gemm_tn": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "mpb_sa_gemm_wgrad_workspace": (_L, [_I, _I, _I, _I, _I]),
     "mpb_sa_gemm_wgrad": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "mpb_sa_gemm_wgrad_reduce": (_I, [_I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "mpb_rng_advance": (_I, [_P, _P]),
     "mpb_head_act_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _F, _I, _F, ctypes.c_uint64, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "mpb_head_act_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _F, ctypes.c_uint64, _P, _I, _P, _P, _P, _P, _P]),
@@ -55,7 +56,7 @@ SIGNATURES = {
     "mpb_head_pose_out_bwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "mpb_bn_stat_partials": (_I, [_L, _I]),
     "mpb_bn_colstats": (_I, [_I, _P, _L, _I, _P, _I, _P]),
-    "mpb_bn_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    "mpb_bn_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "mpb_bn_relu": (_I, [_I, _P, _P, _P, _L, _I, _P, _P]),
     "mpb_bn_relu_max": (_I, [_I, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
     "mpb_bn_bwd_stats": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _I, _P]),

@@ -181,15 +181,26 @@ __global__ void __launch_bounds__(1024) loss_value_kernel(const LossValueArgs a)
 __global__ void __launch_bounds__(128) loss_bwd_masks_kernel(const float *__restrict__ masks, const float *__restrict__ scores,
                                                              const int32_t *__restrict__ ids, const uint8_t *__restrict__ present,
                                                              const int64_t *__restrict__ row, const float *__restrict__ weights,
-                                                             const float *__restrict__ terms, const float *__restrict__ g, float no_stroke_w,
+                                                             const float *__restrict__ n_pairs_in, const float *__restrict__ g, float no_stroke_w,
                                                              int B, int NM, int P1, float *__restrict__ gmasks, float *__restrict__ gscores)
 {
     const int p = blockIdx.x, b = blockIdx.y;
     int tm = -1;
     for (int t = 0; t < NM; ++t)
         if (present[b * NM + t] && (int)row[b * NM + t] == p) tm = t;
+    // matched-pair normaliser (:906): the given (global) count, or the number of present strokes of this batch -- recomputed
+    // here from B * NM bytes so that the backward pass does not wait for the loss-value kernel
+    __shared__ int s_np[4];
+    int np = 0;
+    if (!n_pairs_in)
+        for (int i = threadIdx.x; i < B * NM; i += 128) np += present[i] ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) np += __shfl_xor_sync(0xffffffffu, np, off);
+    if ((threadIdx.x & 31) == 0) s_np[threadIdx.x >> 5] = np;
+    __syncthreads();
+    const float n_pairs = n_pairs_in ? n_pairs_in[0] : (float)(s_np[0] + s_np[1] + s_np[2] + s_np[3]);
     const float go = g[0];
-    const float coef = go * weights[3] / terms[7];
+    const float coef = go * weights[3] / n_pairs;
     const float *x = masks + ((size_t)b * NM + p) * P1;
     float *gx = gmasks + ((size_t)b * NM + p) * P1;
     const int32_t *id = ids + (size_t)b * P1;
@@ -305,18 +316,18 @@ extern "C" int mpb_asymm_v6_loss_value_f32(const float *d_x, const float *d_y, c
 extern "C" int mpb_asymm_v6_loss_bwd_f32(const float *y_pred, const float *traj, const float *traj_as_pc, const float *masks,
                                          const float *scores, const int64_t *idx_x, const int64_t *idx_y, const int64_t *len_y,
                                          const int64_t *idx_y2, const int64_t *len_y2, const int32_t *ids, const uint8_t *present,
-                                         const int64_t *row, const float *weights5, const float *terms8, const float *grad_loss,
+                                         const int64_t *row, const float *weights5, const float *n_pairs_in, const float *grad_loss,
                                          float no_stroke_w, int B, int P1, int P2, int D, int P3, int D2, int NM, float *grad_pred,
                                          float *grad_masks, float *grad_scores, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(B >= 1 && P1 >= 1 && P2 >= 1 && P3 >= 1 && D >= 1 && D2 >= 1 && D % D2 == 0 && NM >= 1 && NM <= kLossMaxMasks, "bad size");
     MPB_REQUIRE(y_pred && traj && traj_as_pc && masks && scores && idx_x && idx_y && len_y && idx_y2 && len_y2 && ids && present && row &&
-                    weights5 && terms8 && grad_loss && grad_pred && grad_masks && grad_scores,
+                    weights5 && grad_loss && grad_pred && grad_masks && grad_scores,
                 "null pointer");
     MPB_REQUIRE(B <= 65535, "B exceeds grid.y");
     cudaStream_t st = (cudaStream_t)stream;
-    loss_bwd_masks_kernel<<<dim3(NM, B), 128, 0, st>>>(masks, scores, ids, present, row, weights5, terms8, grad_loss, no_stroke_w, B, NM, P1,
+    loss_bwd_masks_kernel<<<dim3(NM, B), 128, 0, st>>>(masks, scores, ids, present, row, weights5, n_pairs_in, grad_loss, no_stroke_w, B, NM, P1,
                                                       grad_masks, grad_scores);
     const int64_t tx = (int64_t)B * P1 * D, t3 = (int64_t)B * P2 * D, t2 = (int64_t)B * P3 * D2;
     loss_bwd_pred_own_kernel<<<loss_grid(tx, 256), 256, 0, st>>>(y_pred, traj, idx_x, len_y, weights5, grad_loss, B, P1, P2, D, tx, grad_pred);

@@ -985,6 +985,14 @@ static int launch_wg(const WgPlan &pl, const CUtensorMap &tmZ, const CUtensorMap
     kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmZ, tmA, args);
     return check_launch("wgrad_kernel");
 }
+static int launch_wgrad_reduce(const WgPlan &pl, const float *workspace, int K, int cout, int cin, int xyz_last, int accumulate, float *dW,
+                               cudaStream_t st)
+{
+    int G = 1;                                           // warps per block: ~4 splits per thread, at most 32 warps
+    while (G < kReduceMaxWarps && G * 4 < pl.m_splits) G <<= 1;
+    wgrad_reduce_kernel<<<(cout * cin + 31) / 32, 32 * G, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, accumulate, dW);
+    return check_launch("wgrad_reduce_kernel");
+}
 }  // namespace mpb
 
 // Bytes of fp32 workspace the weight-gradient call needs for its per-split partial tiles.
@@ -1031,9 +1039,20 @@ extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M
     MPB_WG_CASE(DT_TF32X3, true);
 #undef MPB_WG_CASE
     if (rc) return rc;
-    int G = 1;                                           // warps per block: ~4 splits per thread, at most 32 warps
-    while (G < kReduceMaxWarps && G * 4 < pl.m_splits) G <<= 1;
-    wgrad_reduce_kernel<<<(cout * cin + 31) / 32, 32 * G, 0, st>>>(workspace, pl.m_splits, pl.n_pad, K, cout, cin, xyz_last, accumulate, dW);
-    return check_launch("wgrad_reduce_kernel");
+    if (accumulate < 0) return MPB_OK;                   // partial tiles only: the caller reduces them with mpb_sa_gemm_wgrad_reduce
+    return launch_wgrad_reduce(pl, workspace, K, cout, cin, xyz_last, accumulate, dW, st);
 }
 
+// Second half of mpb_sa_gemm_wgrad(accumulate = -1): the fixed-order sum of the per-split partial tiles.  Separate entry point
+// so that the caller can issue it on another stream (it only feeds the optimizer, the next GEMM need not wait for it).
+extern "C" int mpb_sa_gemm_wgrad_reduce(int dtype, int M, int N, int K, int xform, const float *workspace, int cout, int cin,
+                                        int xyz_last, int accumulate, float *dW, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(dtype >= DT_BF16 && dtype <= DT_TF32X3, "dtype must be 0 (bf16), 1 (tf32) or 2 (tf32x3)");
+    MPB_REQUIRE(M > 0 && N > 0 && K > 0 && workspace && dW, "bad argument");
+    MPB_REQUIRE(cout > 0 && cout <= N && cin > 0 && cin <= K, "cout / cin must fit the padded operand widths");
+    WgPlan pl;
+    MPB_REQUIRE(plan_wgrad(dtype, xform != 0, M, N, K, &pl), "unsupported shape");
+    return launch_wgrad_reduce(pl, workspace, K, cout, cin, xyz_last, accumulate != 0, dW, (cudaStream_t)stream);
+}

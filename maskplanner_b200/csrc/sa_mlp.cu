@@ -223,8 +223,9 @@ __global__ void __launch_bounds__(kFinThreads)
 bn_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M, const float *__restrict__ bias,
                    const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean,
                    float *__restrict__ running_var, float momentum, float eps, float *__restrict__ scale, float *__restrict__ shift,
-                   float *__restrict__ mean_out, float *__restrict__ rstd_out)
+                   float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t *__restrict__ num_batches_tracked)
 {
+    if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;   // BatchNorm's own counter (one launch less)
     int c;
     double s, q;
     if (reduce_partials(partials, nparts, C, c, s, q)) {
@@ -937,14 +938,15 @@ extern "C" int mpb_bn_colstats(int dtype, const void *Z, int64_t M, int C, float
 
 extern "C" int mpb_bn_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M, const float *bias,
                                    const float *gamma, const float *beta, float *running_mean, float *running_var, float momentum,
-                                   float eps, float *scale, float *shift, float *mean, float *rstd, void *stream)
+                                   float eps, float *scale, float *shift, float *mean, float *rstd, int64_t *num_batches_tracked,
+                                   void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(partials && scale && shift && mean && rstd && C > 0 && nparts > 0 && M > 0, "bad argument");
     MPB_REQUIRE(C_valid >= 0 && C_valid <= C, "C_valid out of range");
     bn_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, bias, gamma, beta,
                                                                               running_mean, running_var, momentum, eps, scale, shift, mean,
-                                                                              rstd);
+                                                                              rstd, num_batches_tracked);
     return check_launch("bn_finalize_kernel");
 }
 

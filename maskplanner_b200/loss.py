@@ -258,10 +258,15 @@ class _FusedAsymmV6(torch.autograd.Function):
         fork.join(d_y2, idx_y2)
         loss = torch.empty((), **f32)
         terms = torch.empty(8, **f32)
-        check(lib.mpb_asymm_v6_loss_value_f32(ptr(d_x), ptr(d_y), ptr(len_y), ptr(d_y2), ptr(len_y2), ptr(cost), ptr(present), ptr(row),
-                                              ptr(sc), ptr(w5), ptr(n_pairs), float(no_stroke_w), B, P1, P2, P3, NM, ptr(loss), ptr(terms),
-                                              stream_ptr()), "mpb_asymm_v6_loss_value_f32")
-        ctx.save_for_backward(x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5, terms)
+        # the VALUE of the loss feeds nothing downstream (the backward kernels recompute what they need): its single-CTA
+        # reduction runs on the side stream, off the step's critical path; whoever reads the loss joins that stream first
+        with Fork(d_x, d_y, d_y2, len_y, len_y2, cost, present, row, sc, w5, n_pairs, loss, terms, slot=3) as vfork:
+            check(lib.mpb_asymm_v6_loss_value_f32(ptr(d_x), ptr(d_y), ptr(len_y), ptr(d_y2), ptr(len_y2), ptr(cost), ptr(present),
+                                                  ptr(row), ptr(sc), ptr(w5), ptr(n_pairs), float(no_stroke_w), B, P1, P2, P3, NM,
+                                                  ptr(loss), ptr(terms), stream_ptr()), "mpb_asymm_v6_loss_value_f32")
+        _PENDING_VALUE.append(vfork)
+        ctx.n_pairs = n_pairs
+        ctx.save_for_backward(x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5)
         ctx.dims = (B, P1, P2, D, P3, pose_dim, NM, float(no_stroke_w))
         ctx.shapes = (y_pred.shape, masks.shape, scores.shape)
         ctx.mark_non_differentiable(terms)
@@ -272,16 +277,26 @@ class _FusedAsymmV6(torch.autograd.Function):
     def backward(ctx, g_loss, _g_terms):
         from . import _cabi
         from ._cabi import check, ptr, stream_ptr
-        x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5, terms = ctx.saved_tensors
+        x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5 = ctx.saved_tensors
         B, P1, P2, D, P3, D2, NM, nsw = ctx.dims
         g = g_loss.detach().float().reshape(1).contiguous()
         gp, gm, gs = torch.empty_like(x), torch.empty_like(mk), torch.empty_like(sc)
         check(_cabi.load().mpb_asymm_v6_loss_bwd_f32(ptr(x), ptr(yy), ptr(pc), ptr(mk), ptr(sc), ptr(idx_x), ptr(idx_y), ptr(len_y),
-                                                     ptr(idx_y2), ptr(len_y2), ptr(ids), ptr(present), ptr(row), ptr(w5), ptr(terms), ptr(g),
+                                                     ptr(idx_y2), ptr(len_y2), ptr(ids), ptr(present), ptr(row), ptr(w5), ptr(ctx.n_pairs), ptr(g),
                                                      nsw, B, P1, P2, D, P3, D2, NM, ptr(gp), ptr(gm), ptr(gs), stream_ptr()),
               "mpb_asymm_v6_loss_bwd_f32", launches=3)
         s0, s1, s2 = ctx.shapes
         return gp.view(s0), gm.view(s1), gs.view(s2), None, None, None, None, None, None, None
+
+
+_PENDING_VALUE = []      # side-stream forks of loss-value kernels not yet joined
+
+
+def join_loss_value():
+    """Make the current stream wait for every loss-value kernel issued so far (call before reading a loss returned by
+    the fused path on another stream's schedule; asymm_v6_chamfer_with_stroke_masks(join_value=True) does it itself)."""
+    while _PENDING_VALUE:
+        _PENDING_VALUE.pop().join()
 
 
 _W5_CACHE = {}
@@ -303,7 +318,7 @@ def _weights_tensor(cfg, weights, device):
 
 
 def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores, stroke_ids, traj_as_pc, cfg=None,
-                                       fused=True, return_terms=False, matcher="device", weights=None):
+                                       fused=True, return_terms=False, matcher="device", weights=None, join_value=True):
     """The whole training loss (loss_handler.py:596-666); per_segment_confidence is False in the MaskPlanner config.
     weights: optional DeviceLossWeights overriding cfg's five schedulable weights (CUDA-graph replays).
     fused=True (default): the fused kernels of csrc/loss.cu (_FusedAsymmV6) when the device matcher is used;
@@ -317,6 +332,8 @@ def asymm_v6_chamfer_with_stroke_masks(y_pred, y, pred_stroke_masks, mask_scores
         loss, terms = _FusedAsymmV6.apply(y_pred, pred_stroke_masks, mask_scores, y, stroke_ids.to(y_pred.device), traj_as_pc,
                                           _weights_tensor(cfg, weights, y_pred.device), cfg.explicit_no_stroke_weight, cfg.pose_dim,
                                           bool(cfg.mask_loss_global_mean))
+        if join_value:        # join_value=False: the caller (Trainer) joins after backward / the optimizer step instead
+            join_loss_value()
         if return_terms:
             return loss, dict(asymm_segment=terms[0], reverse_point=terms[1], reverse_segment=terms[2], masks=terms[3])
         return loss

@@ -80,18 +80,40 @@ def _gemm_tn(lib, gd, esz, a, b, b_lo, c, M, N, K, st, real, a_affine=None, epi=
                                  ptr(z_affine[1]) if z_affine else None, st), "mpb_sa_gemm_tn")
 
 
+DEFER_WGRAD_REDUCE = os.environ.get("MPB_DEFER_WGRAD_REDUCE", "1") == "1"
+_PENDING_REDUCE = []
+
+
+def join_wgrad_reductions():
+    """Make the current stream wait for the weight-gradient reductions issued on the side stream."""
+    while _PENDING_REDUCE:
+        fork, dw = _PENDING_REDUCE.pop()
+        fork.join(dw)
+
+
 def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz_last, dw):
-    """dW[cout,cin] = crop(dZ[M,N]^T @ f(A)[M,K]).  Algorithmic bytes: dZ and A read once, dW written once (fp32)."""
+    """dW[cout,cin] = crop(dZ[M,N]^T @ f(A)[M,K]).  Algorithmic bytes: dZ and A read once, dW written once (fp32).
+    The fixed-order sum of the per-split partial tiles only feeds the optimizer: it is issued on a side stream (joined at the
+    end of the module's backward), so the dgrad GEMM that follows starts as soon as the partial tiles are written."""
+    from .streams import Fork
     rk, rn = real
-    ws_bytes = lib.mpb_sa_gemm_wgrad_workspace(gd, M, N, K, 1 if a_affine else 0)
+    xf = 1 if a_affine else 0
+    ws_bytes = lib.mpb_sa_gemm_wgrad_workspace(gd, M, N, K, xf)
     if ws_bytes < 0:
         raise _cabi.MpbError("mpb_sa_gemm_wgrad: unsupported shape M=%d N=%d K=%d" % (M, N, K))
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dw.device)
-    with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d" % (M, N, K, 1 if a_affine else 0)):
+    defer = DEFER_WGRAD_REDUCE
+    with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d" % (M, N, K, xf)):
         check(lib.mpb_sa_gemm_wgrad(gd, ptr(dz), ptr(a), M, N, K, ptr(a_affine[0]) if a_affine else None,
-                                    ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, 0, ptr(dw), st),
-              "mpb_sa_gemm_wgrad", launches=2)
-
+                                    ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, -1 if defer else 0, ptr(dw), st),
+              "mpb_sa_gemm_wgrad", launches=1 if defer else 2)
+    if defer:
+        with Fork(ws, dw, slot=4) as fork:
+            check(lib.mpb_sa_gemm_wgrad_reduce(gd, M, N, K, xf, ptr(ws), cout, cin, 1 if xyz_last else 0, 0, ptr(dw), stream_ptr()),
+                  "mpb_sa_gemm_wgrad_reduce")
+        if fork.active:
+            _PENDING_REDUCE.append((fork, dw))
+        
 
 def _padded_weight(conv_weight, cout_p, cin_p, xyz_last, mode):
     """[Cout,Cin,1,1] fp32 -> the GEMM's B operand [cout_p, cin_p] (zero padded) and its transpose [cin_p, cout_p].
@@ -177,7 +199,7 @@ class SharedMLPMax(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, a0, K, training, momentum_eps, xyz_last, mode, *flat):
+    def forward(ctx, a0, K, training, momentum_eps, xyz_last, mode, counters, *flat):
         lib = _cabi.load()
         gd, ad, tdt = MODES[mode]
         esz = 2 if tdt == torch.bfloat16 else 4
@@ -242,8 +264,8 @@ class SharedMLPMax(torch.autograd.Function):
                     check(lib.mpb_bn_colstats(ad, ptr(z), M, cout_p, ptr(part), nparts, st), "mpb_bn_colstats")
             if training:
                 check(lib.mpb_bn_finalize_f32(ptr(part), nparts, cout_p, cout, M, ptr(bias), ptr(gamma), ptr(beta), ptr(rmean),
-                                              ptr(rvar), mom, eps, ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), st),
-                      "mpb_bn_finalize_f32")
+                                              ptr(rvar), mom, eps, ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]),
+                                              ptr(counters[l]) if counters is not None else None, st), "mpb_bn_finalize_f32")
             else:
                 # eval: running statistics; the conv bias folds into the shift (tiny per-channel host-side math)
                 sc.zero_()
@@ -384,7 +406,8 @@ class SharedMLPMax(torch.autograd.Function):
                 if l > 0:
                     part, nparts = part_n, np_n
             d_a = d_prev
-        return (d_a, None, None, None, None, None, *grads)
+        join_wgrad_reductions()
+        return (d_a, None, None, None, None, None, None, *grads)
 
 
 def shared_mlp_max(a0, K, convs, bns, training, xyz_last=False, mode="bf16"):
@@ -398,9 +421,14 @@ def shared_mlp_max(a0, K, convs, bns, training, xyz_last=False, mode="bf16"):
     for conv, bn in zip(convs, bns):
         flat += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
         me.append((bn.momentum if bn.momentum is not None else 0.1, bn.eps))
-    out = SharedMLPMax.apply(a0, K, training, tuple(me), bool(xyz_last), mode, *flat)
+    # BatchNorm's num_batches_tracked counters are advanced by the finalize launches (device int64 scalars)
+    counters = None
     if training:
-        for bn in bns:
-            if bn.num_batches_tracked is not None:
+        counters = tuple(bn.num_batches_tracked if (bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda
+                                                    and bn.num_batches_tracked.dtype == torch.int64) else None for bn in bns)
+    out = SharedMLPMax.apply(a0, K, training, tuple(me), bool(xyz_last), mode, counters, *flat)
+    if training:
+        for bn, c in zip(bns, counters):
+            if c is None and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1
     return out

@@ -264,7 +264,7 @@ class Trainer:
         pred, masks, scores, _ = self.model(cloud, fps_seeds, plan=plan, after_encode=after_encode)   # :210
         loss = L.asymm_v6_chamfer_with_stroke_masks(pred, batch["traj"], masks, scores, batch["stroke_ids"],
                                                     batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss,
-                                                    weights=self.loss_weights)    # :212-218
+                                                    weights=self.loss_weights, join_value=False)    # :212-218
         self._heads_pending = 0
         loss.backward()                                                           # :220
         if self.world_size > 1:
@@ -279,6 +279,7 @@ class Trainer:
             self.opt.step(grad_scale=1.0 / self.world_size)                       # :221 (the buffer holds the SUM over ranks)
         else:
             self.opt.step()                                                       # :221
+        L.join_loss_value()       # the loss VALUE was reduced on a side stream, off the critical path
         if fork is not None:
             fork.join()
             if plan is not None:          # the plan just computed becomes the current one (backward has finished reading `plan`)
