@@ -343,6 +343,13 @@ MPB_API int mpb_asymm_v6_loss_bwd_f32(const float *y_pred, const float *traj, co
                                       int D2, int NM, float *grad_pred, float *grad_masks, float *grad_scores,
                                       void *stream);
 
+/* ---- the step's input boundary                        train_maskplanner.py:207-208, paintnet_ODv1.py:738-747 ----
+ * One launch copies up to 8 tensors (as 32-bit words) into the fixed buffers a captured step reads, padding rows:
+ * dst[b, r, :] = r < src_rows ? src[b, r, :] : pad_bits.  All arrays are HOST arrays of length nsegs. */
+MPB_API int mpb_stage_batch(int nsegs, const void *const *src, void *const *dst, const int64_t *batch,
+                            const int64_t *src_rows, const int64_t *dst_rows, const int64_t *row_words,
+                            const uint32_t *pad_bits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -297,7 +297,53 @@ class Trainer:
             self._plan_for = None
 
     def _draw_seeds(self, B, n_points):
-        return (draw_fps_seed(B, n_points, self.device), draw_fps_seed(B, self.model.sa1.npoint, self.device))
+        """The reference's seed draws (models/pointnet2_utils.py:77: one CPU randint per SA layer, same generator consumption),
+        staged through ONE pinned [2, B] tensor and one asynchronous copy."""
+        host = torch.empty(2, B, dtype=torch.long, pin_memory=self.device.type == "cuda")
+        host[0] = torch.randint(0, n_points, (B,), dtype=torch.long)
+        host[1] = torch.randint(0, self.model.sa1.npoint, (B,), dtype=torch.long)
+        dev = host.to(self.device, non_blocking=True)
+        return (dev[0], dev[1])
+
+    _PAD_BITS = {"traj": 0xC2C80000, "traj_as_pc": 0xC2C80000, "stroke_ids": 0xBF800000, "point_cloud": 0}   # -100.0f, -1.0f
+
+    def _stage_inputs(self, batch, seeds, next_cloud, next_seeds):
+        """Copy this call's inputs into the captured graph's fixed buffers with ONE launch (mpb_stage_batch): the four batch
+        tensors, padded to the configured maxima with the loader's sentinels, plus (pipelined sampling) the next batch's cloud
+        and seeds.  Returns False when a tensor does not qualify (then the caller falls back to pad_batch + copy_)."""
+        import ctypes
+        from . import _cabi
+        segs = []
+        for k in self.KEYS:
+            src, dst = batch[k], self._static[k]
+            if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.shape[0] == dst.shape[0]
+                    and src.shape[1] <= dst.shape[1] and src.shape[2:] == dst.shape[2:]):
+                return False
+            row = 1
+            for d in dst.shape[2:]:
+                row *= d
+            segs.append((src, dst, dst.shape[0], src.shape[1], dst.shape[1], row, self._PAD_BITS[k]))
+        if next_cloud is not None:
+            dst = self._next_static[0]
+            if not (next_cloud.is_cuda and next_cloud.dtype == torch.float32 and next_cloud.is_contiguous() and next_cloud.shape == dst.shape):
+                return False
+            segs.append((next_cloud, dst, 1, 1, 1, dst.numel(), 0))
+        for src2, dst2 in ((seeds, self._static.get("seeds")), (next_seeds, self._next_static[1] if self._next_static else None)):
+            if src2 is None:
+                continue
+            for a, b in zip(src2, dst2):
+                if not (a.is_cuda and a.dtype == torch.long and a.is_contiguous() and a.shape == b.shape):
+                    return False
+                segs.append((a, b, 1, 1, 1, 2 * b.numel(), 0))
+        n = len(segs)
+        if n > 8:
+            return False
+        vp, i64, u32 = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_uint32 * n
+        _cabi.check(_cabi.load().mpb_stage_batch(
+            n, vp(*[g[0].data_ptr() for g in segs]), vp(*[g[1].data_ptr() for g in segs]), i64(*[g[2] for g in segs]),
+            i64(*[g[3] for g in segs]), i64(*[g[4] for g in segs]), i64(*[g[5] for g in segs]), u32(*[g[6] for g in segs]),
+            _cabi.stream_ptr()), "mpb_stage_batch")
+        return True
 
     def step(self, batch, fps_seeds=None, next_batch=None, next_fps_seeds=None):
         """One optimisation step on a device-resident batch.  Returns the loss as a 0-d device tensor.
@@ -337,25 +383,41 @@ class Trainer:
         if hasattr(self.opt, "sync_hyper"):
             self.opt.sync_hyper()
         self.loss_weights.sync(self.loss_cfg)
-        batch = pad_batch(batch, self.max_segments, self.max_poses)
         if not pipe:
             if fps_seeds is None:
                 fps_seeds = self._draw_seeds(B, n_points)
             else:
                 fps_seeds = to_dev(fps_seeds)
-        if pipe and self._next_static is None:
-            self._next_static = (torch.zeros_like(batch["point_cloud"]), tuple(torch.zeros(B, dtype=torch.long, device=self.device) for _ in range(2)))
-        if pipe and next_batch is not None:
-            self._next_static[0].copy_(n_cloud, non_blocking=True)
-            for dst, src in zip(self._next_static[1], n_seeds):
-                dst.copy_(src, non_blocking=True)
-        if pipe:
-            # the side branch is part of the captured graph: without a next batch it recomputes a plan nobody will use
-            nxt = (self._next_static[0], self._next_static[1], self._plan_next)
-        if self._calls <= self._graph_warmup_steps:      # real eager steps: lazy initialisation + Adam state
-            out = self._step_core(batch, fps_seeds, plan, nxt)
+        if self._graph is not None:
+            # steady state: ONE staging launch (padding included) + the replay
+            if not self._stage_inputs(batch, None if pipe else fps_seeds, n_cloud if (pipe and next_batch is not None) else None,
+                                      n_seeds if (pipe and next_batch is not None) else None):
+                padded = pad_batch(batch, self.max_segments, self.max_poses)
+                for k in self.KEYS:
+                    self._static[k].copy_(padded[k], non_blocking=True)
+                if not pipe:
+                    for dst, src in zip(self._static["seeds"], fps_seeds):
+                        dst.copy_(src, non_blocking=True)
+                elif next_batch is not None:
+                    self._next_static[0].copy_(n_cloud, non_blocking=True)
+                    for dst, src in zip(self._next_static[1], n_seeds):
+                        dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            out = self._static_loss
         else:
-            if self._graph is None:
+            batch = pad_batch(batch, self.max_segments, self.max_poses)
+            if pipe and self._next_static is None:
+                self._next_static = (torch.zeros_like(batch["point_cloud"]), tuple(torch.zeros(B, dtype=torch.long, device=self.device) for _ in range(2)))
+            if pipe and next_batch is not None:
+                self._next_static[0].copy_(n_cloud, non_blocking=True)
+                for dst, src in zip(self._next_static[1], n_seeds):
+                    dst.copy_(src, non_blocking=True)
+            if pipe:
+                # the side branch is part of the captured graph: without a next batch it recomputes a plan nobody will use
+                nxt = (self._next_static[0], self._next_static[1], self._plan_next)
+            if self._calls <= self._graph_warmup_steps:      # real eager steps: lazy initialisation + Adam state
+                out = self._step_core(batch, fps_seeds, plan, nxt)
+            else:
                 self._static = {k: batch[k].clone() for k in self.KEYS}
                 if not pipe:
                     self._static["seeds"] = tuple(s.clone() for s in fps_seeds)
@@ -366,14 +428,8 @@ class Trainer:
                 with torch.cuda.graph(self._graph):
                     self._static_loss = self._step_core(self._static, None if pipe else self._static["seeds"], plan, nxt)
                 self.kernels_per_step = _cabi.KERNEL_LAUNCHES - n0     # libmaskplanner_b200 kernels inside one replay
-            else:
-                for k in self.KEYS:
-                    self._static[k].copy_(batch[k], non_blocking=True)
-                if not pipe:
-                    for dst, src in zip(self._static["seeds"], fps_seeds):
-                        dst.copy_(src, non_blocking=True)
-            self._graph.replay()
-            out = self._static_loss
+                self._graph.replay()
+                out = self._static_loss
         if pipe:
             self._plan_for = n_cloud if next_batch is not None else None
         return out
@@ -411,12 +467,10 @@ class Trainer:
             self._staged.pop(id(host_batch))
         return dev
 
-    def step_from_host(self, host_batch, fps_seeds=None, next_host_batch=None, after_next_host_batch=None, next_fps_seeds=None):
-        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223).
-        `next_host_batch`: the batch of the following call.  Its H2D copy is issued right after this step has been
-        enqueued and runs concurrently with it; with pipeline_sampling its sampling plan is computed during this step, which
-        needs its cloud on the device already -- pass `after_next_host_batch` (the batch after that) as well and every
-        copy is issued two calls ahead, off the critical path."""
+    def step_from_host_async(self, host_batch, fps_seeds=None, next_host_batch=None, after_next_host_batch=None, next_fps_seeds=None):
+        """step_from_host without the host-side wait: returns a PendingLoss whose .result() blocks until this step's loss
+        has reached pinned host memory.  A loop that reads step i's loss after enqueuing step i+1 keeps the GPU busy while
+        the host prepares the next call (staging launch, seed draws, prefetch)."""
         dev = self._take_staged(host_batch, pop=True)
         nxt = None
         if self.pipeline_sampling and next_host_batch is not None:
@@ -424,10 +478,33 @@ class Trainer:
                 self.prefetch(next_host_batch)           # first call / no look-ahead given: the copy heads this step
             nxt = self._take_staged(next_host_batch, pop=False)
         loss = self.step(dev, fps_seeds, next_batch=nxt, next_fps_seeds=next_fps_seeds)
+        pending = PendingLoss(loss)
         for hb in (next_host_batch, after_next_host_batch):
             if hb is not None:
                 self.prefetch(hb)
-        return float(loss.item())
+        return pending
+
+    def step_from_host(self, host_batch, fps_seeds=None, next_host_batch=None, after_next_host_batch=None, next_fps_seeds=None):
+        """End-to-end step as a user calls it: pinned host batch in, Python float loss out (:223).
+        `next_host_batch`: the batch of the following call.  Its H2D copy is issued right after this step has been
+        enqueued and runs concurrently with it; with pipeline_sampling its sampling plan is computed during this step, which
+        needs its cloud on the device already -- pass `after_next_host_batch` (the batch after that) as well and every
+        copy is issued two calls ahead, off the critical path."""
+        return self.step_from_host_async(host_batch, fps_seeds, next_host_batch, after_next_host_batch, next_fps_seeds).result()
+
+
+class PendingLoss:
+    """A step's loss on its way to the host: asynchronous device -> pinned-host copy (4 bytes) + an event."""
+
+    def __init__(self, loss):
+        self._host = torch.empty((), dtype=torch.float32, pin_memory=True)
+        self._host.copy_(loss.detach(), non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+
+    def result(self):
+        self._event.synchronize()
+        return float(self._host)
 
 
 def pin_batch(batch):
