@@ -190,6 +190,18 @@ MPB_API int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, i
                               int cin, int xyz_last, int accumulate, float *dW, void *stream);
 /* accumulate = -1 in mpb_sa_gemm_wgrad writes the per-split partial tiles only; this call sums them (fixed order) into dW.
  * Split so the caller can run the reduction on another stream: it feeds the optimizer, not the next GEMM. */
+/* The two GEMMs that consume dZ of a MAX-POOLED layer, with dZ rebuilt in shared memory from that layer's stored
+ * pre-activation Zl (bf16) instead of being written by mpb_bn_bwd_apply and read back twice:
+ *   dZ[m,c] = pgo[g,c] * [m - g*pool_k == argmax[g,c]] + negw_e[0][c] * Zl[m,c] + negw_e[1][c],  g = m / pool_k.
+ * Everything else as in mpb_sa_gemm_tn (epi 0 / 2) and mpb_sa_gemm_wgrad.          pointnet2_utils.py:210-214 (autograd) */
+MPB_API int mpb_sa_gemm_tn_pool(int dtype, const void *Zl, const void *B, void *C, int M, int N, int K, int pool_k,
+                                const int32_t *argmax, const float *pgo, const float *negw_e, int epi,
+                                float *partials, int nparts, const void *Z, const float *z_scale,
+                                const float *z_shift, void *stream);
+MPB_API int mpb_sa_gemm_wgrad_pool(int dtype, const void *Zl, const void *A, int M, int N, int K,
+                                   const float *a_scale, const float *a_shift, int pool_k, const int32_t *argmax,
+                                   const float *pgo, const float *negw_e, float *workspace, int cout, int cin,
+                                   int xyz_last, int accumulate, float *dW, void *stream);
 MPB_API int mpb_sa_gemm_wgrad_reduce(int dtype, int M, int N, int K, int xform, const float *workspace, int cout,
                                      int cin, int xyz_last, int accumulate, float *dW, void *stream);
 MPB_API int mpb_bn_stat_partials(int64_t rows, int C);
@@ -218,11 +230,15 @@ MPB_API int mpb_bn_relu_max(int dtype, const void *Z, const float *scale, const 
 MPB_API int mpb_bn_bwd_stats(int dtype, const void *dA, const float *dOut, const int32_t *argmax,
                              const float *zmax, int K, const void *Z, const float *scale,
                              const float *shift, const float *mean, const float *rstd, int64_t M, int C,
-                             float *partials, int nparts, void *stream);
+                             float *partials, int nparts, float *pgo, void *stream);
 MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M,
                                     const float *gamma, const float *mean, const float *rstd,
                                     float *dgamma, float *dbeta, float *coef, float *clear,
-                                    int64_t clear_count, void *stream);
+                                    int64_t clear_count, float *negw_e, void *stream);
+/* pgo (pooled form of _bwd_stats, optional, fp32 [G,C]) and negw_e (_bwd_finalize, optional, fp32 [2,C]) feed the POOLED
+ * operand transform of mpb_sa_gemm_tn_pool / mpb_sa_gemm_wgrad_pool: with dZ = p*dY - w*z + e and dY non-zero only at the
+ * arg-max row of each (group, channel), pgo[g,c] = p[c]*dY[g,c] and negw_e = (-w, e); the GEMMs then rebuild the dZ tile
+ * from the stored pre-activation z in shared memory and mpb_bn_bwd_apply (one read + one write of [M,C]) is not needed. */
 MPB_API int mpb_bn_bwd_apply(int dtype, const void *dA, const float *dOut, const int32_t *argmax, int K,
                              const void *Z, const float *scale, const float *shift, const float *mean,
                              const float *rstd, const float *coef, int64_t M, int C, void *dZ,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "mpb_sa_gemm_tn": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "mpb_sa_gemm_wgrad_workspace": (_L, [_I, _I, _I, _I, _I]),
     "mpb_sa_gemm_wgrad": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "mpb_sa_gemm_tn_pool": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "mpb_sa_gemm_wgrad_pool": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "mpb_sa_gemm_wgrad_reduce": (_I, [_I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "mpb_rng_advance": (_I, [_P, _P]),
     "mpb_head_act_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _F, _I, _F, ctypes.c_uint64, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
@@ -59,8 +61,8 @@ SIGNATURES = {
     "mpb_bn_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "mpb_bn_relu": (_I, [_I, _P, _P, _P, _L, _I, _P, _P]),
     "mpb_bn_relu_max": (_I, [_I, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
-    "mpb_bn_bwd_stats": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _I, _P]),
-    "mpb_bn_bwd_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "mpb_bn_bwd_stats": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _I, _P, _P]),
+    "mpb_bn_bwd_finalize_f32": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P]),
     "mpb_pack_weight_bf16": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "mpb_pack_weight_tf32": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mpb_bn_bwd_apply": (_I, [_I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),

@@ -134,7 +134,7 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
 // 16-byte loads per data load, 3/4 of the kernel's shared-memory wavefronts in the ncu capture) and, RSTEP being a
 // multiple of 8, the swizzled chunk position is a per-thread constant.  A quarter warp (8 lanes = the 8 chunks of one
 // row) touches one whole 128-byte row per access: conflict-free.  Rows >= rows_valid (TMA zero fill past M) stay zero.
-template <int DT, bool XFORM, bool ATOM32, int NR, int RSTEP>
+template <int DT, bool XFORM, bool ATOM32, int NR, int RSTEP, bool RELU = true>
 __device__ __forceinline__ void transform_cols(uint8_t *box, uint8_t *box_lo, int c, int r0, const float *sc, const float *sh, int rows_valid)
 {
     static_assert(RSTEP % 8 == 0, "the swizzle key must not change along the thread's rows");
@@ -161,7 +161,7 @@ __device__ __forceinline__ void transform_cols(uint8_t *box, uint8_t *box_lo, in
                 float2 x = unpack_bf16(w[u]);
                 if (XFORM) {
                     x = __ffma2_rn(x, s2[u], h2[u]);
-                    o[u] = pack_bf16_relu(x.x, x.y);
+                    o[u] = RELU ? pack_bf16_relu(x.x, x.y) : pack_bf16(x.x, x.y);
                 } else {
                     o[u] = w[u];
                 }
@@ -193,10 +193,68 @@ __device__ __forceinline__ void transform_cols(uint8_t *box, uint8_t *box_lo, in
     }
 }
 
+// Pooled operand transform (bf16): the landed box holds the stored pre-activation z of the LAST shared-MLP layer and is
+// rewritten in place as the BatchNorm/ReLU/max-pool backward of it,
+//     dZ[m, ch] = pgo[g, ch] * [m - g*Kg == arg[g, ch]]  -  w[ch] * z[m, ch]  +  e[ch]          (g = m / Kg),
+// i.e. what mpb_bn_bwd_apply (pooled form) would have written to HBM and the two consumer GEMMs read back: one read and one
+// write of the widest activation tensor of the layer stack are gone (reference: the autograd of pointnet2_utils.py:210-214).
+// The dense part is the plain column-owner affine transform (transform_cols without the ReLU); the sparse part -- ONE element
+// per (group, channel) -- is handled around it: pool_gather computes the FINAL value of every special element of the box from
+// the original z before the dense pass overwrites it, pool_scatter stores those values after it (two 128-thread named
+// barriers in between).  A first version compared every element's row against arg[g, ch] inside the dense pass: 16 extra
+// instructions per 16 bytes made the GEMMs transform-bound (dgrad 80 -> 139 us at M = 1M).
+// Box geometry: `rows` rows of 128 bytes (64 channels ch_base .. ch_base+63), first row = global row R0; Kg divides `rows`
+// or is a multiple of it (group boundaries never fall inside... a box holds whole groups or part of one).
+// pool_fetch: the (arg, pgo) entries of this thread's special elements of one box -- plain global loads with no dependence on
+// the box's contents, so the caller issues them one pipeline iteration AHEAD and their L2 latency never shows.
+// pool_gather: the final values of those elements from the original z in the landed box.
+template <int NP>
+__device__ __forceinline__ void pool_fetch(int rows, int R0, int M, int Kg, int C, int ch_base, const int32_t *__restrict__ arg,
+                                           const float *__restrict__ pgo, int t, int (&a)[NP], float (&pg)[NP])
+{
+    const int g0 = R0 / Kg;
+    const int ngroups = Kg >= rows ? 1 : rows / Kg;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int q = t + 128 * i;
+        const int gl = q >> 6, ch = q & 63;
+        const int g = g0 + gl;
+        const bool ok = gl < ngroups && g * Kg < M && R0 < M;
+        a[i] = ok ? g * Kg + arg[(size_t)g * C + ch_base + ch] - R0 : -1;      // arg-max row of (g, ch) relative to the box
+        pg[i] = ok ? pgo[(size_t)g * C + ch_base + ch] : 0.f;
+    }
+}
+template <int NP>
+__device__ __forceinline__ void pool_gather(const uint8_t *box, int rows, const float *negw, const float *e, int t, const int (&a)[NP],
+                                            const float (&pg)[NP], uint32_t (&off)[NP], uint32_t (&val)[NP])
+{
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        off[i] = 0xffffffffu;
+        const int ch = (t + 128 * i) & 63, r = a[i];
+        if (r >= 0 && r < rows) {
+            const uint32_t o = (uint32_t)(r * 128 + ((((ch >> 3) ^ (r & 7)) << 4) | ((ch & 7) << 1)));
+            const float z = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(box + o));
+            off[i] = o;
+            val[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaf(z, negw[ch], e[ch]) + pg[i]));
+        }
+    }
+}
+template <int NP>
+__device__ __forceinline__ void pool_scatter(uint8_t *box, const uint32_t (&off)[NP], const uint32_t (&val)[NP])
+{
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (off[i] != 0xffffffffu) *reinterpret_cast<uint16_t *>(box + off[i]) = (uint16_t)val[i];
+}
+
 struct GemmTnArgs {
     int M, N, K, BN, stages, out_bufs;
-    const float *a_scale, *a_shift;    // XFORM: A' = relu(a_scale[k] * A + a_shift[k])
+    const float *a_scale, *a_shift;    // XFORM 1: A' = relu(a_scale[k] * A + a_shift[k]); XFORM 2 (pooled): (-w[k], e[k])
     const float *z_scale, *z_shift;    // EPI 2: relu mask of the layer below
+    const int32_t *pool_arg;           // XFORM 2: arg-max row of every (group, channel) [M / pool_k, K]
+    const float *pool_pgo;             //          p * dY at that row [M / pool_k, K]
+    int pool_k;                        //          rows per pooling group
     float *partials;                   // EPI 1/2: [nparts][2][N]; nparts = 8 * grid (CUDA-core statistics) or 2 * grid (tensor-core)
 };
 
@@ -214,13 +272,15 @@ constexpr int kGemmTnThreadsXf = 640;  // + two transform warpgroups (each threa
 // layer below (TMA-loaded), Y = dY = C * [z_scale*z + z_shift > 0] -> (sum dY, sum dY*z).  The accumulators live in TMEM for
 // the whole kernel (one set per epilogue warpgroup) and are read once at the end.
 // EPI: 0 = store only; 1 = + forward BatchNorm statistics of the stored values; 2 = + BatchNorm-backward statistics.
-template <int DT, bool XFORM, int EPI>
+// XFORM: 0 = A as stored; 1 = previous layer's BatchNorm + ReLU on A; 2 = pooled BatchNorm/ReLU/max backward on A (bf16).
+template <int DT, int XFORM, int EPI>
 __global__ void __launch_bounds__((XFORM || DT == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const GemmTnArgs p)
 {
-    constexpr bool kXf = XFORM || DT == DT_TF32X3;
+    constexpr bool kXf = XFORM != 0 || DT == DT_TF32X3;
     constexpr bool TCS = DT == DT_BF16 && EPI != 0;       // statistics on the tensor core
+    static_assert(XFORM != 2 || DT == DT_BF16, "the pooled operand transform is built for bf16 activations");
     constexpr int EPR = DT == DT_BF16 ? 64 : 32;          // elements per 128-byte row = columns per k-block and per output block
     constexpr int NA = DT == DT_TF32X3 ? 2 : 1;           // operand copies per stage (hi, lo)
     constexpr uint32_t kAccStride = TCS ? 128u : 256u;    // TMEM columns between the two accumulators (TCS: BN <= 128)
@@ -344,20 +404,62 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int wg = (warp - 12) >> 2;
         const int t = (threadIdx.x - 384) & 127;
         const int c = t & 7, r0 = t >> 3;
-        int stage = 0, it = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * kTileM;
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                if ((it & 1) == wg) {
-                    mbar_wait(&tail->full[stage], phase);
-                    uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                    transform_cols<DT, XFORM, false, 8, 16>(sa, sa + kABytes, c, r0, s_ascale + kb * EPR, s_ashift + kb * EPR, M - m0);
-                    fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tail->ready[stage]);
+        if (XFORM == 2) {
+            // pooled transform: flat loop over this warpgroup's (tile, k-block) iterations (it = wg, wg + 2, ...) with the
+            // (arg, pgo) lookups of iteration it + 2 in flight while iteration it is processed
+            const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int n_it = my_tiles * num_kb;
+            int it = wg, tl = 0, kb = wg;
+            while (kb >= num_kb) kb -= num_kb, ++tl;
+            int stage = wg % stages;
+            uint32_t phase = (uint32_t)(wg / stages) & 1u;
+            int na[4];
+            float npg[4];
+            if (it < n_it)
+                pool_fetch<4>(kTileM, (((int)blockIdx.x + tl * (int)gridDim.x) / tiles_n) * kTileM, M, p.pool_k, K, kb * EPR, p.pool_arg, p.pool_pgo, t, na, npg);
+            while (it < n_it) {
+                const int m0 = (((int)blockIdx.x + tl * (int)gridDim.x) / tiles_n) * kTileM;
+                const int kb_cur = kb;
+                int ca[4];
+                float cpg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ca[i] = na[i], cpg[i] = npg[i];
+                kb += 2;
+                while (kb >= num_kb) kb -= num_kb, ++tl;
+                if (it + 2 < n_it)
+                    pool_fetch<4>(kTileM, (((int)blockIdx.x + tl * (int)gridDim.x) / tiles_n) * kTileM, M, p.pool_k, K, kb * EPR, p.pool_arg, p.pool_pgo, t, na,
+                                  npg);
+                uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                mbar_wait(&tail->full[stage], phase);
+                uint32_t soff[4], sval[4];
+                pool_gather<4>(sa, kTileM, s_ascale + kb_cur * EPR, s_ashift + kb_cur * EPR, t, ca, cpg, soff, sval);
+                named_bar_sync(3 + wg, 128);       // every special element has been read from the original z
+                transform_cols<DT, true, false, 8, 16, false>(sa, sa, c, r0, s_ascale + kb_cur * EPR, s_ashift + kb_cur * EPR, M - m0);
+                named_bar_sync(3 + wg, 128);
+                pool_scatter<4>(sa, soff, sval);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                it += 2;
+                stage += 2;
+                if (stage >= stages) stage -= stages, phase ^= 1;
+            }
+        } else {
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * kTileM;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    if ((it & 1) == wg) {
+                        uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                        mbar_wait(&tail->full[stage], phase);
+                        transform_cols<DT, XFORM == 1, false, 8, 16>(sa, sa + kABytes, c, r0, s_ascale + kb * EPR, s_ashift + kb * EPR, M - m0);
+                        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                    }
+                    if (++stage == stages) stage = 0, phase ^= 1;
                 }
-                if (++stage == stages) stage = 0, phase ^= 1;
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -614,16 +716,22 @@ struct WgradArgs {
     const float *a_scale, *a_shift;   // XFORM on A
     float *partials;                  // [m_splits][N_pad128][K] fp32
     int n_pad;
+    const int32_t *pool_arg;          // ZPOOL: arg-max row per (group, channel) [M / pool_k, N]
+    const float *pool_pgo;            //        p * dY at that row [M / pool_k, N]
+    const float *pool_negw, *pool_e;  //        [N] each
+    int pool_k;
 };
 
 constexpr int kWgradThreads = 256;
 constexpr int kWgradThreadsXf = 384;
 
-template <int DT, bool XFORM>
-__global__ void __launch_bounds__((XFORM || DT == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads, DT == DT_BF16 ? 2 : 1)
+// ZPOOL (bf16): the dZ operand is rebuilt from the stored pre-activation of the max-pooled layer (transform_pool).
+template <int DT, bool XFORM, bool ZPOOL = false>
+__global__ void __launch_bounds__((XFORM || ZPOOL || DT == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads, DT == DT_BF16 ? 2 : 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmA, const WgradArgs p)
 {
-    constexpr bool kXf = XFORM || DT == DT_TF32X3;
+    constexpr bool kXf = XFORM || ZPOOL || DT == DT_TF32X3;
+    static_assert(!ZPOOL || DT == DT_BF16, "the pooled operand transform is built for bf16 activations");
     constexpr int EPR = DT == DT_BF16 ? 64 : 32;          // channels per 128-byte box row
     constexpr int RB = DT == DT_BF16 ? 64 : 32;           // contraction rows per stage
     constexpr int kBox = RB * 128;                        // one box: RB rows x 128 bytes
@@ -647,12 +755,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
     const uint32_t stage_bytes = NA * half_bytes;
     float *s_ascale = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes);
     float *s_ashift = s_ascale + (XFORM ? KT : 0);
-    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(s_ashift + (XFORM ? KT : 0));
+    float *s_pw = s_ashift + (XFORM ? KT : 0), *s_pe = s_pw + (ZPOOL ? 128 : 0);
+    GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(s_pe + (ZPOOL ? 128 : 0));
     const int m_begin = ms * p.rows_per_split, m_end = min(M, m_begin + p.rows_per_split);
     const int num_rb = m_end > m_begin ? (m_end - m_begin + RB - 1) / RB : 0;
 
     if (XFORM)
         for (int i = threadIdx.x; i < NU; i += blockDim.x) s_ascale[i] = p.a_scale[k0 + i], s_ashift[i] = p.a_shift[k0 + i];
+    if (ZPOOL)
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+            const bool in = n0 + i < N;
+            s_pw[i] = in ? p.pool_negw[n0 + i] : 0.f, s_pe[i] = in ? p.pool_e[n0 + i] : 0.f;
+        }
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmZ);
         prefetch_tensormap(&tmA);
@@ -731,18 +845,52 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             const int first_box = DT == DT_TF32X3 ? 0 : ZB;            // bf16 / single-pass tf32: only the A boxes change
+            int na[2][2];
+            float npg[2][2];
+            if (ZPOOL && num_rb > 0) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) pool_fetch<2>(RB, m_begin, b < a_boxes ? M : 0, p.pool_k, N, n0 + b * EPR, p.pool_arg, p.pool_pgo, t, na[b], npg[b]);
+            }
             for (int rb = 0; rb < num_rb; ++rb) {
-                mbar_wait(&tail->full[stage], phase);
                 uint8_t *s = smem + (size_t)stage * stage_bytes;
                 // rows past M were zero-filled by the TMA; they must stay zero through relu(shift)
                 const int rows_valid = M - (m_begin + rb * RB);
+                int ca[2][2];
+                float cpg[2][2];
+                if (ZPOOL) {
+                    // the (arg, pgo) lookups of the NEXT row block are issued before this one is waited for
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) ca[b][i] = na[b][i], cpg[b][i] = npg[b][i];
+                        if (rb + 1 < num_rb)
+                            pool_fetch<2>(RB, m_begin + (rb + 1) * RB, b < a_boxes ? M : 0, p.pool_k, N, n0 + b * EPR, p.pool_arg, p.pool_pgo, t, na[b], npg[b]);
+                    }
+                }
+                mbar_wait(&tail->full[stage], phase);
+                if (ZPOOL) {
+                    // dZ boxes: special elements first (from the original z), the dense affine pass, then the special values back
+                    uint32_t soff[2][2], sval[2][2];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) pool_gather<2>(s + (size_t)b * kBox, RB, s_pw + b * EPR, s_pe + b * EPR, t, ca[b], cpg[b], soff[b], sval[b]);
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        if (b < a_boxes) {
+                            uint8_t *bp = s + (size_t)b * kBox;
+                            transform_cols<DT, true, false, RB / 16, 16, false>(bp, bp, c, r0, s_pw + b * EPR, s_pe + b * EPR, rows_valid);
+                        }
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) pool_scatter<2>(s + (size_t)b * kBox, soff[b], sval[b]);
+                }
                 for (int box = first_box; box < ZB + AB; ++box) {
                     if (box < ZB ? (box >= a_boxes) : (box - ZB >= b_boxes)) continue;
                     uint8_t *bp = s + (size_t)box * kBox;
                     if (XFORM && box >= ZB)
                         transform_cols<DT, true, DT != DT_BF16, RB / 16, 16>(bp, bp + half_bytes, c, r0, s_ascale + (box - ZB) * EPR,
                                                                              s_ashift + (box - ZB) * EPR, rows_valid);
-                    else
+                    else if (!ZPOOL || box >= ZB)
                         transform_cols<DT, false, DT != DT_BF16, RB / 16, 16>(bp, bp + half_bytes, c, r0, s_ascale, s_ashift, rows_valid);
                 }
                 fence_proxy_async_smem();
@@ -832,7 +980,7 @@ struct TnPlan {
     size_t smem;
 };
 
-static bool plan_gemm_tn(int dt, bool xform, int epi, int M, int N, int K, TnPlan *pl)
+static bool plan_gemm_tn(int dt, int xform, int epi, int M, int N, int K, TnPlan *pl)
 {
     const int epr = dt == DT_BF16 ? 64 : 32;
     const int na = dt == DT_TF32X3 ? 2 : 1;
@@ -865,7 +1013,7 @@ static bool plan_gemm_tn(int dt, bool xform, int epi, int M, int N, int K, TnPla
     return true;
 }
 
-template <int DT, bool XFORM, int EPI>
+template <int DT, int XFORM, int EPI>
 static int launch_tn(const TnPlan &pl, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmBlo, const CUtensorMap &tmC,
                      const CUtensorMap &tmZ, const GemmTnArgs &args, cudaStream_t st)
 {
@@ -881,26 +1029,24 @@ static int launch_tn(const TnPlan &pl, const CUtensorMap &tmA, const CUtensorMap
 extern "C" int mpb_sa_gemm_stat_partials(int dtype, int M, int N, int K, int xform, int epi)
 {
     mpb::TnPlan pl;
-    if (epi == 0 || !mpb::plan_gemm_tn(dtype, xform != 0, epi, M, N, K, &pl)) return 0;
+    if (epi == 0 || !mpb::plan_gemm_tn(dtype, xform, epi, M, N, K, &pl)) return 0;
     return pl.parts_per_cta * pl.grid;
 }
 
-extern "C" int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const void *B_lo, void *C, int M, int N, int K,
-                              const float *a_scale, const float *a_shift, int epi, float *partials, int nparts, const void *Z,
-                              const float *z_scale, const float *z_shift, void *stream)
+namespace mpb {
+static int gemm_tn_impl(int dtype, const void *A, const void *B, const void *B_lo, void *C, int M, int N, int K, int xform,
+                        const float *a_scale, const float *a_shift, const int32_t *pool_arg, const float *pool_pgo, int pool_k, int epi,
+                        float *partials, int nparts, const void *Z, const float *z_scale, const float *z_shift, void *stream)
 {
-    using namespace mpb;
     MPB_REQUIRE(dtype >= DT_BF16 && dtype <= DT_TF32X3, "dtype must be 0 (bf16), 1 (tf32) or 2 (tf32x3)");
     MPB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad size");
     if (M == 0) return MPB_OK;
     MPB_REQUIRE(A && B && C, "null pointer");
     MPB_REQUIRE(dtype != DT_TF32X3 || B_lo, "tf32x3 needs the low part of B");
-    MPB_REQUIRE((a_scale != nullptr) == (a_shift != nullptr), "a_scale / a_shift must come together");
     MPB_REQUIRE(epi >= 0 && epi <= 2, "epi must be 0, 1 or 2");
     MPB_REQUIRE(epi == 0 || partials, "statistics need a partials buffer");
     MPB_REQUIRE(epi != 2 || (Z && z_scale && z_shift), "epi 2 needs Z, z_scale, z_shift");
     MPB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
-    const bool xform = a_scale != nullptr;
     TnPlan pl;
     MPB_REQUIRE(plan_gemm_tn(dtype, xform, epi, M, N, K, &pl), "unsupported shape (K multiple of 64 bf16 / 32 tf32, N multiple of 32, tiles must fit)");
     MPB_REQUIRE(epi == 0 || nparts == pl.parts_per_cta * pl.grid, "nparts mismatch (ask mpb_sa_gemm_stat_partials)");
@@ -925,27 +1071,58 @@ extern "C" int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const voi
     GemmTnArgs args;
     args.M = M, args.N = N, args.K = K, args.BN = pl.BN, args.stages = pl.stages, args.out_bufs = pl.out_bufs;
     args.a_scale = a_scale, args.a_shift = a_shift, args.z_scale = z_scale, args.z_shift = z_shift, args.partials = partials;
+    args.pool_arg = pool_arg, args.pool_pgo = pool_pgo, args.pool_k = pool_k;
     cudaStream_t st = (cudaStream_t)stream;
 #define MPB_TN_CASE(DT, XF, EP) \
     if (dtype == DT && xform == XF && epi == EP) return launch_tn<DT, XF, EP>(pl, tmA, tmB, tmBlo, tmC, tmZ, args, st)
-    MPB_TN_CASE(DT_BF16, false, 0);
-    MPB_TN_CASE(DT_BF16, false, 1);
-    MPB_TN_CASE(DT_BF16, false, 2);
-    MPB_TN_CASE(DT_BF16, true, 0);
-    MPB_TN_CASE(DT_BF16, true, 1);
-    MPB_TN_CASE(DT_TF32, false, 0);
-    MPB_TN_CASE(DT_TF32, false, 1);
-    MPB_TN_CASE(DT_TF32, false, 2);
-    MPB_TN_CASE(DT_TF32, true, 0);
-    MPB_TN_CASE(DT_TF32, true, 1);
-    MPB_TN_CASE(DT_TF32X3, false, 0);
-    MPB_TN_CASE(DT_TF32X3, false, 1);
-    MPB_TN_CASE(DT_TF32X3, false, 2);
-    MPB_TN_CASE(DT_TF32X3, true, 0);
-    MPB_TN_CASE(DT_TF32X3, true, 1);
+    MPB_TN_CASE(DT_BF16, 0, 0);
+    MPB_TN_CASE(DT_BF16, 0, 1);
+    MPB_TN_CASE(DT_BF16, 0, 2);
+    MPB_TN_CASE(DT_BF16, 1, 0);
+    MPB_TN_CASE(DT_BF16, 1, 1);
+    MPB_TN_CASE(DT_BF16, 2, 0);
+    MPB_TN_CASE(DT_BF16, 2, 2);
+    MPB_TN_CASE(DT_TF32, 0, 0);
+    MPB_TN_CASE(DT_TF32, 0, 1);
+    MPB_TN_CASE(DT_TF32, 0, 2);
+    MPB_TN_CASE(DT_TF32, 1, 0);
+    MPB_TN_CASE(DT_TF32, 1, 1);
+    MPB_TN_CASE(DT_TF32X3, 0, 0);
+    MPB_TN_CASE(DT_TF32X3, 0, 1);
+    MPB_TN_CASE(DT_TF32X3, 0, 2);
+    MPB_TN_CASE(DT_TF32X3, 1, 0);
+    MPB_TN_CASE(DT_TF32X3, 1, 1);
 #undef MPB_TN_CASE
-    set_error("mpb_sa_gemm_tn: combination dtype=%d xform=%d epi=%d not built", dtype, (int)xform, epi);
+    set_error("mpb_sa_gemm_tn: combination dtype=%d xform=%d epi=%d not built", dtype, xform, epi);
     return MPB_ERR_UNSUPPORTED;
+}
+}  // namespace mpb
+
+extern "C" int mpb_sa_gemm_tn(int dtype, const void *A, const void *B, const void *B_lo, void *C, int M, int N, int K,
+                              const float *a_scale, const float *a_shift, int epi, float *partials, int nparts, const void *Z,
+                              const float *z_scale, const float *z_shift, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE((a_scale != nullptr) == (a_shift != nullptr), "a_scale / a_shift must come together");
+    return gemm_tn_impl(dtype, A, B, B_lo, C, M, N, K, a_scale ? 1 : 0, a_scale, a_shift, nullptr, nullptr, 0, epi, partials, nparts, Z, z_scale,
+                        z_shift, stream);
+}
+
+// C[M,N] = dZ[M,K] * B[N,K]^T where dZ is rebuilt on the fly from the stored pre-activation Zl [M,K] (bf16) of a max-pooled
+// layer: dZ = pgo * [row is the arg-max row of its (group, channel)] + negw_e[0] * Zl + negw_e[1]   (see mpb_bn_bwd_stats /
+// mpb_bn_bwd_finalize_f32).  pool_k rows per group (16, 32, 64 or a multiple of 128), argmax / pgo [M / pool_k, K].
+extern "C" int mpb_sa_gemm_tn_pool(int dtype, const void *Zl, const void *B, void *C, int M, int N, int K, int pool_k,
+                                   const int32_t *argmax, const float *pgo, const float *negw_e, int epi, float *partials, int nparts,
+                                   const void *Z, const float *z_scale, const float *z_shift, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(dtype == DT_BF16, "the pooled operand transform needs bf16 activations");
+    MPB_REQUIRE(argmax && pgo && negw_e, "null pointer");
+    MPB_REQUIRE(pool_k >= 16 && (128 % pool_k == 0 || pool_k % 128 == 0) && M % pool_k == 0,
+                "pool_k must be 16, 32, 64 or a multiple of 128, and divide M");
+    MPB_REQUIRE(epi == 0 || epi == 2, "epi must be 0 or 2");
+    return gemm_tn_impl(dtype, Zl, B, nullptr, C, M, N, K, 2, negw_e, negw_e + K, argmax, pgo, pool_k, epi, partials, nparts, Z, z_scale, z_shift,
+                        stream);
 }
 
 namespace mpb {
@@ -953,7 +1130,7 @@ struct WgPlan {
     int n_tiles, k_tiles, m_splits, rows_per_split, stages, n_pad, threads, grid;
     size_t smem;
 };
-static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl)
+static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl, bool zpool = false)
 {
     const int epr = dt == DT_BF16 ? 64 : 32, rb = dt == DT_BF16 ? 64 : 32, kt = dt == DT_BF16 ? 256 : 128;
     const int na = dt == DT_TF32X3 ? 2 : 1;
@@ -972,15 +1149,15 @@ static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl)
     stages = stages < 2 ? 2 : (stages > 4 ? 4 : stages);
     pl->stages = stages;
     pl->n_pad = pl->n_tiles * 128;
-    pl->threads = (xform || dt == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads;
+    pl->threads = (xform || zpool || dt == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads;
     pl->grid = pl->n_tiles * pl->k_tiles * pl->m_splits;
-    pl->smem = (size_t)stages * stage_bytes + (xform ? 2 * kt * 4 : 0) + sizeof(GemmSmemTail) + 1024;
+    pl->smem = (size_t)stages * stage_bytes + (xform ? 2 * kt * 4 : 0) + (zpool ? 2 * 128 * 4 : 0) + sizeof(GemmSmemTail) + 1024;
     return pl->smem <= 227 * 1024;
 }
-template <int DT, bool XFORM>
+template <int DT, bool XFORM, bool ZPOOL = false>
 static int launch_wg(const WgPlan &pl, const CUtensorMap &tmZ, const CUtensorMap &tmA, const WgradArgs &args, cudaStream_t st)
 {
-    auto kern = wgrad_kernel<DT, XFORM>;
+    auto kern = wgrad_kernel<DT, XFORM, ZPOOL>;
     MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
     kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmZ, tmA, args);
     return check_launch("wgrad_kernel");
@@ -1003,20 +1180,20 @@ extern "C" int64_t mpb_sa_gemm_wgrad_workspace(int dtype, int M, int N, int K, i
     return (int64_t)pl.m_splits * pl.n_pad * K * 4;
 }
 
-extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K, const float *a_scale,
-                                 const float *a_shift, float *workspace, int cout, int cin, int xyz_last, int accumulate, float *dW,
-                                 void *stream)
+namespace mpb {
+static int wgrad_impl(int dtype, const void *dZ, const void *A, int M, int N, int K, const float *a_scale, const float *a_shift,
+                      const int32_t *pool_arg, const float *pool_pgo, const float *pool_negw_e, int pool_k, float *workspace, int cout, int cin,
+                      int xyz_last, int accumulate, float *dW, void *stream)
 {
-    using namespace mpb;
     MPB_REQUIRE(dtype >= DT_BF16 && dtype <= DT_TF32X3, "dtype must be 0 (bf16), 1 (tf32) or 2 (tf32x3)");
     MPB_REQUIRE(M > 0 && N > 0 && K > 0, "bad size");
     MPB_REQUIRE(dZ && A && dW && workspace, "null pointer");
     MPB_REQUIRE((a_scale != nullptr) == (a_shift != nullptr), "a_scale / a_shift must come together");
     MPB_REQUIRE(cout > 0 && cout <= N && cin > 0 && cin <= K, "cout / cin must fit the padded operand widths");
     MPB_REQUIRE(((uintptr_t)dZ & 15) == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "operands must be 16-byte aligned");
-    const bool xform = a_scale != nullptr;
+    const bool xform = a_scale != nullptr, zpool = pool_arg != nullptr;
     WgPlan pl;
-    MPB_REQUIRE(plan_wgrad(dtype, xform, M, N, K, &pl), "unsupported shape (N multiple of 8, K multiple of 64 bf16 / 32 tf32)");
+    MPB_REQUIRE(plan_wgrad(dtype, xform, M, N, K, &pl, zpool), "unsupported shape (N multiple of 8, K multiple of 64 bf16 / 32 tf32)");
     const int esz = dtype == DT_BF16 ? 2 : 4;
     const int rb = dtype == DT_BF16 ? 64 : 32;
     CUtensorMap tmZ, tmA;
@@ -1027,10 +1204,12 @@ extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M
     WgradArgs args;
     args.M = M, args.N = N, args.K = K, args.k_tiles = pl.k_tiles, args.m_splits = pl.m_splits, args.rows_per_split = pl.rows_per_split;
     args.stages = pl.stages, args.a_scale = a_scale, args.a_shift = a_shift, args.partials = workspace, args.n_pad = pl.n_pad;
+    args.pool_arg = pool_arg, args.pool_pgo = pool_pgo, args.pool_negw = pool_negw_e, args.pool_e = pool_negw_e ? pool_negw_e + N : nullptr;
+    args.pool_k = pool_k;
     cudaStream_t st = (cudaStream_t)stream;
     rc = MPB_ERR_UNSUPPORTED;
 #define MPB_WG_CASE(DT, XF) \
-    if (dtype == DT && xform == XF) rc = launch_wg<DT, XF>(pl, tmZ, tmA, args, st)
+    if (dtype == DT && xform == XF && !zpool) rc = launch_wg<DT, XF>(pl, tmZ, tmA, args, st)
     MPB_WG_CASE(DT_BF16, false);
     MPB_WG_CASE(DT_BF16, true);
     MPB_WG_CASE(DT_TF32, false);
@@ -1038,9 +1217,36 @@ extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M
     MPB_WG_CASE(DT_TF32X3, false);
     MPB_WG_CASE(DT_TF32X3, true);
 #undef MPB_WG_CASE
+    if (zpool && dtype == DT_BF16 && xform) rc = launch_wg<DT_BF16, true, true>(pl, tmZ, tmA, args, st);
+    if (zpool && dtype == DT_BF16 && !xform) rc = launch_wg<DT_BF16, false, true>(pl, tmZ, tmA, args, st);
+    if (rc == MPB_ERR_UNSUPPORTED) set_error("mpb_sa_gemm_wgrad: combination dtype=%d xform=%d pool=%d not built", dtype, (int)xform, (int)zpool);
     if (rc) return rc;
     if (accumulate < 0) return MPB_OK;                   // partial tiles only: the caller reduces them with mpb_sa_gemm_wgrad_reduce
     return launch_wgrad_reduce(pl, workspace, K, cout, cin, xyz_last, accumulate, dW, st);
+}
+}  // namespace mpb
+
+extern "C" int mpb_sa_gemm_wgrad(int dtype, const void *dZ, const void *A, int M, int N, int K, const float *a_scale,
+                                 const float *a_shift, float *workspace, int cout, int cin, int xyz_last, int accumulate, float *dW,
+                                 void *stream)
+{
+    return mpb::wgrad_impl(dtype, dZ, A, M, N, K, a_scale, a_shift, nullptr, nullptr, nullptr, 0, workspace, cout, cin, xyz_last, accumulate, dW,
+                           stream);
+}
+
+// dW = dZ^T * f(A) with dZ rebuilt on the fly from the stored pre-activation Zl [M,N] (bf16) of a max-pooled layer, exactly as in
+// mpb_sa_gemm_tn_pool (a 64-row operand box holds whole pooling groups or part of one: pool_k = 16, 32 or a multiple of 64).
+extern "C" int mpb_sa_gemm_wgrad_pool(int dtype, const void *Zl, const void *A, int M, int N, int K, const float *a_scale,
+                                      const float *a_shift, int pool_k, const int32_t *argmax, const float *pgo, const float *negw_e,
+                                      float *workspace, int cout, int cin, int xyz_last, int accumulate, float *dW, void *stream)
+{
+    using namespace mpb;
+    MPB_REQUIRE(dtype == DT_BF16, "the pooled operand transform needs bf16 activations");
+    MPB_REQUIRE(argmax && pgo && negw_e, "null pointer");
+    MPB_REQUIRE(pool_k >= 16 && (64 % pool_k == 0 || pool_k % 64 == 0) && M % pool_k == 0,
+                "pool_k must be 16, 32 or a multiple of 64, and divide M");
+    MPB_REQUIRE(N % 64 == 0, "N must be a multiple of 64 (padded channels)");
+    return wgrad_impl(dtype, Zl, A, M, N, K, a_scale, a_shift, argmax, pgo, negw_e, pool_k, workspace, cout, cin, xyz_last, accumulate, dW, stream);
 }
 
 // Second half of mpb_sa_gemm_wgrad(accumulate = -1): the fixed-order sum of the per-split partial tiles.  Separate entry point

@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kEwThreads, kStatCtasPerSm)
 bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ arg, const T *__restrict__ Z,
                         const float *__restrict__ zmax, const float *__restrict__ scale, const float *__restrict__ shift,
                         const float *__restrict__ mean, const float *__restrict__ rstd, int64_t G, int K, int C,
-                        float *__restrict__ partials)
+                        float *__restrict__ partials, float *__restrict__ pgo)
 {
     column_sums(G, C, partials, [&](int64_t g0, int64_t stride, int nr, int c0, float(&s0)[8], float(&s1)[8]) {
         for (int u = 0; u < nr; ++u) {
@@ -460,6 +460,9 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
                 const float dy = fmaf(z, scale[c], shift[c]) > 0.f ? dOut[g * C + c] : 0.f;
                 s0[i] += dy;
                 s1[i] = fmaf(dy, z, s1[i]);
+                // the one non-zero of the pooled upstream gradient in (group g, channel c), pre-multiplied by p = gamma * rstd
+                // (= scale): what the GEMMs' pooled operand transform adds at row arg[g, c] (mpb_sa_gemm_*_pool)
+                if (pgo) pgo[g * C + c] = scale[c] * dy;
             }
         }
     });
@@ -470,7 +473,8 @@ bwd_stats_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
 __global__ void __launch_bounds__(kFinThreads)
 bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C_valid, double M, const float *__restrict__ gamma,
                     const float *__restrict__ mean, const float *__restrict__ rstd, float *__restrict__ dgamma,
-                    float *__restrict__ dbeta, float *__restrict__ coef, float4 *__restrict__ clear, int64_t clear_vec4)
+                    float *__restrict__ dbeta, float *__restrict__ coef, float4 *__restrict__ clear, int64_t clear_vec4,
+                    float *__restrict__ negw_e)
 {
     // side job: zero the accumulation buffer of the weight-gradient GEMM that follows (saves a fill launch)
     for (int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x; i < clear_vec4; i += (int64_t)gridDim.x * kFinThreads)
@@ -480,6 +484,7 @@ bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C
     if (reduce_partials(partials, nparts, C, c, s, q)) {
         if (c >= C_valid) {
             coef[c] = coef[C + c] = coef[2 * C + c] = 0.f;
+            if (negw_e) negw_e[c] = negw_e[C + c] = 0.f;
             return;
         }
         q = (double)rstd[c] * (q - (double)mean[c] * s);
@@ -488,6 +493,11 @@ bwd_finalize_kernel(const float *__restrict__ partials, int nparts, int C, int C
         coef[c] = (gamma ? gamma[c] : 1.f) * rstd[c];
         coef[C + c] = (float)(s / M);
         coef[2 * C + c] = (float)(q / M);
+        if (negw_e) {   // dZ = p*dY - w*z + e (ApplyConst), handed to the GEMMs' pooled operand transform as (-w, e)
+            const float w = coef[c] * coef[2 * C + c] * rstd[c];
+            negw_e[c] = -w;
+            negw_e[C + c] = fmaf(mean[c], w, -coef[c] * coef[C + c]);
+        }
     }
 }
 
@@ -991,7 +1001,7 @@ extern "C" int mpb_bn_relu_max(int dtype, const void *Z, const float *scale, con
 
 extern "C" int mpb_bn_bwd_stats(int dtype, const void *dA, const float *dOut, const int32_t *argmax, const float *zmax, int K, const void *Z,
                                 const float *scale, const float *shift, const float *mean, const float *rstd, int64_t M, int C,
-                                float *partials, int nparts, void *stream)
+                                float *partials, int nparts, float *pgo, void *stream)
 {
     using namespace mpb;
     MPB_CHECK_C(C);
@@ -1006,14 +1016,14 @@ extern "C" int mpb_bn_bwd_stats(int dtype, const void *dA, const float *dOut, co
     } else {
         MPB_REQUIRE(argmax && K > 0 && M % K == 0 && nparts == stat_parts(M / K, C), "pooled: bad argmax/K/nparts");
         MPB_DISPATCH_ACT(dtype, bwd_stats_pooled_kernel<T><<<nparts, kEwThreads, stat_smem(C), st>>>(dOut, argmax, (const T *)Z, zmax, scale, shift, mean,
-                                                                                                   rstd, M / K, K, C, partials));
+                                                                                                   rstd, M / K, K, C, partials, pgo));
     }
     return check_launch("bwd_stats kernel");
 }
 
 extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, int C_valid, int64_t M, const float *gamma,
                                        const float *mean, const float *rstd, float *dgamma, float *dbeta, float *coef,
-                                       float *clear, int64_t clear_count, void *stream)
+                                       float *clear, int64_t clear_count, float *negw_e, void *stream)
 {
     using namespace mpb;
     MPB_REQUIRE(partials && mean && rstd && coef && C > 0 && nparts > 0 && M > 0, "bad argument");
@@ -1022,7 +1032,7 @@ extern "C" int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C,
     MPB_REQUIRE(clear_count % 4 == 0 && (reinterpret_cast<uintptr_t>(clear) & 15) == 0, "clear buffer must be 16-byte granular");
     bwd_finalize_kernel<<<(C + 7) / 8, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nparts, C, C_valid, (double)M, gamma, mean, rstd,
                                                                                dgamma, dbeta, coef, reinterpret_cast<float4 *>(clear),
-                                                                               clear_count / 4);
+                                                                               clear_count / 4, negw_e);
     return check_launch("bwd_finalize_kernel");
 }
 

@@ -49,6 +49,12 @@ GEMM_TIMELINE = None
 FUSE_STATS = os.environ.get("MPB_FUSE_STATS", "1") == "1"        # forward BatchNorm statistics in the GEMM epilogue
 FUSE_APPLY = os.environ.get("MPB_FUSE_APPLY", "1") == "1"        # BatchNorm + ReLU of the previous layer in the operand path
 FUSE_BWD_STATS = os.environ.get("MPB_FUSE_BWD_STATS", "1") == "1"  # BatchNorm-backward statistics in the dgrad epilogue
+# Pooled layer: dZ rebuilt in the two consumer GEMMs' operand path (mpb_sa_gemm_tn_pool / _wgrad_pool) instead of written by
+# mpb_bn_bwd_apply and read back twice.  Correct and tested, saves 1.07 GB of HBM traffic per step at B = 64 -- but OFF by
+# default: the dgrad GEMM with the BatchNorm-backward statistics epilogue is bound by shared-memory bandwidth, not HBM, and the
+# extra operand pass costs more (dgrad 80 -> 153 us, wgrad 74 -> 168 us at M = 1M) than the removed 105 us kernel; step
+# 3.25 ms with it, 3.13 ms without (profiles/r02_notes.md).
+FUSE_POOL_APPLY = os.environ.get("MPB_FUSE_POOL_APPLY", "0") == "1"
 
 
 class _Timed:
@@ -68,12 +74,20 @@ class _Timed:
         return False
 
 
-def _gemm_tn(lib, gd, esz, a, b, b_lo, c, M, N, K, st, real, a_affine=None, epi=0, partials=None, nparts=0, z=None, z_affine=None):
+def _gemm_tn(lib, gd, esz, a, b, b_lo, c, M, N, K, st, real, a_affine=None, epi=0, partials=None, nparts=0, z=None, z_affine=None, pool=None):
     """C[M,N] = f(A)[M,K] @ B[N,K]^T.  real = (real K channels, real N channels) for the algorithmic byte count:
-    A and B read once, C written once (+ Z read once for epi 2)."""
+    A and B read once, C written once (+ Z read once for epi 2).  pool = (group size, argmax, pgo, negw_e): A is the stored
+    pre-activation of the max-pooled layer and the kernel rebuilds dZ from it (mpb_sa_gemm_tn_pool)."""
     rk, rn = real
     nbytes = esz * (M * rk + rn * rk + M * rn + (M * rn if epi == 2 else 0))
-    with _Timed("gemm_tn_kernel", nbytes, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d epi=%d" % (M, N, K, 1 if a_affine else 0, epi)):
+    xf = 2 if pool else (1 if a_affine else 0)
+    with _Timed("gemm_tn_kernel", nbytes, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d epi=%d" % (M, N, K, xf, epi)):
+        if pool:
+            pk, p_arg, p_pgo, p_we = pool
+            check(lib.mpb_sa_gemm_tn_pool(gd, ptr(a), ptr(b), ptr(c), M, N, K, pk, ptr(p_arg), ptr(p_pgo), ptr(p_we), epi, ptr(partials), nparts,
+                                          ptr(z), ptr(z_affine[0]) if z_affine else None, ptr(z_affine[1]) if z_affine else None, st),
+                  "mpb_sa_gemm_tn_pool")
+            return
         check(lib.mpb_sa_gemm_tn(gd, ptr(a), ptr(b), ptr(b_lo), ptr(c), M, N, K,
                                  ptr(a_affine[0]) if a_affine else None, ptr(a_affine[1]) if a_affine else None,
                                  epi, ptr(partials), nparts, ptr(z), ptr(z_affine[0]) if z_affine else None,
@@ -91,7 +105,7 @@ def join_wgrad_reductions():
         fork.join(dw)
 
 
-def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz_last, dw):
+def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz_last, dw, pool=None):
     """dW[cout,cin] = crop(dZ[M,N]^T @ f(A)[M,K]).  Algorithmic bytes: dZ and A read once, dW written once (fp32).
     The fixed-order sum of the per-split partial tiles only feeds the optimizer: it is issued on a side stream (joined at the
     end of the module's backward), so the dgrad GEMM that follows starts as soon as the partial tiles are written."""
@@ -103,10 +117,16 @@ def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz
         raise _cabi.MpbError("mpb_sa_gemm_wgrad: unsupported shape M=%d N=%d K=%d" % (M, N, K))
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dw.device)
     defer = DEFER_WGRAD_REDUCE
-    with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d" % (M, N, K, xf)):
-        check(lib.mpb_sa_gemm_wgrad(gd, ptr(dz), ptr(a), M, N, K, ptr(a_affine[0]) if a_affine else None,
-                                    ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, -1 if defer else 0, ptr(dw), st),
-              "mpb_sa_gemm_wgrad", launches=1 if defer else 2)
+    with _Timed("wgrad_kernel", esz * M * (rn + rk) + 4 * rn * rk, 2 * M * rn * rk, "M=%d N=%d K=%d xform=%d pool=%d" % (M, N, K, xf, 1 if pool else 0)):
+        if pool:
+            pk, p_arg, p_pgo, p_we = pool
+            check(lib.mpb_sa_gemm_wgrad_pool(gd, ptr(dz), ptr(a), M, N, K, ptr(a_affine[0]) if a_affine else None,
+                                             ptr(a_affine[1]) if a_affine else None, pk, ptr(p_arg), ptr(p_pgo), ptr(p_we), ptr(ws), cout, cin,
+                                             1 if xyz_last else 0, -1 if defer else 0, ptr(dw), st), "mpb_sa_gemm_wgrad_pool", launches=1 if defer else 2)
+        else:
+            check(lib.mpb_sa_gemm_wgrad(gd, ptr(dz), ptr(a), M, N, K, ptr(a_affine[0]) if a_affine else None,
+                                        ptr(a_affine[1]) if a_affine else None, ptr(ws), cout, cin, 1 if xyz_last else 0, -1 if defer else 0, ptr(dw), st),
+                  "mpb_sa_gemm_wgrad", launches=1 if defer else 2)
     if defer:
         with Fork(ws, dw, slot=4) as fork:
             check(lib.mpb_sa_gemm_wgrad_reduce(gd, M, N, K, xf, ptr(ws), cout, cin, 1 if xyz_last else 0, 0, ptr(dw), stream_ptr()),
@@ -328,8 +348,11 @@ class SharedMLPMax(torch.autograd.Function):
         nparts = lib.mpb_bn_stat_partials(G, cl_p)
         part = torch.empty(nparts, 2 * cl_p, dtype=torch.float32, device=dev)
         sc = stats[L - 1]
+        # pooled layer: the dZ tensor is not materialised -- its two consumer GEMMs rebuild it from Z_L in their operand path
+        pool_fuse = (FUSE_POOL_APPLY and FUSE_APPLY and mode == "bf16" and L >= 2 and K >= 16 and (K in (16, 32, 64) or K % 128 == 0))
+        pgo = torch.empty(G, cl_p, dtype=torch.float32, device=dev) if pool_fuse else None
         check(lib.mpb_bn_bwd_stats(ad, None, ptr(d_pool), ptr(argmax), ptr(zmax), K, ptr(zs[L - 1]), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]),
-                                   ptr(sc[3]), M, cl_p, ptr(part), nparts, st), "mpb_bn_bwd_stats")
+                                   ptr(sc[3]), M, cl_p, ptr(part), nparts, ptr(pgo), st), "mpb_bn_bwd_stats")
         d_a = None
         for l in range(L - 1, -1, -1):
             cout, cin, cout_p, cin_p = dims[l]
@@ -348,8 +371,12 @@ class SharedMLPMax(torch.autograd.Function):
             nw = cout_p * NARROW_LDW if is_narrow else 0
             wbuf = torch.empty(nw + (cout + 3) // 4 * 4, dtype=torch.float32, device=dev)
             dbias = wbuf[nw:nw + cout]
+            pool = None
+            negw_e = torch.empty(2, cout_p, dtype=torch.float32, device=dev) if (pooled and pool_fuse) else None
             check(lib.mpb_bn_bwd_finalize_f32(ptr(part), nparts, cout_p, cout, M, ptr(gamma), ptr(sc[2]), ptr(sc[3]), ptr(dgamma),
-                                              ptr(dbeta), ptr(coef), ptr(wbuf), wbuf.numel(), st), "mpb_bn_bwd_finalize_f32")
+                                              ptr(dbeta), ptr(coef), ptr(wbuf), wbuf.numel(), ptr(negw_e), st), "mpb_bn_bwd_finalize_f32")
+            if negw_e is not None:
+                pool = (K, argmax, pgo, negw_e)
             if is_narrow:
                 # fused dZ + weight gradient against the re-gathered rows; nothing upstream of the grouping needs a gradient
                 dw = wbuf[:nw].view(cout_p, NARROW_LDW)
@@ -364,11 +391,14 @@ class SharedMLPMax(torch.autograd.Function):
                 grads[3] = dbeta if sink_be is None else None
                 d_a = None
                 break
-            dz = torch.empty(M, cout_p, dtype=tdt, device=dev)
-            if pooled:
+            if pool is not None:
+                dz = z          # the GEMMs transform the stored pre-activation into dZ tile by tile
+            elif pooled:
+                dz = torch.empty(M, cout_p, dtype=tdt, device=dev)
                 check(lib.mpb_bn_bwd_apply(ad, None, ptr(d_pool), ptr(argmax), K, ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]),
                                            ptr(coef), M, cout_p, ptr(dz), st), "mpb_bn_bwd_apply")
             else:
+                dz = torch.empty(M, cout_p, dtype=tdt, device=dev)
                 check(lib.mpb_bn_bwd_apply(ad, ptr(d_a), None, None, K, ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), ptr(coef),
                                            M, cout_p, ptr(dz), st), "mpb_bn_bwd_apply")
             # weight gradient against the layer's input f_{l-1}(Z_{l-1}) (or the stored first-layer rows)
@@ -381,7 +411,7 @@ class SharedMLPMax(torch.autograd.Function):
                 _gemm_wgrad(lib, gd, esz, dz, a_prev, M, cout_p, cin_p, st, real, None, cout, cin, False, dw)
             else:
                 _gemm_wgrad(lib, gd, esz, dz, zs[l - 1] if l > 0 else a0, M, cout_p, cin_p, st, real, (ps[0], ps[1]) if l > 0 else None,
-                            cout, cin, ctx.xyz_last and l == 0, dw)
+                            cout, cin, ctx.xyz_last and l == 0, dw, pool=pool)
             grads[6 * l] = dw.view(cout, cin, 1, 1) if sink_w is None else None
             grads[6 * l + 1] = dbias if sink_b is None else None                       # exact zeros: BN removes the conv bias
             grads[6 * l + 2] = dgamma if sink_g is None else None
@@ -391,18 +421,18 @@ class SharedMLPMax(torch.autograd.Function):
             if need_da:
                 d_prev = torch.empty(M, cin_p, dtype=tdt, device=dev)
                 wt, wt_lo = wts[l]
-                np_n = lib.mpb_sa_gemm_stat_partials(gd, M, cin_p, cout_p, 0, 2) if (l > 0 and FUSE_BWD_STATS) else 0
+                np_n = lib.mpb_sa_gemm_stat_partials(gd, M, cin_p, cout_p, 2 if pool else 0, 2) if (l > 0 and FUSE_BWD_STATS) else 0
                 if np_n:   # the layer below's BatchNorm-backward statistics come out of this GEMM's epilogue
                     part_n = torch.empty(np_n, 2 * cin_p, dtype=torch.float32, device=dev)
                     _gemm_tn(lib, gd, esz, dz, wt, wt_lo, d_prev, M, cin_p, cout_p, st, (cout, real[0]), epi=2, partials=part_n, nparts=np_n,
-                             z=zs[l - 1], z_affine=(ps[0], ps[1]))
+                             z=zs[l - 1], z_affine=(ps[0], ps[1]), pool=pool)
                 else:
-                    _gemm_tn(lib, gd, esz, dz, wt, wt_lo, d_prev, M, cin_p, cout_p, st, (cout, real[0]))
+                    _gemm_tn(lib, gd, esz, dz, wt, wt_lo, d_prev, M, cin_p, cout_p, st, (cout, real[0]), pool=pool)
                     if l > 0:
                         np_n = lib.mpb_bn_stat_partials(M, cin_p)
                         part_n = torch.empty(np_n, 2 * cin_p, dtype=torch.float32, device=dev)
                         check(lib.mpb_bn_bwd_stats(ad, ptr(d_prev), None, None, None, K, ptr(zs[l - 1]), ptr(ps[0]), ptr(ps[1]), ptr(ps[2]),
-                                                   ptr(ps[3]), M, cin_p, ptr(part_n), np_n, st), "mpb_bn_bwd_stats")
+                                                   ptr(ps[3]), M, cin_p, ptr(part_n), np_n, None, st), "mpb_bn_bwd_stats")
                 if l > 0:
                     part, nparts = part_n, np_n
             d_a = d_prev

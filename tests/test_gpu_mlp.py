@@ -56,6 +56,24 @@ def test_gemm_wgrad_matches_float64_matmul_and_is_deterministic(M, N, K, dt):
     assert not r.startswith("FAIL"), r
 
 
+@pytest.mark.parametrize("M,N,K,Kg", [(4096, 64, 128, 32), (8192, 128, 256, 64), (70016, 64, 128, 32), (1024, 320, 256, 128), (1024, 64, 128, 256), (128, 64, 64, 16)])
+def test_gemm_tn_pool_rebuilds_dz_from_the_stored_preactivation(M, N, K, Kg):
+    """mpb_sa_gemm_tn_pool: the dgrad GEMM of a max-pooled layer with its dZ operand rebuilt in shared memory from the stored
+    pre-activation, the arg-max rows, p*dY and (-w, e) -- against float64 matmul on the explicitly formed (bf16-rounded) dZ."""
+    cg = _check_gemm()
+    for epi in (0, 2):
+        r = cg.run_tn_pool(M, N, K, Kg, epi)
+        assert not r.startswith("FAIL"), (epi, r)
+
+
+@pytest.mark.parametrize("M,N,K,Kg", [(4096, 128, 64, 32), (8192, 256, 128, 64), (70016, 128, 64, 32), (1024, 64, 192, 128), (1024, 128, 64, 256), (64, 64, 64, 16)])
+def test_gemm_wgrad_pool_rebuilds_dz_and_is_deterministic(M, N, K, Kg):
+    cg = _check_gemm()
+    for xform in (False, True):
+        r = cg.run_wg_pool(M, N, K, Kg, xform)
+        assert not r.startswith("FAIL"), (xform, r)
+
+
 def _emulate(a0, K, convs, bns, mode="bf16"):
     """Same math as the kernels in plain torch.  mode "bf16": rounding to bf16 where the kernels store or feed bf16
     (weights, pre-activations, the normalised operand of the next GEMM); "tf32"/"fp32": float64 ground truth."""

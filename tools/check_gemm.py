@@ -105,6 +105,71 @@ def run_wg(dt, M, N, K, xform, cout=None, cin=None, xyz_last=False, seed=0):
     return ("ok   " if ok else "FAIL ") + "dW rel %.2e bitwise-repeatable %s" % (err, same)
 
 
+def _pool_inputs(M, C, Kg, g):
+    """Random stored pre-activation Zl [M,C] (bf16), arg-max rows, pgo and (-w, e), plus the float64 dZ they define."""
+    Zl = torch.randn(M, C, device=dev, generator=g).bfloat16()
+    G = M // Kg
+    arg = torch.randint(0, Kg, (G, C), device=dev, generator=g, dtype=torch.int32)
+    pgo = torch.randn(G, C, device=dev, generator=g) * (torch.rand(G, C, device=dev, generator=g) > 0.2)
+    negw_e = torch.stack([torch.randn(C, device=dev, generator=g) * 0.5, torch.randn(C, device=dev, generator=g) * 0.3]).contiguous()
+    k = (torch.arange(M, device=dev) % Kg).view(G, Kg, 1)
+    sparse = torch.where(k == arg.view(G, 1, C).long(), pgo.view(G, 1, C).double(), torch.zeros((), device=dev, dtype=torch.float64)).view(M, C)
+    dz = sparse + negw_e[0].double() * Zl.double() + negw_e[1].double()
+    return Zl, arg, pgo, negw_e, dz.float().bfloat16().double()      # the kernel rounds the rebuilt tile to bf16
+
+
+def run_tn_pool(M, N, K, Kg, epi, seed=0):
+    """mpb_sa_gemm_tn_pool: C = dZ @ B^T with dZ rebuilt from (Zl, argmax, pgo, negw_e) in shared memory."""
+    g = torch.Generator(device="cuda").manual_seed(seed + M + N + K)
+    Zl, arg, pgo, negw_e, dz = _pool_inputs(M, K, Kg, g)
+    B = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    C = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    Z = torch.randn(M, N, device=dev, generator=g).bfloat16() if epi == 2 else None
+    zs = (torch.rand(N, device=dev, generator=g) + 0.5) if epi == 2 else None
+    zh = (torch.randn(N, device=dev, generator=g) * 0.3) if epi == 2 else None
+    nparts = lib.mpb_sa_gemm_stat_partials(0, M, N, K, 2, epi) if epi else 0
+    if epi and not nparts:
+        return "skip (cannot fuse)"
+    part = torch.full((max(nparts, 1), 2, N), float("nan"), device=dev) if epi else None
+    check(lib.mpb_sa_gemm_tn_pool(0, ptr(Zl), ptr(B), ptr(C), M, N, K, Kg, ptr(arg), ptr(pgo), ptr(negw_e), epi, ptr(part), nparts, ptr(Z),
+                                  ptr(zs), ptr(zh), stream_ptr()), "gemm_tn_pool")
+    torch.cuda.synchronize()
+    want = dz @ B.double().t()
+    err = rel(C, want)
+    msg = "C rel %.2e" % err
+    ok = err < TOL[0]
+    if epi == 2:
+        Cs, Zd = C.double(), Z.double()
+        dy = torch.where(Zd.float() * zs + zh > 0, Cs, torch.zeros_like(Cs))
+        e0, e1 = rel(part[:, 0].double().sum(0), dy.sum(0)), rel(part[:, 1].double().sum(0), (dy * Zd).sum(0))
+        msg += " sum_dy %.1e sum_dyz %.1e" % (e0, e1)
+        ok = ok and e0 < 1e-3 and e1 < 1e-3
+    return ("ok   " if ok else "FAIL ") + msg
+
+
+def run_wg_pool(M, N, K, Kg, xform, seed=0):
+    """mpb_sa_gemm_wgrad_pool: dW = dZ^T @ f(A) with dZ rebuilt from (Zl, argmax, pgo, negw_e)."""
+    g = torch.Generator(device="cuda").manual_seed(seed + M + N + K)
+    Zl, arg, pgo, negw_e, dz = _pool_inputs(M, N, Kg, g)
+    A = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    sc = (torch.rand(K, device=dev, generator=g) + 0.5) if xform else None
+    sh = (torch.randn(K, device=dev, generator=g) * 0.3) if xform else None
+    ws = torch.empty(lib.mpb_sa_gemm_wgrad_workspace(0, M, N, K, int(xform)) // 4, device=dev)
+    outs = []
+    for _ in range(2):
+        dW = torch.full((N, K), float("nan"), device=dev)
+        check(lib.mpb_sa_gemm_wgrad_pool(0, ptr(Zl), ptr(A), M, N, K, ptr(sc), ptr(sh), Kg, ptr(arg), ptr(pgo), ptr(negw_e), ptr(ws), N, K, 0, 0,
+                                         ptr(dW), stream_ptr()), "wgrad_pool")
+        torch.cuda.synchronize()
+        outs.append(dW)
+    Af = A.double()
+    if xform:
+        Af = torch.relu(Af * sc.double() + sh.double()).float().bfloat16().double()
+    err = rel(outs[0], dz.t() @ Af)
+    same = bool(torch.equal(outs[0], outs[1]))
+    return ("ok   " if err < 2e-3 and same else "FAIL ") + "dW rel %.2e bitwise-repeatable %s" % (err, same)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     dts = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2]
@@ -136,5 +201,16 @@ if __name__ == "__main__":
             r = run_wg(dt, 4096, 128, 192, True, cout=100, cin=131, xyz_last=True)
             fails += r.startswith("FAIL")
             print("wgrad %-6s crop 100x131 xyz_last                  %s" % (NAMES[dt], r), flush=True)
+    if which in ("all", "pool"):
+        for (M, N, K, Kg) in [(4096, 64, 128, 32), (8192, 128, 256, 64), (70016, 64, 128, 32), (1024, 320, 256, 128), (1024, 64, 128, 256), (128, 64, 64, 16)]:
+            for epi in (0, 2):
+                r = run_tn_pool(M, N, K, Kg, epi)
+                fails += r.startswith("FAIL")
+                print("tn_pool    M=%-6d N=%-4d K=%-4d Kg=%-3d epi=%d  %s" % (M, N, K, Kg, epi, r), flush=True)
+        for (M, N, K, Kg) in [(4096, 128, 64, 32), (8192, 256, 128, 64), (70016, 128, 64, 32), (1024, 64, 192, 128), (1024, 128, 64, 256), (64, 64, 64, 16)]:
+            for xform in (False, True):
+                r = run_wg_pool(M, N, K, Kg, xform)
+                fails += r.startswith("FAIL")
+                print("wgrad_pool M=%-6d N=%-4d K=%-4d Kg=%-3d xform=%d %s" % (M, N, K, Kg, xform, r), flush=True)
     print("FAILURES: %d" % fails)
     sys.exit(1 if fails else 0)
