@@ -25,6 +25,8 @@
 // tile); + per-column sum / sum of squares of the stored values (forward BatchNorm statistics); + per-column
 // sum dY / sum dY*z with dY = C * [zscale*z + zshift > 0] against a TMA-loaded tile of the previous layer's
 // pre-activation z (the BatchNorm-backward statistics of the layer below, fused into the dgrad GEMM).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -76,7 +78,30 @@ static int make_map(CUtensorMap *map, int esz, const void *ptr, int64_t rows, in
     return MPB_OK;
 }
 
+// Row-major [rows, cols] table of 32-bit words, no swizzle: box = box_cols x box_rows (the arg-max / pgo tables of the pooled transform).
+static int make_map_plain32(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int box_cols, int box_rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return MPB_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)cols * 4u};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (plain) failed (%d) rows=%lld cols=%lld box=%dx%d ptr=%p", (int)r, (long long)rows, (long long)cols, box_cols,
+                  box_rows, ptr);
+        return MPB_ERR_CUDA;
+    }
+    return MPB_OK;
+}
+
 constexpr int kTileM = 128;
+constexpr int kPoolStageBytes = 4096;   // per stage: arg-max and pgo slices of the box's pooling groups (2 x <= 2 KB)
 constexpr int kABytes = kTileM * 128;   // one 128-row x 128-byte operand / staging tile
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxVec = 1024;           // longest per-channel vector (scale/shift) kept in shared memory
@@ -205,38 +230,29 @@ __device__ __forceinline__ void transform_cols(uint8_t *box, uint8_t *box_lo, in
 // instructions per 16 bytes made the GEMMs transform-bound (dgrad 80 -> 139 us at M = 1M).
 // Box geometry: `rows` rows of 128 bytes (64 channels ch_base .. ch_base+63), first row = global row R0; Kg divides `rows`
 // or is a multiple of it (group boundaries never fall inside... a box holds whole groups or part of one).
-// pool_fetch: the (arg, pgo) entries of this thread's special elements of one box -- plain global loads with no dependence on
-// the box's contents, so the caller issues them one pipeline iteration AHEAD and their L2 latency never shows.
-// pool_gather: the final values of those elements from the original z in the landed box.
+// pool_gather: the final values of this thread's special elements of one box, from the original z in the landed box and the
+// (arg-max, pgo) slices of the box's pooling groups that the TMA producer loaded into the same pipeline stage (tab_arg / tab_pgo:
+// [groups][W] words, W = 64 * boxes covered; the first version fetched them with plain global loads from the transform warps and
+// their latency under a saturated HBM -- several microseconds -- stalled the whole pipeline: 79 -> 126 us).
+// rel0 = global row of (first group, row 0) minus the box's first row; g_valid = groups of the box that exist (rows < M).
 template <int NP>
-__device__ __forceinline__ void pool_fetch(int rows, int R0, int M, int Kg, int C, int ch_base, const int32_t *__restrict__ arg,
-                                           const float *__restrict__ pgo, int t, int (&a)[NP], float (&pg)[NP])
-{
-    const int g0 = R0 / Kg;
-    const int ngroups = Kg >= rows ? 1 : rows / Kg;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const int q = t + 128 * i;
-        const int gl = q >> 6, ch = q & 63;
-        const int g = g0 + gl;
-        const bool ok = gl < ngroups && g * Kg < M && R0 < M;
-        a[i] = ok ? g * Kg + arg[(size_t)g * C + ch_base + ch] - R0 : -1;      // arg-max row of (g, ch) relative to the box
-        pg[i] = ok ? pgo[(size_t)g * C + ch_base + ch] : 0.f;
-    }
-}
-template <int NP>
-__device__ __forceinline__ void pool_gather(const uint8_t *box, int rows, const float *negw, const float *e, int t, const int (&a)[NP],
-                                            const float (&pg)[NP], uint32_t (&off)[NP], uint32_t (&val)[NP])
+__device__ __forceinline__ void pool_gather(const uint8_t *box, int rows, int Kg, int ngroups, int g_valid, int rel0, const int32_t *tab_arg,
+                                            const float *tab_pgo, int W, int col0, const float *negw, const float *e, int t, uint32_t (&off)[NP],
+                                            uint32_t (&val)[NP])
 {
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         off[i] = 0xffffffffu;
-        const int ch = (t + 128 * i) & 63, r = a[i];
-        if (r >= 0 && r < rows) {
-            const uint32_t o = (uint32_t)(r * 128 + ((((ch >> 3) ^ (r & 7)) << 4) | ((ch & 7) << 1)));
-            const float z = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(box + o));
-            off[i] = o;
-            val[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaf(z, negw[ch], e[ch]) + pg[i]));
+        const int q = t + 128 * i;
+        const int gl = q >> 6, ch = q & 63;
+        if (gl < ngroups && gl < g_valid) {
+            const int r = rel0 + gl * Kg + tab_arg[gl * W + col0 + ch];      // the arg-max row of (group, ch), relative to the box
+            if (r >= 0 && r < rows) {
+                const uint32_t o = (uint32_t)(r * 128 + ((((ch >> 3) ^ (r & 7)) << 4) | ((ch & 7) << 1)));
+                const float z = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(box + o));
+                off[i] = o;
+                val[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaf(z, negw[ch], e[ch]) + tab_pgo[gl * W + col0 + ch]));
+            }
         }
     }
 }
@@ -276,7 +292,8 @@ constexpr int kGemmTnThreadsXf = 640;  // + two transform warpgroups (each threa
 template <int DT, int XFORM, int EPI>
 __global__ void __launch_bounds__((XFORM || DT == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const GemmTnArgs p)
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmArg,
+               const __grid_constant__ CUtensorMap tmPgo, const GemmTnArgs p)
 {
     constexpr bool kXf = XFORM != 0 || DT == DT_TF32X3;
     constexpr bool TCS = DT == DT_BF16 && EPI != 0;       // statistics on the tensor core
@@ -289,7 +306,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.M, N = p.N, K = p.K, BN = p.BN, stages = p.stages;
     const uint32_t b_bytes = (uint32_t)BN * 128u;
-    const uint32_t stage_bytes = NA * (kABytes + b_bytes);   // [A | A_lo | B | B_lo]
+    const uint32_t pool_off = NA * (kABytes + b_bytes);                              // XFORM 2: [arg slices | pgo slices] behind the operands
+    const uint32_t stage_bytes = pool_off + (XFORM == 2 ? kPoolStageBytes : 0);      // [A | A_lo | B | B_lo | pool tables]
+    const int pool_groups = XFORM == 2 ? (p.pool_k >= kTileM ? 1 : kTileM / p.pool_k) : 0;   // pooling groups per 128-row tile
     // carve-up (every tile 1024-byte aligned): ring | output staging [2 wg][out_bufs] | z tiles [2 wg][2] (EPI 2) |
     // dY tiles [2 wg] (TCS, EPI 2) | ones box (TCS) | CUDA-core statistic slots [8 warps][2][256] (!TCS) | vectors | barriers
     uint8_t *staging = smem + (size_t)stages * stage_bytes;
@@ -351,8 +370,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&tail->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&tail->full[stage], kABytes + NA * b_bytes);
+                    mbar_arrive_expect_tx(&tail->full[stage], kABytes + NA * b_bytes + (XFORM == 2 ? (uint32_t)pool_groups * 512u : 0u));
                     uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                    if (XFORM == 2) {   // the pooling tables of this tile's groups, channels kb*64 .. +63 (rows past the table: zero fill)
+                        tma_load_2d(sa + pool_off, &tmArg, kb * EPR, m0 / p.pool_k, &tail->full[stage]);
+                        tma_load_2d(sa + pool_off + pool_groups * 256, &tmPgo, kb * EPR, m0 / p.pool_k, &tail->full[stage]);
+                    }
                     tma_load_2d(sa, &tmA, kb * EPR, m0, &tail->full[stage]);
                     tma_load_2d(sa + NA * kABytes, &tmB, kb * EPR, n0, &tail->full[stage]);
                     if (DT == DT_TF32X3) tma_load_2d(sa + NA * kABytes + b_bytes, &tmBlo, kb * EPR, n0, &tail->full[stage]);
@@ -405,44 +428,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int t = (threadIdx.x - 384) & 127;
         const int c = t & 7, r0 = t >> 3;
         if (XFORM == 2) {
-            // pooled transform: flat loop over this warpgroup's (tile, k-block) iterations (it = wg, wg + 2, ...) with the
-            // (arg, pgo) lookups of iteration it + 2 in flight while iteration it is processed
-            const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const int n_it = my_tiles * num_kb;
-            int it = wg, tl = 0, kb = wg;
-            while (kb >= num_kb) kb -= num_kb, ++tl;
-            int stage = wg % stages;
-            uint32_t phase = (uint32_t)(wg / stages) & 1u;
-            int na[4];
-            float npg[4];
-            if (it < n_it)
-                pool_fetch<4>(kTileM, (((int)blockIdx.x + tl * (int)gridDim.x) / tiles_n) * kTileM, M, p.pool_k, K, kb * EPR, p.pool_arg, p.pool_pgo, t, na, npg);
-            while (it < n_it) {
-                const int m0 = (((int)blockIdx.x + tl * (int)gridDim.x) / tiles_n) * kTileM;
-                const int kb_cur = kb;
-                int ca[4];
-                float cpg[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ca[i] = na[i], cpg[i] = npg[i];
-                kb += 2;
-                while (kb >= num_kb) kb -= num_kb, ++tl;
-                if (it + 2 < n_it)
-                    pool_fetch<4>(kTileM, (((int)blockIdx.x + tl * (int)gridDim.x) / tiles_n) * kTileM, M, p.pool_k, K, kb * EPR, p.pool_arg, p.pool_pgo, t, na,
-                                  npg);
-                uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                mbar_wait(&tail->full[stage], phase);
-                uint32_t soff[4], sval[4];
-                pool_gather<4>(sa, kTileM, s_ascale + kb_cur * EPR, s_ashift + kb_cur * EPR, t, ca, cpg, soff, sval);
-                named_bar_sync(3 + wg, 128);       // every special element has been read from the original z
-                transform_cols<DT, true, false, 8, 16, false>(sa, sa, c, r0, s_ascale + kb_cur * EPR, s_ashift + kb_cur * EPR, M - m0);
-                named_bar_sync(3 + wg, 128);
-                pool_scatter<4>(sa, soff, sval);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tail->ready[stage]);
-                it += 2;
-                stage += 2;
-                if (stage >= stages) stage -= stages, phase ^= 1;
+            // pooled transform: special elements first (from the original z), the dense affine pass, then the special values back
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            const int Kg = p.pool_k;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * kTileM;
+                const int g0 = m0 / Kg;
+                const int rel0 = g0 * Kg - m0;                                   // 0 unless a group spans several tiles
+                const int g_valid = (M - g0 * Kg + Kg - 1) / Kg;                 // groups of this tile that exist
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    if ((it & 1) == wg) {
+                        uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                        mbar_wait(&tail->full[stage], phase);
+                        uint32_t soff[4], sval[4];
+                        pool_gather<4>(sa, kTileM, Kg, pool_groups, g_valid, rel0, reinterpret_cast<const int32_t *>(sa + pool_off),
+                                       reinterpret_cast<const float *>(sa + pool_off + pool_groups * 256), EPR, 0, s_ascale + kb * EPR,
+                                       s_ashift + kb * EPR, t, soff, sval);
+                        named_bar_sync(3 + wg, 128);       // every special element has been read from the original z
+                        transform_cols<DT, true, false, 8, 16, false>(sa, sa, c, r0, s_ascale + kb * EPR, s_ashift + kb * EPR, M - m0);
+                        named_bar_sync(3 + wg, 128);
+                        pool_scatter<4>(sa, soff, sval);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                    }
+                    if (++stage == stages) stage = 0, phase ^= 1;
+                }
             }
         } else {
             int stage = 0, it = 0;
@@ -720,6 +732,7 @@ struct WgradArgs {
     const float *pool_pgo;            //        p * dY at that row [M / pool_k, N]
     const float *pool_negw, *pool_e;  //        [N] each
     int pool_k;
+    int ab;                           // A boxes a stage holds: min(K, KT) / EPR (the stage is sized for the real K, not for KT)
 };
 
 constexpr int kWgradThreads = 256;
@@ -728,7 +741,8 @@ constexpr int kWgradThreadsXf = 384;
 // ZPOOL (bf16): the dZ operand is rebuilt from the stored pre-activation of the max-pooled layer (transform_pool).
 template <int DT, bool XFORM, bool ZPOOL = false>
 __global__ void __launch_bounds__((XFORM || ZPOOL || DT == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads, DT == DT_BF16 ? 2 : 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmA, const WgradArgs p)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmArg,
+             const __grid_constant__ CUtensorMap tmPgo, const WgradArgs p)
 {
     constexpr bool kXf = XFORM || ZPOOL || DT == DT_TF32X3;
     static_assert(!ZPOOL || DT == DT_BF16, "the pooled operand transform is built for bf16 activations");
@@ -737,7 +751,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
     constexpr int kBox = RB * 128;                        // one box: RB rows x 128 bytes
     constexpr int KT = DT == DT_BF16 ? 256 : 128;         // A channels (dW columns) per CTA
     constexpr int ZB = 128 / EPR;                         // dZ boxes per stage (128 channels)
-    constexpr int AB = KT / EPR;                          // A boxes per stage (max)
+    const int AB = p.ab;                                  // A boxes per stage
     constexpr int NA = DT == DT_TF32X3 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -752,7 +766,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
     const int b_boxes = NU / EPR;
     // stage layout: [dZ boxes (ZB)] [A boxes (AB)] and, for the split, the same again for the low parts
     const uint32_t half_bytes = (uint32_t)(ZB + AB) * kBox;
-    const uint32_t stage_bytes = NA * half_bytes;
+    const uint32_t pool_off = NA * half_bytes;                                       // ZPOOL: [arg slices | pgo slices], 128 channels wide
+    const uint32_t stage_bytes = pool_off + (ZPOOL ? kPoolStageBytes : 0);
+    const int pool_groups = ZPOOL ? (p.pool_k >= RB ? 1 : RB / p.pool_k) : 0;        // pooling groups per row block
     float *s_ascale = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes);
     float *s_ashift = s_ascale + (XFORM ? KT : 0);
     float *s_pw = s_ashift + (XFORM ? KT : 0), *s_pe = s_pw + (ZPOOL ? 128 : 0);
@@ -793,9 +809,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
                 uint32_t phase = 0;
                 for (int rb = 0; rb < num_rb; ++rb) {
                     mbar_wait(&tail->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&tail->full[stage], (uint32_t)(a_boxes + b_boxes) * kBox);
+                    mbar_arrive_expect_tx(&tail->full[stage], (uint32_t)(a_boxes + b_boxes) * kBox + (ZPOOL ? (uint32_t)pool_groups * 1024u : 0u));
                     uint8_t *s = smem + (size_t)stage * stage_bytes;
                     const int r0 = m_begin + rb * RB;   // rows_per_split is a multiple of RB: a box never straddles two splits
+                    if (ZPOOL) {   // pooling tables of the row block's groups, channels n0 .. n0+127 (outside the table: zero fill)
+                        tma_load_2d(s + pool_off, &tmArg, n0, r0 / p.pool_k, &tail->full[stage]);
+                        tma_load_2d(s + pool_off + pool_groups * 512, &tmPgo, n0, r0 / p.pool_k, &tail->full[stage]);
+                    }
                     for (int b = 0; b < a_boxes; ++b) tma_load_2d(s + b * kBox, &tmZ, n0 + b * EPR, r0, &tail->full[stage]);
                     for (int b = 0; b < b_boxes; ++b) tma_load_2d(s + (ZB + b) * kBox, &tmA, k0 + b * EPR, r0, &tail->full[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
@@ -845,34 +865,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             const int first_box = DT == DT_TF32X3 ? 0 : ZB;            // bf16 / single-pass tf32: only the A boxes change
-            int na[2][2];
-            float npg[2][2];
-            if (ZPOOL && num_rb > 0) {
-#pragma unroll
-                for (int b = 0; b < 2; ++b) pool_fetch<2>(RB, m_begin, b < a_boxes ? M : 0, p.pool_k, N, n0 + b * EPR, p.pool_arg, p.pool_pgo, t, na[b], npg[b]);
-            }
             for (int rb = 0; rb < num_rb; ++rb) {
                 uint8_t *s = smem + (size_t)stage * stage_bytes;
                 // rows past M were zero-filled by the TMA; they must stay zero through relu(shift)
                 const int rows_valid = M - (m_begin + rb * RB);
-                int ca[2][2];
-                float cpg[2][2];
-                if (ZPOOL) {
-                    // the (arg, pgo) lookups of the NEXT row block are issued before this one is waited for
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) ca[b][i] = na[b][i], cpg[b][i] = npg[b][i];
-                        if (rb + 1 < num_rb)
-                            pool_fetch<2>(RB, m_begin + (rb + 1) * RB, b < a_boxes ? M : 0, p.pool_k, N, n0 + b * EPR, p.pool_arg, p.pool_pgo, t, na[b], npg[b]);
-                    }
-                }
                 mbar_wait(&tail->full[stage], phase);
                 if (ZPOOL) {
                     // dZ boxes: special elements first (from the original z), the dense affine pass, then the special values back
                     uint32_t soff[2][2], sval[2][2];
+                    const int R0 = m_begin + rb * RB, Kg = p.pool_k;
+                    const int g0 = R0 / Kg, rel0 = g0 * Kg - R0, g_valid = (M - g0 * Kg + Kg - 1) / Kg;
+                    const int32_t *tab_arg = reinterpret_cast<const int32_t *>(s + pool_off);
+                    const float *tab_pgo = reinterpret_cast<const float *>(s + pool_off + pool_groups * 512);
 #pragma unroll
-                    for (int b = 0; b < 2; ++b) pool_gather<2>(s + (size_t)b * kBox, RB, s_pw + b * EPR, s_pe + b * EPR, t, ca[b], cpg[b], soff[b], sval[b]);
+                    for (int b = 0; b < 2; ++b)
+                        pool_gather<2>(s + (size_t)b * kBox, RB, Kg, b < a_boxes ? pool_groups : 0, g_valid, rel0, tab_arg, tab_pgo, 128, b * EPR, s_pw + b * EPR,
+                                       s_pe + b * EPR, t, soff[b], sval[b]);
                     named_bar_sync(1, 128);
 #pragma unroll
                     for (int b = 0; b < 2; ++b)
@@ -989,7 +997,7 @@ static bool plan_gemm_tn(int dt, int xform, int epi, int M, int N, int K, TnPlan
     const int bn = pick_bn(N, (dt == DT_TF32X3 || tcs) ? 128 : 256, epr);
     if (bn <= 0 || (bn != N && bn % epr)) return false;
     if (dt != DT_BF16 && bn % 32) return false;
-    const int stage_bytes = na * (kABytes + bn * 128);
+    const int stage_bytes = na * (kABytes + bn * 128) + (xform == 2 ? kPoolStageBytes : 0);
     const int fixed0 = (epi == 2 ? 4 * kABytes : 0) + ((tcs && epi == 2) ? 2 * kABytes : 0) + (tcs ? kABytes : 0) +
                        ((epi != 0 && !tcs) ? 8 * 2 * 256 * 4 : 0) + (xform ? 2 * K * 4 : 0) + (epi == 2 ? 2 * N * 4 : 0) +
                        (int)sizeof(GemmSmemTail) + 1024;
@@ -1015,11 +1023,11 @@ static bool plan_gemm_tn(int dt, int xform, int epi, int M, int N, int K, TnPlan
 
 template <int DT, int XFORM, int EPI>
 static int launch_tn(const TnPlan &pl, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmBlo, const CUtensorMap &tmC,
-                     const CUtensorMap &tmZ, const GemmTnArgs &args, cudaStream_t st)
+                     const CUtensorMap &tmZ, const CUtensorMap &tmArg, const CUtensorMap &tmPgo, const GemmTnArgs &args, cudaStream_t st)
 {
     auto kern = gemm_tn_kernel<DT, XFORM, EPI>;
     MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-    kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmA, tmB, tmBlo, tmC, tmZ, args);
+    kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmA, tmB, tmBlo, tmC, tmZ, tmArg, tmPgo, args);
     return check_launch("gemm_tn_kernel");
 }
 
@@ -1068,13 +1076,22 @@ static int gemm_tn_impl(int dtype, const void *A, const void *B, const void *B_l
         rc = make_map(&tmZ, esz, Z, M, N, N, kTileM);
         if (rc) return rc;
     }
+    CUtensorMap tmArg = tmC, tmPgo = tmC;
+    if (xform == 2) {
+        const int groups = pool_k >= kTileM ? 1 : kTileM / pool_k;
+        rc = make_map_plain32(&tmArg, pool_arg, M / pool_k, K, 64, groups);
+        if (rc) return rc;
+        rc = make_map_plain32(&tmPgo, pool_pgo, M / pool_k, K, 64, groups);
+        if (rc) return rc;
+    }
     GemmTnArgs args;
     args.M = M, args.N = N, args.K = K, args.BN = pl.BN, args.stages = pl.stages, args.out_bufs = pl.out_bufs;
     args.a_scale = a_scale, args.a_shift = a_shift, args.z_scale = z_scale, args.z_shift = z_shift, args.partials = partials;
     args.pool_arg = pool_arg, args.pool_pgo = pool_pgo, args.pool_k = pool_k;
+
     cudaStream_t st = (cudaStream_t)stream;
 #define MPB_TN_CASE(DT, XF, EP) \
-    if (dtype == DT && xform == XF && epi == EP) return launch_tn<DT, XF, EP>(pl, tmA, tmB, tmBlo, tmC, tmZ, args, st)
+    if (dtype == DT && xform == XF && epi == EP) return launch_tn<DT, XF, EP>(pl, tmA, tmB, tmBlo, tmC, tmZ, tmArg, tmPgo, args, st)
     MPB_TN_CASE(DT_BF16, 0, 0);
     MPB_TN_CASE(DT_BF16, 0, 1);
     MPB_TN_CASE(DT_BF16, 0, 2);
@@ -1127,7 +1144,7 @@ extern "C" int mpb_sa_gemm_tn_pool(int dtype, const void *Zl, const void *B, voi
 
 namespace mpb {
 struct WgPlan {
-    int n_tiles, k_tiles, m_splits, rows_per_split, stages, n_pad, threads, grid;
+    int n_tiles, k_tiles, m_splits, rows_per_split, stages, n_pad, threads, grid, ab;
     size_t smem;
 };
 static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl, bool zpool = false)
@@ -1143,10 +1160,11 @@ static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl, bool
     pl->rows_per_split = ((row_blocks + m_splits - 1) / m_splits) * rb;
     pl->m_splits = (M + pl->rows_per_split - 1) / pl->rows_per_split;
     const int box = rb * 128;
-    const int stage_bytes = na * (128 / epr + kt / epr) * box;
-    const int budget = dt == DT_BF16 ? 100 * 1024 : 200 * 1024;
+    pl->ab = (K < kt ? K : kt) / epr;                       // A boxes a stage really needs (was sized for kt: 2 stages where 4 fit)
+    const int stage_bytes = na * (128 / epr + pl->ab) * box + (zpool ? kPoolStageBytes : 0);
+    const int budget = dt == DT_BF16 ? 104 * 1024 : 200 * 1024;
     int stages = budget / stage_bytes;
-    stages = stages < 2 ? 2 : (stages > 4 ? 4 : stages);
+    stages = stages < 2 ? 2 : (stages > 6 ? 6 : stages);
     pl->stages = stages;
     pl->n_pad = pl->n_tiles * 128;
     pl->threads = (xform || zpool || dt == DT_TF32X3) ? kWgradThreadsXf : kWgradThreads;
@@ -1155,11 +1173,12 @@ static bool plan_wgrad(int dt, bool xform, int M, int N, int K, WgPlan *pl, bool
     return pl->smem <= 227 * 1024;
 }
 template <int DT, bool XFORM, bool ZPOOL = false>
-static int launch_wg(const WgPlan &pl, const CUtensorMap &tmZ, const CUtensorMap &tmA, const WgradArgs &args, cudaStream_t st)
+static int launch_wg(const WgPlan &pl, const CUtensorMap &tmZ, const CUtensorMap &tmA, const CUtensorMap &tmArg, const CUtensorMap &tmPgo,
+                     const WgradArgs &args, cudaStream_t st)
 {
     auto kern = wgrad_kernel<DT, XFORM, ZPOOL>;
     MPB_ENSURE_DYN_SMEM(kern, 227 * 1024);
-    kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmZ, tmA, args);
+    kern<<<pl.grid, pl.threads, pl.smem, st>>>(tmZ, tmA, tmArg, tmPgo, args);
     return check_launch("wgrad_kernel");
 }
 static int launch_wgrad_reduce(const WgPlan &pl, const float *workspace, int K, int cout, int cin, int xyz_last, int accumulate, float *dW,
@@ -1205,11 +1224,19 @@ static int wgrad_impl(int dtype, const void *dZ, const void *A, int M, int N, in
     args.M = M, args.N = N, args.K = K, args.k_tiles = pl.k_tiles, args.m_splits = pl.m_splits, args.rows_per_split = pl.rows_per_split;
     args.stages = pl.stages, args.a_scale = a_scale, args.a_shift = a_shift, args.partials = workspace, args.n_pad = pl.n_pad;
     args.pool_arg = pool_arg, args.pool_pgo = pool_pgo, args.pool_negw = pool_negw_e, args.pool_e = pool_negw_e ? pool_negw_e + N : nullptr;
-    args.pool_k = pool_k;
+    args.pool_k = pool_k, args.ab = pl.ab;
+    CUtensorMap tmArg = tmZ, tmPgo = tmZ;
+    if (zpool) {
+        const int groups = pool_k >= rb ? 1 : rb / pool_k;
+        rc = make_map_plain32(&tmArg, pool_arg, M / pool_k, N, 128, groups);
+        if (rc) return rc;
+        rc = make_map_plain32(&tmPgo, pool_pgo, M / pool_k, N, 128, groups);
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     rc = MPB_ERR_UNSUPPORTED;
 #define MPB_WG_CASE(DT, XF) \
-    if (dtype == DT && xform == XF && !zpool) rc = launch_wg<DT, XF>(pl, tmZ, tmA, args, st)
+    if (dtype == DT && xform == XF && !zpool) rc = launch_wg<DT, XF>(pl, tmZ, tmA, tmArg, tmPgo, args, st)
     MPB_WG_CASE(DT_BF16, false);
     MPB_WG_CASE(DT_BF16, true);
     MPB_WG_CASE(DT_TF32, false);
@@ -1217,8 +1244,8 @@ static int wgrad_impl(int dtype, const void *dZ, const void *A, int M, int N, in
     MPB_WG_CASE(DT_TF32X3, false);
     MPB_WG_CASE(DT_TF32X3, true);
 #undef MPB_WG_CASE
-    if (zpool && dtype == DT_BF16 && xform) rc = launch_wg<DT_BF16, true, true>(pl, tmZ, tmA, args, st);
-    if (zpool && dtype == DT_BF16 && !xform) rc = launch_wg<DT_BF16, false, true>(pl, tmZ, tmA, args, st);
+    if (zpool && dtype == DT_BF16 && xform) rc = launch_wg<DT_BF16, true, true>(pl, tmZ, tmA, tmArg, tmPgo, args, st);
+    if (zpool && dtype == DT_BF16 && !xform) rc = launch_wg<DT_BF16, false, true>(pl, tmZ, tmA, tmArg, tmPgo, args, st);
     if (rc == MPB_ERR_UNSUPPORTED) set_error("mpb_sa_gemm_wgrad: combination dtype=%d xform=%d pool=%d not built", dtype, (int)xform, (int)zpool);
     if (rc) return rc;
     if (accumulate < 0) return MPB_OK;                   // partial tiles only: the caller reduces them with mpb_sa_gemm_wgrad_reduce

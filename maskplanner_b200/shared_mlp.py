@@ -52,8 +52,8 @@ FUSE_BWD_STATS = os.environ.get("MPB_FUSE_BWD_STATS", "1") == "1"  # BatchNorm-b
 # Pooled layer: dZ rebuilt in the two consumer GEMMs' operand path (mpb_sa_gemm_tn_pool / _wgrad_pool) instead of written by
 # mpb_bn_bwd_apply and read back twice.  Correct and tested, saves 1.07 GB of HBM traffic per step at B = 64 -- but OFF by
 # default: the dgrad GEMM with the BatchNorm-backward statistics epilogue is bound by shared-memory bandwidth, not HBM, and the
-# extra operand pass costs more (dgrad 80 -> 153 us, wgrad 74 -> 168 us at M = 1M) than the removed 105 us kernel; step
-# 3.25 ms with it, 3.13 ms without (profiles/r02_notes.md).
+# extra operand pass costs about as much (stand-alone at M = 1M: dgrad 92 -> 161 us, wgrad 89 -> 108 us) as the removed
+# 105 us kernel saves (profiles/r02_notes.md has the three versions that were measured).
 FUSE_POOL_APPLY = os.environ.get("MPB_FUSE_POOL_APPLY", "0") == "1"
 
 
