@@ -448,18 +448,20 @@ def run_ours(args, ws, rank, local):
     # secondary legs: each one is a full Trainer of its own (own graph); the headline trainer is dropped first
     legs = {}
     if not args.quick:
-        trainer._graph = None
-        del trainer, resident
-        torch.cuda.empty_cache()
+        # Trainers of finished legs are kept alive until the process exits: destroying a captured graph that holds NCCL work
+        # while the communicator stays in use crashed rank 1 inside a later cudaGraphLaunch (2 of 3 runs at N = 2); a leg's
+        # graph pool is a few GB of the 180 GB HBM
+        keep = [trainer, resident]
         n_leg = min(args.steps, 100)
-        if args.precision == "both":
+        # the reference-precision leg is reported at N = 1; under data parallelism it is opt-in (MPB_BENCH_FP32_DP=1): the 3xTF32
+        # step next to captured NCCL work failed intermittently (a CUDA error / a crash inside cudaGraphLaunch in ~1 of 4 runs at
+        # N = 2, bf16 legs never did) -- an open issue recorded in DESIGN.md, and one flaky leg must not cost the scaling runs
+        if args.precision == "both" and (ws == 1 or os.environ.get("MPB_BENCH_FP32_DP", "0") == "1"):
             tr2, _, res2 = make_trainer(args, dev, ws, B, "fp32", rank)
             ms2, _, _ = timed_steps(tr2, res2, n_leg, args.warmup, ws, dev)
             legs["fp32_path"] = {"value": B * ws / (ms2 / 1e3), "unit": "samples/s", "ms_per_step": ms2, "steps": n_leg, "dtype": "tf32x3",
                                  "arithmetic": ARITH["fp32"], "tolerance": "rel 1e-4 (encoder outputs vs the fp32 reference)"}
-            tr2._graph = None
-            del tr2, res2
-            torch.cuda.empty_cache()
+            keep += [tr2, res2]
         if args.scaling == "both" and ws > 1:
             Bs = max(1, args.batch // ws)
             tr3, _, res3 = make_trainer(args, dev, ws, Bs, head_prec, rank)
@@ -467,9 +469,7 @@ def run_ours(args, ws, rank, local):
             legs["strong"] = {"value": Bs * ws / (ms3 / 1e3), "unit": "samples/s", "ms_per_step": ms3, "steps": n_leg, "global_batch": Bs * ws,
                               "per_gpu_batch": Bs, "scaling": "strong",
                               "note": "B = %d global (windows_v2.yaml batch_size), %d samples per rank; BatchNorm statistics per rank (replica semantics)" % (Bs * ws, Bs)}
-            tr3._graph = None
-            del tr3, res3
-            torch.cuda.empty_cache()
+            keep += [tr3, res3]
         from maskplanner_b200 import pointnet2_utils as P
         P.set_mlp_precision(head_prec)
 
@@ -528,10 +528,10 @@ def run_ours(args, ws, rank, local):
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
-        try:
-            dist.destroy_process_group()
-        except Exception as e:        # teardown only; the measurement is already printed
-            print("destroy_process_group: %s" % e, file=sys.stderr)
+        sys.stderr.flush()
+        # the measurement is printed and every rank has passed the barrier: leave without tearing down the captured NCCL work
+        # and the communicator (graph destruction + communicator abort is where multi-rank runs have crashed)
+        os._exit(0)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """2-rank DP smoke test with progress markers (run under torchrun + timeout)."""
-import os, sys, time
+import os, sys, time, faulthandler
+faulthandler.enable()
 os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", os.environ.get("ASYNC_EH", "0"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -16,11 +17,12 @@ use_graph = os.environ.get("GRAPH", "1") == "1"
 B = 16
 tr = Trainer("windows_v2", dev, world_size=ws, use_graph=use_graph)
 tr.model.dropout.p = 0.0
-batch = tr.to_device(synthetic.make_batch(B, "windows_v2", seed0=100 * rank))
+batches = [tr.to_device(synthetic.make_batch(B, "windows_v2", seed0=100 * rank + 7 * j)) for j in range(2)]
 gen = torch.Generator().manual_seed(5)
-for i in range(6):
-    seeds = (torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen))
-    loss = tr.step(batch, seeds)
+seeds = [(torch.randint(0, 5120, (B,), generator=gen), torch.randint(0, 512, (B,), generator=gen)) for _ in range(9)]
+for i in range(8):
+    # pipelined sampling: the next batch (and its FPS seeds) is announced with every call
+    loss = tr.step(batches[i % 2], seeds[i] if i == 0 else None, next_batch=batches[(i + 1) % 2], next_fps_seeds=seeds[i + 1])
     torch.cuda.synchronize()
     log("step", i, float(loss))
 # parameters must stay identical across ranks
