@@ -485,7 +485,9 @@ def run_ours(args, ws, rank, local):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            dkey = top + ("<0" if head_prec == "bf16" else "<2")       # the shared-MLP launches only (the heads' TF32 launches share the kernel)
+            traffic = (tj.get(dkey) or tj.get(top, {})).get("dram_bytes_per_launch")
         roof = {"bound": "hbm", "kernel": "%s (tcgen05/TMA shared-MLP GEMM, %d launches per step)" % (top, d["launches"] // 3),
                 "achieved": d["bytes"] / d["ms"] / 1e6, "peak": peak, "unit": "GB/s", "frac": d["bytes"] / d["ms"] / 1e6 / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],

@@ -70,13 +70,18 @@ def main():
         kn = short(r[k_name])
         lines.append((kn, vals, r[k_grid].replace(",", " ")))
         base = re.sub(r"<.*", "", kn)
-        a = agg.setdefault(base, {"launches": 0, "bytes": 0.0, "us": 0.0})
-        a["launches"] += 1
-        a["bytes"] += (vals["dram_read_MB"] + vals["dram_write_MB"]) * 1e6
-        a["us"] += vals["duration_us"]
+        keys = [base]
+        m = re.match(r"((?:gemm_tn|wgrad)_kernel<\d)", kn)      # the GEMMs also per arithmetic: <0 = bf16 (shared MLP), <1 / <2 = TF32 / 3xTF32
+        if m:
+            keys.append(m.group(1))
+        for key in keys:
+            a = agg.setdefault(key, {"launches": 0, "bytes": 0.0, "us": 0.0})
+            a["launches"] += 1
+            a["bytes"] += (vals["dram_read_MB"] + vals["dram_write_MB"]) * 1e6
+            a["us"] += vals["duration_us"]
     csv_path = os.path.join(out_dir, "%s_ncu_top_kernels.csv" % tag)
     with open(csv_path, "w") as f:
-        f.write("# ncu --set full --clock-control none --profile-from-start off, one eager training step "
+        f.write("# ncu --clock-control none --profile-from-start off (metrics of the columns below), one eager training step "
                 "(tools/ncu_step.py, B=64, windows_v2); made by tools/ncu_report.py from %s\n" % os.path.basename(rep))
         f.write("# per launch (cold cache, serialised, ~40 replays): compare traffic and pipe shares, not absolutes\n")
         f.write("kernel," + ",".join(n for _, n, _ in WANT) + ",grid\n")
