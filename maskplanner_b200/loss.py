@@ -277,6 +277,8 @@ class _FusedAsymmV6(torch.autograd.Function):
     def backward(ctx, g_loss, _g_terms):
         from . import _cabi
         from ._cabi import check, ptr, stream_ptr
+        while BACKWARD_START_HOOKS:
+            BACKWARD_START_HOOKS.pop()()
         x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5 = ctx.saved_tensors
         B, P1, P2, D, P3, D2, NM, nsw = ctx.dims
         g = g_loss.detach().float().reshape(1).contiguous()
@@ -290,6 +292,7 @@ class _FusedAsymmV6(torch.autograd.Function):
 
 
 _PENDING_VALUE = []      # side-stream forks of loss-value kernels not yet joined
+BACKWARD_START_HOOKS = []    # callables run once at the start of the fused loss's backward (the first node of the step's backward)
 
 
 def join_loss_value():

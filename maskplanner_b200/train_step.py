@@ -252,16 +252,26 @@ class Trainer:
         cloud = batch["point_cloud"].permute(0, 2, 1)                             # :207
         fork = None
 
-        def after_encode():
+        def fork_sampling():
+            # the NEXT batch's sampling plan (FPS -> centroids -> ball query of sa1 and sa2) on a side stream
             nonlocal fork
-            if nxt is None:
-                return
             n_cloud, n_seeds, n_out = nxt
             with streams.Fork(n_cloud, slot=2) as fork:
                 with torch.no_grad():
                     self.model.sampling_plan(n_cloud.permute(0, 2, 1), n_seeds, out=n_out)
 
-        pred, masks, scores, _ = self.model(cloud, fps_seeds, plan=plan, after_encode=after_encode)   # :210
+        # Where the branch starts (MPB_SAMPLING_FORK): "encode" (default) = after the encoder forward, next to heads + loss +
+        # head backward; "loss_bwd" = at the start of the loss backward, next to the head backward and SA3's backward.  The
+        # first placement runs the 64-CTA FPS beside the two fma-bound nearest-neighbour searches of the loss, which then take
+        # 0.20-0.23 ms instead of 0.08-0.10 (profiles/r02_graph_timeline.txt); the second keeps them fast but its tail reaches the
+        # persistent GEMMs of SA2's backward, which cannot share an SM with an FPS CTA: measured 3.17 vs 3.14 ms, so "encode" stays.
+        where = os.environ.get("MPB_SAMPLING_FORK", "encode") if nxt is not None else None
+        del L.BACKWARD_START_HOOKS[:]
+        if where == "loss_bwd" and self.fused_loss and os.environ.get("MPB_FUSED_LOSS", "1") == "1":
+            L.BACKWARD_START_HOOKS.append(fork_sampling)
+        pred, masks, scores, _ = self.model(cloud, fps_seeds, plan=plan,
+                                            after_encode=fork_sampling if where in ("encode", "loss_bwd") and not L.BACKWARD_START_HOOKS
+                                            and nxt is not None else None)   # :210
         loss = L.asymm_v6_chamfer_with_stroke_masks(pred, batch["traj"], masks, scores, batch["stroke_ids"],
                                                     batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss,
                                                     weights=self.loss_weights, join_value=False)    # :212-218
