@@ -278,24 +278,113 @@ bn_relu_kernel(const T *__restrict__ Z, const float *__restrict__ scale, const f
     }
 }
 
-constexpr int kMaxUnroll = 4;   // rows in flight per thread in the pooling kernel (8 was measured no faster)
+constexpr int kMaxUnroll = 4;   // rows in flight per thread in the pooling kernel (8 at 3 CTAs/SM: 66-69 us, 4 at 4 CTAs/SM: 63-66 us)
 // out[g, c] = max_k relu(scale*Z[g*K + k, c] + shift); arg[g, c] = first k attaining it (torch.max semantics).
+// relu(scale*z + shift) is monotone in z (non-decreasing for scale >= 0, non-increasing otherwise, and a correctly rounded fma
+// keeps that), so the pooled row is the first maximum of s*z with s = sign(scale): the scan runs on the RAW pre-activations --
+// for bf16 in packed form: one XOR flips the sign of the decreasing channels, one HSETP2 compares two channels against the
+// running maxima, one HMNMX2 updates them, two selects keep the row index; ~20 instructions per 16 bytes and 12 registers of
+// state instead of ~50 (unpack, fma, max, compare, two selects per element) and 24 -- and the affine + ReLU is applied ONCE
+// per (group, channel) at the end.  Groups that the ReLU kills entirely (pooled value 0) report the arg-max of s*z instead of
+// row 0; no gradient flows through them either way.  Round-1 form: 69-71 us for 268 MB (3.8 TB/s), this one 63-66 us (4.2 TB/s);
+// a value-only variant (max / min of z, no index: 8 instructions per 16 bytes) ran at 55 us but moved the arg-max search into
+// bwd_apply_pooled (+9 us each), so the index stays here.
+__device__ __forceinline__ void setp_gt_bf16x2(uint32_t a, uint32_t b, bool &lo, bool &hi)
+{
+    uint32_t l, h;
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.gt.bf16x2 p|q, %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "selp.u32 %1, 1, 0, q;\n\t}"
+        : "=r"(l), "=r"(h)
+        : "r"(a), "r"(b));
+    lo = l != 0, hi = h != 0;
+}
+struct PoolScanBf16 {
+    uint32_t best[4], sgn[4];
+    int bi[8];
+    __device__ __forceinline__ void init(const float (&sc)[8])
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            best[i] = 0xFF80FF80u;                                   // (-inf, -inf)
+            sgn[i] = (sc[2 * i] < 0.f ? 0x00008000u : 0u) | (sc[2 * i + 1] < 0.f ? 0x80000000u : 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bi[i] = 0;
+    }
+    __device__ __forceinline__ void update(const uint4 &raw, int k)
+    {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t v = w[i] ^ sgn[i];
+            bool lo, hi;
+            setp_gt_bf16x2(v, best[i], lo, hi);
+            bi[2 * i] = lo ? k : bi[2 * i];
+            bi[2 * i + 1] = hi ? k : bi[2 * i + 1];
+            __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&v), *reinterpret_cast<const __nv_bfloat162 *>(&best[i]));
+            best[i] = *reinterpret_cast<uint32_t *>(&m);
+        }
+    }
+    __device__ __forceinline__ void get(float (&z)[8]) const     // the selected pre-activations, sign restored
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t v = best[i] ^ sgn[i];
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v));
+            z[2 * i] = f.x, z[2 * i + 1] = f.y;
+        }
+    }
+};
+struct PoolScanF32 {
+    float best[8], sg[8];
+    int bi[8];
+    __device__ __forceinline__ void init(const float (&sc)[8])
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = -INFINITY, sg[i] = sc[i] < 0.f ? -1.f : 1.f, bi[i] = 0;
+    }
+    __device__ __forceinline__ void update(const Act<float>::raw_t &raw, int k)
+    {
+        float z[8];
+        Act<float>::unpack(raw, z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float v = z[i] * sg[i];
+            if (v > best[i]) best[i] = v, bi[i] = k;
+        }
+    }
+    __device__ __forceinline__ void get(float (&z)[8]) const
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = best[i] * sg[i];
+    }
+};
 template <class T>
-__global__ void __launch_bounds__(kEwThreads)
+struct PoolScanOf {
+    typedef PoolScanF32 type;
+};
+template <>
+struct PoolScanOf<__nv_bfloat16> {
+    typedef PoolScanBf16 type;
+};
+
+template <class T>
+__global__ void __launch_bounds__(kEwThreads, sizeof(T) == 2 ? 4 : 2)
 bn_relu_max_kernel(const T *__restrict__ Z, const float *__restrict__ scale, const float *__restrict__ shift, int64_t G,
                    int K, int C, float *__restrict__ out, int *__restrict__ arg, float *__restrict__ zmax)
 {
     const RowWalk w(C);
     if (!w.active) return;
     const int c0 = w.tc * 8;
-    float sc[8], sh[8];
-    load8(scale + c0, sc);
-    load8(shift + c0, sh);
     for (int64_t g = (int64_t)blockIdx.x * w.rpp + w.tr; g < G; g += (int64_t)gridDim.x * w.rpp) {
-        float best[8], bz[8];
-        int bi[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) best[i] = -INFINITY, bi[i] = 0, bz[i] = 0.f;
+        typename PoolScanOf<T>::type scan;
+        {
+            float sc[8];
+            load8(scale + c0, sc);
+            scan.init(sc);          // only the signs stay in registers during the scan
+        }
         const T *zp = Z + (g * K) * C + c0;
         for (int k = 0; k < K; k += kMaxUnroll) {
             typename Act<T>::raw_t raw[kMaxUnroll];
@@ -304,22 +393,20 @@ bn_relu_max_kernel(const T *__restrict__ Z, const float *__restrict__ scale, con
                 if (k + u < K) raw[u] = Act<T>::ld(zp + (int64_t)(k + u) * C);
 #pragma unroll
             for (int u = 0; u < kMaxUnroll; ++u)
-                if (k + u < K) {
-                    float z[8];
-                    Act<T>::unpack(raw[u], z);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float a = fmaxf(fmaf(z[i], sc[i], sh[i]), 0.f);
-                        if (a > best[i]) best[i] = a, bi[i] = k + u, bz[i] = z[i];
-                    }
-                }
+                if (k + u < K) scan.update(raw[u], k + u);
         }
+        float bz[8], best[8], sc[8], sh[8];
+        scan.get(bz);
+        load8(scale + c0, sc);
+        load8(shift + c0, sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = fmaxf(fmaf(bz[i], sc[i], sh[i]), 0.f);
         float4 *op = reinterpret_cast<float4 *>(out + g * C + c0);
         op[0] = make_float4(best[0], best[1], best[2], best[3]);
         op[1] = make_float4(best[4], best[5], best[6], best[7]);
         int4 *ap = reinterpret_cast<int4 *>(arg + g * C + c0);
-        ap[0] = make_int4(bi[0], bi[1], bi[2], bi[3]);
-        ap[1] = make_int4(bi[4], bi[5], bi[6], bi[7]);
+        ap[0] = make_int4(scan.bi[0], scan.bi[1], scan.bi[2], scan.bi[3]);
+        ap[1] = make_int4(scan.bi[4], scan.bi[5], scan.bi[6], scan.bi[7]);
         if (zmax) {   // pre-activation at the arg-max row: lets the backward statistics skip a 2-byte gather per (g, c)
             float4 *zp4 = reinterpret_cast<float4 *>(zmax + g * C + c0);
             zp4[0] = make_float4(bz[0], bz[1], bz[2], bz[3]);
