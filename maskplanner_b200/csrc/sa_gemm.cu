@@ -266,6 +266,8 @@ __device__ __forceinline__ void pool_scatter(uint8_t *box, const uint32_t (&off)
 
 struct GemmTnArgs {
     int M, N, K, BN, stages, out_bufs;
+    int pair;                          // N == 2*BN computed as ONE tile: both halves share the landed (and transformed) A stage, accumulator h and
+                                       // epilogue warpgroup h take columns h*BN .. (bf16 + tensor-core statistics, whose TMEM layout caps BN at 128)
     const float *a_scale, *a_shift;    // XFORM 1: A' = relu(a_scale[k] * A + a_shift[k]); XFORM 2 (pooled): (-w[k], e[k])
     const float *z_scale, *z_shift;    // EPI 2: relu mask of the layer below
     const int32_t *pool_arg;           // XFORM 2: arg-max row of every (group, channel) [M / pool_k, K]
@@ -306,7 +308,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.M, N = p.N, K = p.K, BN = p.BN, stages = p.stages;
     const uint32_t b_bytes = (uint32_t)BN * 128u;
-    const uint32_t pool_off = NA * (kABytes + b_bytes);                              // XFORM 2: [arg slices | pgo slices] behind the operands
+    const int halves = p.pair ? 2 : 1;                                               // B tiles (of BN rows) per stage
+    const uint32_t pool_off = NA * (kABytes + halves * b_bytes);                     // XFORM 2: [arg slices | pgo slices] behind the operands
     const uint32_t stage_bytes = pool_off + (XFORM == 2 ? kPoolStageBytes : 0);      // [A | A_lo | B | B_lo | pool tables]
     const int pool_groups = XFORM == 2 ? (p.pool_k >= kTileM ? 1 : kTileM / p.pool_k) : 0;   // pooling groups per 128-row tile
     // carve-up (every tile 1024-byte aligned): ring | output staging [2 wg][out_bufs] | z tiles [2 wg][2] (EPI 2) |
@@ -321,7 +324,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float *s_zscale = s_ashift + (XFORM ? K : 0), *s_zshift = s_zscale + (EPI == 2 ? N : 0);
     GemmSmemTail *tail = reinterpret_cast<GemmSmemTail *>(s_zshift + (EPI == 2 ? N : 0));
     const int num_kb = K / EPR;
-    const int tiles_m = (M + kTileM - 1) / kTileM, tiles_n = N / BN;
+    const int tiles_m = (M + kTileM - 1) / kTileM, tiles_n = p.pair ? 1 : N / BN;
     const int total = tiles_m * tiles_n;
 
     if (XFORM)
@@ -370,7 +373,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&tail->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&tail->full[stage], kABytes + NA * b_bytes + (XFORM == 2 ? (uint32_t)pool_groups * 512u : 0u));
+                    mbar_arrive_expect_tx(&tail->full[stage], kABytes + NA * halves * b_bytes + (XFORM == 2 ? (uint32_t)pool_groups * 512u : 0u));
                     uint8_t *sa = smem + (size_t)stage * stage_bytes;
                     if (XFORM == 2) {   // the pooling tables of this tile's groups, channels kb*64 .. +63 (rows past the table: zero fill)
                         tma_load_2d(sa + pool_off, &tmArg, kb * EPR, m0 / p.pool_k, &tail->full[stage]);
@@ -378,6 +381,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     tma_load_2d(sa, &tmA, kb * EPR, m0, &tail->full[stage]);
                     tma_load_2d(sa + NA * kABytes, &tmB, kb * EPR, n0, &tail->full[stage]);
+                    if (halves == 2) tma_load_2d(sa + NA * kABytes + b_bytes, &tmB, kb * EPR, BN, &tail->full[stage]);   // pair: bf16 only (NA = 1)
                     if (DT == DT_TF32X3) tma_load_2d(sa + NA * kABytes + b_bytes, &tmBlo, kb * EPR, n0, &tail->full[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
@@ -390,6 +394,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 mbar_wait(&tail->tempty[acc], acc_phase ^ 1);
+                if (halves == 2) mbar_wait(&tail->tempty[1], acc_phase ^ 1);       // pair: both accumulators belong to this tile
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -414,11 +419,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);
                         }
                     }
+                    if (DT == DT_BF16 && halves == 2) {   // second half of the columns: same A stage, second B tile, accumulator 1
+                        const uint64_t bdesc1 = make_smem_desc_sw128(sa + kABytes + b_bytes, 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem + kAccStride, adesc + (uint64_t)(k * 2), bdesc1 + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
                     umma_commit(&tail->empty[stage]);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
                 umma_commit(&tail->tfull[acc]);
-                if ((acc ^= 1) == 0) acc_phase ^= 1;
+                if (halves == 2) {
+                    umma_commit(&tail->tfull[1]);
+                    acc_phase ^= 1;                                                 // acc stays 0: every tile uses both buffers
+                } else if ((acc ^= 1) == 0) {
+                    acc_phase ^= 1;
+                }
             }
         }
     } else if (kXf && warp >= 12) {
@@ -512,8 +528,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         int t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
-            if ((t & 1) != acc) continue;
-            const int m0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
+            if (halves == 1 && (t & 1) != acc) continue;            // pair: every tile, this warpgroup's half of the columns
+            const int m0 = (tile / tiles_n) * kTileM, n0 = halves == 2 ? acc * BN : (tile % tiles_n) * BN;
             mbar_wait(&tail->tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(ew * 32) << 16);
@@ -667,7 +683,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (TCS) {
             // one partial row per warpgroup: wait for its last statistic MMA, then read row 64 (sums) and the Gram diagonal
-            const int n0 = ((int)blockIdx.x % tiles_n) * BN;
+            const int n0 = halves == 2 ? acc * BN : ((int)blockIdx.x % tiles_n) * BN;
             float *dst = p.partials + ((size_t)blockIdx.x * 2 + acc) * 2 * N;
             for (int c = r_in_tile; c < 2 * N; c += 128) dst[c] = 0.f;       // columns of other tiles / no tile processed at all
             named_bar_sync(1 + acc, 128);
@@ -984,9 +1000,19 @@ static int pick_bn(int N, int cap, int blk)
 }
 
 struct TnPlan {
-    int BN, stages, out_bufs, grid, threads, parts_per_cta;
+    int BN, stages, out_bufs, grid, threads, parts_per_cta, pair;
     size_t smem;
 };
+
+static bool os_pair_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MPB_GEMM_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 
 static bool plan_gemm_tn(int dt, int xform, int epi, int M, int N, int K, TnPlan *pl)
 {
@@ -997,7 +1023,11 @@ static bool plan_gemm_tn(int dt, int xform, int epi, int M, int N, int K, TnPlan
     const int bn = pick_bn(N, (dt == DT_TF32X3 || tcs) ? 128 : 256, epr);
     if (bn <= 0 || (bn != N && bn % epr)) return false;
     if (dt != DT_BF16 && bn % 32) return false;
-    const int stage_bytes = na * (kABytes + bn * 128) + (xform == 2 ? kPoolStageBytes : 0);
+    // N = 2 x 128 with the tensor-core statistics (forward, last layer of sa2): ONE tile per 128 rows -- the A stage is loaded and
+    // transformed once for both halves, accumulator / epilogue warpgroup h own columns h*128 .. (two separate N tiles re-read and
+    // re-transformed A and ran at 3.6 TB/s: 105 us for 402 MB)
+    const int pair = (tcs && epi == 1 && N == 2 * bn && bn == 128 && os_pair_enabled()) ? 1 : 0;
+    const int stage_bytes = na * (kABytes + (pair ? 2 : 1) * bn * 128) + (xform == 2 ? kPoolStageBytes : 0);
     const int fixed0 = (epi == 2 ? 4 * kABytes : 0) + ((tcs && epi == 2) ? 2 * kABytes : 0) + (tcs ? kABytes : 0) +
                        ((epi != 0 && !tcs) ? 8 * 2 * 256 * 4 : 0) + (xform ? 2 * K * 4 : 0) + (epi == 2 ? 2 * N * 4 : 0) +
                        (int)sizeof(GemmSmemTail) + 1024;
@@ -1009,12 +1039,12 @@ static bool plan_gemm_tn(int dt, int xform, int epi, int M, int N, int K, TnPlan
     }
     if (stages < 2) return false;
     stages = stages > 8 ? 8 : stages;
-    const int tiles_n = N / bn;
+    const int tiles_n = pair ? 1 : N / bn;
     const int tiles = ((M + kTileM - 1) / kTileM) * tiles_n;
     int grid = tiles < sm_count() ? tiles : sm_count();
     grid = grid / tiles_n * tiles_n;       // a CTA always owns the same column tile (statistics partial rows)
     if (grid < tiles_n) return false;
-    pl->BN = bn, pl->stages = stages, pl->out_bufs = out_bufs, pl->grid = grid;
+    pl->BN = bn, pl->stages = stages, pl->out_bufs = out_bufs, pl->grid = grid, pl->pair = pair;
     pl->parts_per_cta = tcs ? 2 : 8;
     pl->threads = (xform || dt == DT_TF32X3) ? kGemmTnThreadsXf : kGemmTnThreads;
     pl->smem = (size_t)stages * stage_bytes + 2 * out_bufs * kABytes + fixed0;
@@ -1085,7 +1115,7 @@ static int gemm_tn_impl(int dtype, const void *A, const void *B, const void *B_l
         if (rc) return rc;
     }
     GemmTnArgs args;
-    args.M = M, args.N = N, args.K = K, args.BN = pl.BN, args.stages = pl.stages, args.out_bufs = pl.out_bufs;
+    args.M = M, args.N = N, args.K = K, args.BN = pl.BN, args.stages = pl.stages, args.out_bufs = pl.out_bufs, args.pair = pl.pair;
     args.a_scale = a_scale, args.a_shift = a_shift, args.z_scale = z_scale, args.z_shift = z_shift, args.partials = partials;
     args.pool_arg = pool_arg, args.pool_pgo = pool_pgo, args.pool_k = pool_k;
 
