@@ -235,6 +235,10 @@ MPB_API int mpb_bn_bwd_finalize_f32(const float *partials, int nparts, int C, in
                                     const float *gamma, const float *mean, const float *rstd,
                                     float *dgamma, float *dbeta, float *coef, float *clear,
                                     int64_t clear_count, float *negw_e, void *stream);
+/* dZ of a max-pooled layer from the by-products of the statistics pass (pgo, negw_e below): the lean form of the pooled
+ * mpb_bn_bwd_apply (16 instead of 40 per-channel registers, no ReLU re-evaluation). */
+MPB_API int mpb_bn_bwd_apply_pooled(int dtype, const float *pgo, const int32_t *argmax, int K, const void *Z,
+                                    const float *negw_e, int64_t M, int C, void *dZ, void *stream);
 /* pgo (pooled form of _bwd_stats, optional, fp32 [G,C]) and negw_e (_bwd_finalize, optional, fp32 [2,C]) feed the POOLED
  * operand transform of mpb_sa_gemm_tn_pool / mpb_sa_gemm_wgrad_pool: with dZ = p*dY - w*z + e and dY non-zero only at the
  * arg-max row of each (group, channel), pgo[g,c] = p[c]*dY[g,c] and negw_e = (-w, e); the GEMMs then rebuild the dZ tile

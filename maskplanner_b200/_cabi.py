@@ -66,6 +66,7 @@ SIGNATURES = {
     "mpb_pack_weight_bf16": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "mpb_pack_weight_tf32": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mpb_bn_bwd_apply": (_I, [_I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "mpb_bn_bwd_apply_pooled": (_I, [_I, _P, _P, _I, _P, _P, _L, _I, _P, _P]),
     "mpb_sa_first_layer": (_I, [_I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P]),
     "mpb_sa_first_layer_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I,
                                    _P, _I, _P]),

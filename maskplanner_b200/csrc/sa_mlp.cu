@@ -694,6 +694,51 @@ bwd_apply_pooled_kernel(const float *__restrict__ dOut, const int *__restrict__ 
     }
 }
 
+// The same pooled backward from PRE-DIGESTED inputs: pgo[g, c] = p * dY at the pooled row (ReLU gate included, written by
+// bwd_stats_pooled_kernel) and (-w, e) per channel (written by bwd_finalize_kernel), so  dZ = pgo * [row == arg] - w*z + e  needs
+// 16 per-channel registers instead of 40, no ReLU re-evaluation and no coefficient algebra per thread: 117 -> ~70 registers,
+// one more resident CTA per SM.
+template <class T>
+__global__ void __launch_bounds__(kEwThreads, 3)
+bwd_apply_pooled_lean_kernel(const float *__restrict__ pgo, const int *__restrict__ arg, int K, const T *__restrict__ Z,
+                             const float *__restrict__ negw_e, int64_t G, int C, T *__restrict__ dZ)
+{
+    const RowWalk w(C);
+    if (!w.active) return;
+    const int c0 = w.tc * 8;
+    float nw[8], e[8];
+    load8(negw_e + c0, nw);
+    load8(negw_e + C + c0, e);
+    const int kseg = ((K + (int)gridDim.y - 1) / (int)gridDim.y + kRowUnroll - 1) / kRowUnroll * kRowUnroll;
+    const int kb = (int)blockIdx.y * kseg, ke = min(K, kb + kseg);
+    for (int64_t g = (int64_t)blockIdx.x * w.rpp + w.tr; g < G; g += (int64_t)gridDim.x * w.rpp) {
+        float pg[8];
+        int am[8];
+        load8(pgo + g * C + c0, pg);
+        {
+            const int4 a = *reinterpret_cast<const int4 *>(arg + g * C + c0), b = *reinterpret_cast<const int4 *>(arg + g * C + c0 + 4);
+            am[0] = a.x, am[1] = a.y, am[2] = a.z, am[3] = a.w, am[4] = b.x, am[5] = b.y, am[6] = b.z, am[7] = b.w;
+        }
+        const T *zp = Z + (g * K) * C + c0;
+        T *dp = dZ + (g * K) * C + c0;
+        for (int kk = kb; kk < ke; kk += kRowUnroll) {
+            typename Act<T>::raw_t raw[kRowUnroll];
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (kk + u < ke) raw[u] = Act<T>::ld(zp + (int64_t)(kk + u) * C);
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (kk + u < ke) {
+                    float z[8], d[8];
+                    Act<T>::unpack(raw[u], z);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[i] = fmaf(nw[i], z[i], e[i]) + (am[i] == kk + u ? pg[i] : 0.f);
+                    Act<T>::st(dp + (int64_t)(kk + u) * C, Act<T>::pack(d));
+                }
+        }
+    }
+}
+
 // ---- narrow first layer (SA1: 3 or 6 input channels) ------------------------------------------------
 // When the grouped row is only [feats(D) | centred xyz(3)] with 3 + D <= 8, padding it to a 64-column bf16 GEMM
 // operand costs 128 B/row of HBM three times (write, GEMM read, weight-gradient read) for 6-16 real bytes.  These
@@ -1151,6 +1196,25 @@ extern "C" int mpb_bn_bwd_apply(int dtype, const void *dA, const float *dOut, co
         });
     }
     return check_launch("bwd_apply kernel");
+}
+
+// Pooled form of mpb_bn_bwd_apply from the by-products of the statistics pass: pgo (mpb_bn_bwd_stats) and negw_e (mpb_bn_bwd_finalize_f32).
+extern "C" int mpb_bn_bwd_apply_pooled(int dtype, const float *pgo, const int32_t *argmax, int K, const void *Z, const float *negw_e, int64_t M,
+                                       int C, void *dZ, void *stream)
+{
+    using namespace mpb;
+    MPB_CHECK_C(C);
+    MPB_CHECK_DT(dtype);
+    MPB_REQUIRE(M > 0 && K > 0 && M % K == 0 && pgo && argmax && Z && negw_e && dZ, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPB_DISPATCH_ACT(dtype, {
+        static const int occ = resident_per_sm<T>((const void *)bwd_apply_pooled_lean_kernel<T>);
+        const int bx = row_blocks(M / K, C, occ), cap = occ * sm_count();
+        int ks = (cap + bx - 1) / bx;                       // segments needed to fill one wave ...
+        ks = ks > K / 8 ? K / 8 : ks;                       // ... of at least 8 rows each
+        bwd_apply_pooled_lean_kernel<T><<<dim3(bx, ks < 1 ? 1 : ks), kEwThreads, 0, st>>>(pgo, argmax, K, (const T *)Z, negw_e, M / K, C, (T *)dZ);
+    });
+    return check_launch("bwd_apply_pooled_lean_kernel");
 }
 
 namespace mpb {

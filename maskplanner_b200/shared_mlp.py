@@ -55,6 +55,7 @@ FUSE_BWD_STATS = os.environ.get("MPB_FUSE_BWD_STATS", "1") == "1"  # BatchNorm-b
 # extra operand pass costs about as much (stand-alone at M = 1M: dgrad 92 -> 161 us, wgrad 89 -> 108 us) as the removed
 # 105 us kernel saves (profiles/r02_notes.md has the three versions that were measured).
 FUSE_POOL_APPLY = os.environ.get("MPB_FUSE_POOL_APPLY", "0") == "1"
+LEAN_POOLED_APPLY = os.environ.get("MPB_LEAN_POOLED_APPLY", "1") == "1"   # pooled dZ from pgo / (-w, e) (mpb_bn_bwd_apply_pooled)
 
 
 class _Timed:
@@ -350,7 +351,8 @@ class SharedMLPMax(torch.autograd.Function):
         sc = stats[L - 1]
         # pooled layer: the dZ tensor is not materialised -- its two consumer GEMMs rebuild it from Z_L in their operand path
         pool_fuse = (FUSE_POOL_APPLY and FUSE_APPLY and mode == "bf16" and L >= 2 and K >= 16 and (K in (16, 32, 64) or K % 128 == 0))
-        pgo = torch.empty(G, cl_p, dtype=torch.float32, device=dev) if pool_fuse else None
+        lean_apply = LEAN_POOLED_APPLY and L >= 1 and not (L == 1 and narrow is not None)
+        pgo = torch.empty(G, cl_p, dtype=torch.float32, device=dev) if (pool_fuse or lean_apply) else None
         check(lib.mpb_bn_bwd_stats(ad, None, ptr(d_pool), ptr(argmax), ptr(zmax), K, ptr(zs[L - 1]), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]),
                                    ptr(sc[3]), M, cl_p, ptr(part), nparts, ptr(pgo), st), "mpb_bn_bwd_stats")
         d_a = None
@@ -372,10 +374,10 @@ class SharedMLPMax(torch.autograd.Function):
             wbuf = torch.empty(nw + (cout + 3) // 4 * 4, dtype=torch.float32, device=dev)
             dbias = wbuf[nw:nw + cout]
             pool = None
-            negw_e = torch.empty(2, cout_p, dtype=torch.float32, device=dev) if (pooled and pool_fuse) else None
+            negw_e = torch.empty(2, cout_p, dtype=torch.float32, device=dev) if (pooled and (pool_fuse or lean_apply)) else None
             check(lib.mpb_bn_bwd_finalize_f32(ptr(part), nparts, cout_p, cout, M, ptr(gamma), ptr(sc[2]), ptr(sc[3]), ptr(dgamma),
                                               ptr(dbeta), ptr(coef), ptr(wbuf), wbuf.numel(), ptr(negw_e), st), "mpb_bn_bwd_finalize_f32")
-            if negw_e is not None:
+            if negw_e is not None and pool_fuse:
                 pool = (K, argmax, pgo, negw_e)
             if is_narrow:
                 # fused dZ + weight gradient against the re-gathered rows; nothing upstream of the grouping needs a gradient
@@ -393,6 +395,9 @@ class SharedMLPMax(torch.autograd.Function):
                 break
             if pool is not None:
                 dz = z          # the GEMMs transform the stored pre-activation into dZ tile by tile
+            elif pooled and negw_e is not None:
+                dz = torch.empty(M, cout_p, dtype=tdt, device=dev)
+                check(lib.mpb_bn_bwd_apply_pooled(ad, ptr(pgo), ptr(argmax), K, ptr(z), ptr(negw_e), M, cout_p, ptr(dz), st), "mpb_bn_bwd_apply_pooled")
             elif pooled:
                 dz = torch.empty(M, cout_p, dtype=tdt, device=dev)
                 check(lib.mpb_bn_bwd_apply(ad, None, ptr(d_pool), ptr(argmax), K, ptr(z), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]),

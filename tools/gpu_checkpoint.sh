@@ -10,8 +10,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
     --log-file gpurun_out/launches_step.csv python tools/ncu_step.py > gpurun_out/ncu_step.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_step.csv > gpurun_out/${TAG}_launches_train_step.txt 2>&1; head -12 gpurun_out/${TAG}_launches_train_step.txt
 python tools/graph_timeline.py bf16 64 > gpurun_out/${TAG}_graph_timeline.txt 2> gpurun_out/graph_timeline.err; head -2 gpurun_out/${TAG}_graph_timeline.txt
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base function -k regex:"gemm_tn|wgrad|bn_|bwd_|fps_|ball_query|group_rows|chamfer|narrow_first|adam|lap_kernel|loss_|mask_cost|head_act|pose_out|stage_batch" -o gpurun_out/${TAG}_step python tools/ncu_step.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
-ncu -i gpurun_out/${TAG}_step.ncu-rep --page raw --csv > gpurun_out/${TAG}_step_raw.csv 2>/dev/null
+bash tools/gpu_ncu_full.sh ${TAG}
+
 timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${TAG}_sanitizer_memcheck.txt 2>&1; tail -4 gpurun_out/${TAG}_sanitizer_memcheck.txt
 timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${TAG}_sanitizer_racecheck.txt 2>&1; tail -4 gpurun_out/${TAG}_sanitizer_racecheck.txt
 rm -f gpurun_out/graph_trace.json
