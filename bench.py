@@ -453,10 +453,7 @@ def run_ours(args, ws, rank, local):
         # graph pool is a few GB of the 180 GB HBM
         keep = [trainer, resident]
         n_leg = min(args.steps, 100)
-        # the reference-precision leg is reported at N = 1; under data parallelism it is opt-in (MPB_BENCH_FP32_DP=1): the 3xTF32
-        # step next to captured NCCL work failed intermittently (a CUDA error / a crash inside cudaGraphLaunch in ~1 of 4 runs at
-        # N = 2, bf16 legs never did) -- an open issue recorded in DESIGN.md, and one flaky leg must not cost the scaling runs
-        if args.precision == "both" and (ws == 1 or os.environ.get("MPB_BENCH_FP32_DP", "0") == "1"):
+        if args.precision == "both":
             tr2, _, res2 = make_trainer(args, dev, ws, B, "fp32", rank)
             ms2, _, _ = timed_steps(tr2, res2, n_leg, args.warmup, ws, dev)
             legs["fp32_path"] = {"value": B * ws / (ms2 / 1e3), "unit": "samples/s", "ms_per_step": ms2, "steps": n_leg, "dtype": "tf32x3",

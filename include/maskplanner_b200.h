@@ -370,6 +370,10 @@ MPB_API int mpb_stage_batch(int nsegs, const void *const *src, void *const *dst,
                             const int64_t *src_rows, const int64_t *dst_rows, const int64_t *row_words,
                             const uint32_t *pad_bits, void *stream);
 
+/* Developer aid: in a library built with -DMPB_MBAR_DEBUG, where the first timed-out mbarrier wait of the tcgen05 GEMM
+ * pipelines happened (source line, CTA, thread, ...); all zeros in a normal build. */
+MPB_API int mpb_debug_mbar_state(int *out8, int reset);
+
 #ifdef __cplusplus
 }
 #endif

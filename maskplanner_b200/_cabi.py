@@ -72,6 +72,7 @@ SIGNATURES = {
                                    _P, _I, _P]),
     "mpb_adam_step_f32": (_I, [_I, _P, _P, _P, _P, _P, _F, _P, _D, _D, _D, _D, _F, _P, _P, _P]),
     "mpb_lap_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "mpb_debug_mbar_state": (_I, [_P, _I]),
     "mpb_stage_batch": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mpb_loss_lengths_f32": (_I, [_P, _I, _I, _P, _I, _I, _I, _F, _P, _P, _P]),
     "mpb_mask_cost_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),

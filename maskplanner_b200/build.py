@@ -21,6 +21,8 @@ LIB = os.path.join(LIB_DIR, "libmaskplanner_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
               "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177"]
+if os.environ.get("MPB_MBAR_DEBUG", "0") == "1":      # developer build: timed-out mbarrier waits record their location (tc_common.cuh)
+    NVCC_FLAGS.append("-DMPB_MBAR_DEBUG")
 
 
 def _nvcc():

@@ -454,9 +454,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rel0 = g0 * Kg - m0;                                   // 0 unless a group spans several tiles
                 const int g_valid = (M - g0 * Kg + Kg - 1) / Kg;                 // groups of this tile that exist
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    mbar_wait(&tail->full[stage], phase);              // BOTH warpgroups observe every phase (see below)
                     if ((it & 1) == wg) {
                         uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                        mbar_wait(&tail->full[stage], phase);
                         uint32_t soff[4], sval[4];
                         pool_gather<4>(sa, kTileM, Kg, pool_groups, g_valid, rel0, reinterpret_cast<const int32_t *>(sa + pool_off),
                                        reinterpret_cast<const float *>(sa + pool_off + pool_groups * 256), EPR, 0, s_ascale + kb * EPR,
@@ -478,9 +478,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * kTileM;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    // BOTH warpgroups wait for every stage, also the ones they do not transform.  mbarrier waits test a phase PARITY: a
+                    // waiter that has not observed phase n of a barrier and asks for phase n+1 gets "done" while phase n is still
+                    // pending.  With an odd stage count a stage changes hands between the warpgroups every revolution, and when the
+                    // TMA loads of two consecutive stages completed out of order (seen under NCCL traffic with the 3-stage 3xTF32 ring)
+                    // the idle warpgroup ran one revolution ahead, rewrote a stage that had not landed and arrived on `ready` early:
+                    // a deadlock ~once per thousand steps (found with the MPB_MBAR_DEBUG build).
+                    mbar_wait(&tail->full[stage], phase);
                     if ((it & 1) == wg) {
                         uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                        mbar_wait(&tail->full[stage], phase);
                         transform_cols<DT, XFORM == 1, false, 8, 16>(sa, sa + kABytes, c, r0, s_ascale + kb * EPR, s_ashift + kb * EPR, M - m0);
                         fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                         __syncwarp();
@@ -1318,4 +1324,24 @@ extern "C" int mpb_sa_gemm_wgrad_reduce(int dtype, int M, int N, int K, int xfor
     WgPlan pl;
     MPB_REQUIRE(plan_wgrad(dtype, xform != 0, M, N, K, &pl), "unsupported shape");
     return launch_wgrad_reduce(pl, workspace, K, cout, cin, xyz_last, accumulate != 0, dW, (cudaStream_t)stream);
+}
+
+// Developer aid (MPB_MBAR_DEBUG builds): where the first timed-out mbarrier wait happened; all zeros otherwise.
+// out8 = {source line in sa_gemm.cu, blockIdx.x, threadIdx.x, gridDim.x, parity, barrier shared address, blockDim.x, 0}
+extern "C" int mpb_debug_mbar_state(int *out8, int reset)
+{
+    using namespace mpb;
+    MPB_REQUIRE(out8, "null pointer");
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+#ifdef MPB_MBAR_DEBUG
+    MPB_CUDA(cudaMemcpyFromSymbol(out8, tc::g_mbar_dbg, sizeof(int) * 8));
+    if (reset) {
+        int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        MPB_CUDA(cudaMemcpyToSymbol(tc::g_mbar_dbg, z, sizeof(z)));
+        MPB_CUDA(cudaMemcpyToSymbol(tc::g_mbar_abort, z, sizeof(int)));
+    }
+#else
+    (void)reset;
+#endif
+    return MPB_OK;
 }

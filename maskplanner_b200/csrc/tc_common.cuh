@@ -31,8 +31,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded spin: a pipeline bug must surface as a trapped launch (an error code on the host), never as a
-// hung GPU.  ~2^31 polls is minutes of wall clock, far beyond any legitimate wait.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// hung GPU.  ~2^28 polls is ~20 s of wall clock, far beyond any legitimate wait.
+// Built with -DMPB_MBAR_DEBUG (MPB_MBAR_DEBUG=1 python -m maskplanner_b200.build) a timed-out wait instead RECORDS where it
+// happened -- source line of the wait, CTA, thread, parity, barrier address -- in g_mbar_dbg (read back with
+// mpb_debug_mbar_state) and lets every waiter fall through, so the launch ends and the host can ask which barrier starved.
+#ifdef MPB_MBAR_DEBUG
+__device__ int g_mbar_dbg[8];
+__device__ int g_mbar_abort;
+#endif
+__device__ __forceinline__ void mbar_wait_at(uint64_t *bar, uint32_t parity, int line)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
@@ -44,9 +51,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
+#ifdef MPB_MBAR_DEBUG
+        if (!done && (spin & 0xFFFFu) == 0xFFFFu) {
+            if (*(volatile int *)&g_mbar_abort) return;
+            if (spin > (1u << 24)) {
+                if (atomicCAS(&g_mbar_dbg[0], 0, line) == 0) {
+                    g_mbar_dbg[1] = (int)blockIdx.x, g_mbar_dbg[2] = (int)threadIdx.x, g_mbar_dbg[3] = (int)gridDim.x;
+                    g_mbar_dbg[4] = (int)parity, g_mbar_dbg[5] = (int)addr, g_mbar_dbg[6] = (int)blockDim.x;
+                }
+                atomicExch(&g_mbar_abort, 1);
+                return;
+            }
+        }
+#else
+        (void)line;
         if (spin > (1u << 28)) __trap();
+#endif
     }
 }
+#define mbar_wait(bar, parity) mbar_wait_at(bar, parity, __LINE__)
 
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
