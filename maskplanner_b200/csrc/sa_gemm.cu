@@ -21,6 +21,11 @@
 //     f(a) = relu(scale[k] * a + shift[k])      the previous layer's BatchNorm + ReLU (XFORM), so the normalised
 //                                               activation tensor is never written to or read from HBM;
 //     a -> (tf32(a), a - tf32(a))               the hi/lo split of DT_TF32X3.
+// A third transform (XFORM 2, bf16, off by default) rebuilds dZ of the max-pooled layer from its stored pre-activation (sparse
+// gather -> dense affine pass -> scatter, arg-max / p*dY slices delivered by TMA into the stage): mpb_sa_gemm_tn_pool /
+// mpb_sa_gemm_wgrad_pool.  The two transform warpgroups of gemm_tn take alternate k-blocks but BOTH wait on full[stage] for every
+// k-block: mbarrier waits test a phase parity, and a warpgroup that skipped a phase of a barrier can be told "done" one phase early
+// (the deadlock of DESIGN.md section 9.5).  N = 2 x 128 with the tensor-core statistics runs as ONE paired tile (GemmTnArgs::pair).
 // Epilogue options of gemm_tn: plain store (one TMA store per 128-row x 128-byte block through a swizzled staging
 // tile); + per-column sum / sum of squares of the stored values (forward BatchNorm statistics); + per-column
 // sum dY / sum dY*z with dY = C * [zscale*z + zshift > 0] against a TMA-loaded tile of the previous layer's

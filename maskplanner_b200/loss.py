@@ -9,15 +9,23 @@
     3. 100 * GT->pred SEGMENT chamfer (reverse_asymmetric, mean/mean)                                    (:642-645)
     4. stroke-mask loss: Hungarian-matched BCE on masks + weighted BCE on mask confidences              (:816-935)
 
-Terms 1 and 3 use the same tensor pair; ``fused=True`` (default) evaluates both directions of that
-pair in ONE nearest-neighbour launch instead of two full chamfer calls; ``fused=False``
-issues the reference's three ``chamfer_distance`` calls literally (parity tests use both).
+Three implementations, selected by ``fused``:
 
-The mask loss needs a linear assignment per sample (<= 22 x 22).  The reference builds each cost
-matrix with Python loops and moves it to the host one sample at a time (:860-875).  Here all cost
-matrices come from one batched GEMM on the device (BCE-with-logits against a binary target is
-softplus(x) - x*y, so cost[p,t] = sum_i softplus(x[p,i]) - sum_{i in stroke t} x[p,i]); the
-assignment itself runs on the host with scipy from ONE device->host copy per step.
+* ``fused=True`` (default, the training path): ONE autograd node over the fused kernels of ``csrc/loss.cu``
+  (``_FusedAsymmV6``): a length scan of both ground-truth tensors, the segment nearest-neighbour search in both
+  directions (terms 1 + 3 share it) with the pose search (term 2) on a side stream, all B x P x T mask cost matrices,
+  the per-sample Hungarian assignment on the device (``mpb_lap_f32``, one warp per sample), a single-CTA loss-value
+  kernel off the critical path, and three backward launches.  No host synchronisation, CUDA-graph capturable, the five
+  schedulable weights read from device memory.
+* ``fused="nn"``: terms 1 and 3 from one nearest-neighbour launch, everything around it stock torch ops (round 1's path;
+  kept for A/B runs and as a second implementation the parity tests compare against).
+* ``fused=False``: the reference's three ``chamfer_distance`` calls literally, with ``matcher="host"`` the reference's own
+  scipy solver from one device->host copy (parity tests).
+
+The mask loss needs a linear assignment per sample (<= 22 x 22).  The reference builds each cost matrix with Python loops
+and moves it to the host one sample at a time (:860-875).  BCE-with-logits against a binary target is
+softplus(x) - x*y, so cost[p,t] = sum_i softplus(x[p,i]) - sum_{i in stroke t} x[p,i] for every pair at once, and the
+matched BCE of the loss (:886-906) is exactly the selected cost entry.
 """
 import os
 from dataclasses import dataclass

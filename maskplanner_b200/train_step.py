@@ -11,8 +11,12 @@ side stream while the encoder backward is still running.
 
 No step of the body synchronises with the host (the reference's padding scan, per-sample Hungarian
 and .cpu() calls are all on the device here), so with ``use_graph=True`` the whole step -- forward,
-loss, backward, all-reduce, Adam -- is captured once into a CUDA graph and replayed: one launch per
-step instead of ~600, which is what makes a ~5 ms step possible at all from Python.
+loss, backward, all-reduce, Adam -- is captured once into a CUDA graph and replayed; per call the host
+issues one staging launch (``mpb_stage_batch``: the batch into the graph's fixed buffers, GT rows padded
+with the loader's sentinels), one seed copy and the replay.  The FPS / ball-query plan of the NEXT batch
+(``step(..., next_batch=...)``) is computed on a side stream inside the current step (sampling depends on
+the cloud alone), so no step starts with a 0.2 ms FPS that nothing can overlap; ``step_from_host_async``
+keeps the pinned H2D copies two calls ahead and hands the loss back as a ``PendingLoss``.
 
 BatchNorm semantics: replica semantics (each rank normalises over its own samples), the standard DDP
 behaviour; single-process-equivalent statistics would need SyncBN (not built).  `Trainer.sync_bn_buffers()` averages
