@@ -10,6 +10,8 @@ CUDA tensors only -- there is no CPU or pure-torch fallback for the hot ops.
     sample_and_group         :112-148   sample_and_group_all   :151-168
     PointNetSetAbstraction   :171-216
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -27,6 +29,11 @@ def _f32(t, name):
 
 def _strides3(t):
     return t.stride(0), t.stride(1), t.stride(2)
+
+
+def _check_out(out, shape, device):
+    if tuple(out.shape) != tuple(shape) or out.dtype != torch.int64 or out.device != device or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int64 tensor of shape %s on %s" % (tuple(shape), device))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -98,17 +105,20 @@ def draw_fps_seed(B, N, device):
     return torch.randint(0, N, (B,), dtype=torch.long).to(device)
 
 
-def farthest_point_sample(xyz, npoint, seed_idx=None):
+def farthest_point_sample(xyz, npoint, seed_idx=None, out=None):
     """xyz [B,N,3] f32 -> centroids [B,npoint] int64, bit-exact vs the reference (:65-86).
 
     `seed_idx` (extension, default None = reference behaviour) supplies the first index per cloud
-    instead of drawing it."""
+    instead of drawing it; `out` (extension): a preallocated contiguous [B,npoint] int64 result buffer."""
     require_cuda(xyz)
     _f32(xyz, "xyz")
     B, N, C = xyz.shape
     assert C == 3, "farthest_point_sample expects [B, N, 3]"
     seed = draw_fps_seed(B, N, xyz.device) if seed_idx is None else seed_idx.to(device=xyz.device, dtype=torch.long).contiguous()
-    out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
+    if out is None:
+        out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
+    else:
+        _check_out(out, (B, npoint), xyz.device)
     lib = _cabi.load()
     ws_bytes = lib.mpb_fps_workspace_bytes(B, N)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=xyz.device) if ws_bytes else None
@@ -120,13 +130,17 @@ def farthest_point_sample(xyz, npoint, seed_idx=None):
 # ---------------------------------------------------------------------------------------------
 # a3  query_ball_point (+ kNN grouping for the stress configuration)
 # ---------------------------------------------------------------------------------------------
-def query_ball_point(radius, nsample, xyz, new_xyz):
-    """xyz [B,N,3], new_xyz [B,S,3] -> group_idx [B,S,nsample] int64, bit-exact vs the reference (:89-109)."""
+def query_ball_point(radius, nsample, xyz, new_xyz, out=None):
+    """xyz [B,N,3], new_xyz [B,S,3] -> group_idx [B,S,nsample] int64, bit-exact vs the reference (:89-109).
+    `out` (extension): a preallocated contiguous [B,S,nsample] int64 result buffer."""
     require_cuda(xyz, new_xyz)
     _f32(xyz, "xyz"), _f32(new_xyz, "new_xyz")
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
-    out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
+    if out is None:
+        out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
+    else:
+        _check_out(out, (B, S, nsample), xyz.device)
     r2 = float(np.float32(radius ** 2))  # torch compares fp32 tensors against fp32(radius ** 2) (:104)
     check(_cabi.load().mpb_ball_query_f32(ptr(xyz), *_strides3(xyz), ptr(new_xyz), *_strides3(new_xyz), B, N, S, r2,
                                           nsample, ptr(out), stream_ptr()), "mpb_ball_query_f32")
@@ -223,6 +237,21 @@ class _GroupPointsBF16(torch.autograd.Function):
         return None, gf, None, None, None
 
 
+GROUP_ALL_KERNEL = os.environ.get("MPB_GROUP_ALL_KERNEL", "1") == "1"
+_IDENTITY_GROUPS = {}
+
+
+def _identity_group(B, N, device):
+    """idx [B,1,N] = 0..N-1 for every sample (sample_and_group_all as a grouping with one all-points neighbourhood)."""
+    key = (B, N, str(device))
+    idx = _IDENTITY_GROUPS.get(key)
+    if idx is None:
+        idx = torch.arange(N, dtype=torch.long, device=device).expand(B, 1, N).contiguous()
+        if not torch.cuda.is_current_stream_capturing():     # a tensor born inside a capture lives in the graph's private pool
+            _IDENTITY_GROUPS[key] = idx
+    return idx
+
+
 # Arithmetic of the shared MLP (reference :210-212); every mode runs the hand-written tcgen05 GEMMs + BatchNorm
 # kernels of maskplanner_b200.shared_mlp:
 #   "bf16"  bf16 activations/operands, fp32 accumulation and statistics                      tolerance rel 1e-2
@@ -257,13 +286,15 @@ def sampling_plan(xyz, specs, seeds=None, out=None):
     plan = []
     cur = xyz
     for l, (npoint, radius, nsample) in enumerate(specs):
-        fps_idx = farthest_point_sample(cur, npoint, None if seeds is None else seeds[l])
-        new_xyz = index_points(cur, fps_idx)
-        idx = query_ball_point(radius, nsample, cur, new_xyz)
-        if out is not None:
-            for dst, src in zip(out[l], (fps_idx, new_xyz, idx)):
-                dst.copy_(src)
-            fps_idx, new_xyz, idx = out[l]
+        seed = None if seeds is None else seeds[l]
+        if out is not None:      # the index kernels write straight into the caller's buffers
+            fps_idx = farthest_point_sample(cur, npoint, seed, out=out[l][0])
+            new_xyz = out[l][1].copy_(index_points(cur, fps_idx))
+            idx = query_ball_point(radius, nsample, cur, new_xyz, out=out[l][2])
+        else:
+            fps_idx = farthest_point_sample(cur, npoint, seed)
+            new_xyz = index_points(cur, fps_idx)
+            idx = query_ball_point(radius, nsample, cur, new_xyz)
         plan.append((fps_idx, new_xyz, idx))
         cur = new_xyz
     return plan
@@ -374,10 +405,17 @@ class PointNetSetAbstraction(nn.Module):
         mode = self.precision or _MLP_PRECISION
         row_dtype = MODES[mode][2]
         B, N, C = xyz.shape
+        a0 = None
         if self.group_all:                                                              # :151-168
             new_xyz = torch.zeros(B, 1, C, device=xyz.device)
-            rows = xyz if points is None else torch.cat([xyz, points], dim=-1)
             S, K = 1, N
+            if GROUP_ALL_KERNEL and mode == "bf16" and points is not None and C == 3 and not xyz.requires_grad:
+                # one group = every point, centred on the origin: the grouping kernel with the identity index emits the
+                # padded bf16 rows in ONE launch (torch: cat + pad (fill + copy) + cast, and three copies in the backward)
+                a0 = _GroupPointsBF16.apply(xyz, points, new_xyz, _identity_group(B, N, xyz.device), pad64(3 + points.shape[2]))
+                rows = None
+            else:
+                rows = xyz if points is None else torch.cat([xyz, points], dim=-1)
         else:
             S, K = self.npoint, self.nsample
             if sampling is not None:
@@ -389,7 +427,9 @@ class PointNetSetAbstraction(nn.Module):
                 idx = query_ball_point(self.radius, K, xyz, new_xyz)                    # :132
             rows = index_points(full_points, idx) if (points is None and full_points is not None) else None
         xyz_last = False
-        if rows is not None:   # group-all / full_points: plain rows, padded (and rounded to bf16 in that mode)
+        if a0 is not None:
+            xyz_last = True
+        elif rows is not None:   # group-all / full_points: plain rows, padded (and rounded to bf16 in that mode)
             w = rows.shape[-1]
             a0 = F.pad(rows.reshape(B * S * K, w), (0, pad64(w) - w)).to(row_dtype)
         elif narrow_rows_supported(points, K) and len(self.mlp_convs) >= 2:

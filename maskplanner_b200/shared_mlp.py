@@ -136,48 +136,139 @@ def _gemm_wgrad(lib, gd, esz, dz, a, M, N, K, st, real, a_affine, cout, cin, xyz
             _PENDING_REDUCE.append((fork, dw))
         
 
+def _f32_source(conv_weight):
+    src = conv_weight.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    return src
+
+
+def _alloc_packed(kind, cout_p, cin_p, mode, dev):
+    """Operand buffers of one layer: kind "gemm" -> (w, w_lo, wt, wt_lo) [cout_p, cin_p] / [cin_p, cout_p]; kind "narrow" ->
+    (w [cout_p, 8], scratch transpose)."""
+    if mode == "bf16":
+        return (torch.empty(cout_p, cin_p, dtype=torch.bfloat16, device=dev), None,
+                torch.empty(cin_p, cout_p, dtype=torch.bfloat16, device=dev), None)
+    if kind == "narrow":
+        buf = torch.empty(2, cout_p * cin_p, dtype=torch.float32, device=dev)
+        return buf[0].view(cout_p, cin_p), None, buf[1].view(cin_p, cout_p), None
+    buf = torch.empty(4, cout_p * cin_p, dtype=torch.float32, device=dev)
+    return buf[0].view(cout_p, cin_p), buf[1].view(cout_p, cin_p), buf[2].view(cin_p, cout_p), buf[3].view(cin_p, cout_p)
+
+
+def _fill_packed(bufs, kind, conv_weight, cout_p, cin_p, xyz_last, mode):
+    """One launch: [Cout,Cin,1,1] fp32 -> the zero-padded operand and its transpose in `bufs` (on the current stream)."""
+    cout, cin = conv_weight.shape[0], conv_weight.shape[1]
+    src = _f32_source(conv_weight)
+    w, w_lo, wt, wt_lo = bufs
+    lib = _cabi.load()
+    if mode == "bf16":
+        check(lib.mpb_pack_weight_bf16(ptr(src), cout, cin, cout_p, cin_p, 1 if xyz_last else 0, ptr(w), ptr(wt), stream_ptr()),
+              "mpb_pack_weight_bf16")
+    elif kind == "narrow":      # UNSPLIT: the first-layer kernel's CUDA-core FMAs are exact fp32
+        check(lib.mpb_pack_weight_tf32(ptr(src), cout, cin, cout_p, cin_p, 1, ptr(w), None, ptr(wt), None, stream_ptr()),
+              "mpb_pack_weight_tf32")
+    else:
+        check(lib.mpb_pack_weight_tf32(ptr(src), cout, cin, cout_p, cin_p, 1 if xyz_last else 0, ptr(w), ptr(w_lo), ptr(wt), ptr(wt_lo),
+                                       stream_ptr()), "mpb_pack_weight_tf32")
+
+
+class PackAhead:
+    """The weight operands of a whole step, packed beside the first layer instead of in front of every GEMM.
+
+    Packing a layer's weight ([Cout,Cin,1,1] fp32 -> padded bf16 / split-TF32 operand + transpose) is a 2 us launch, but it
+    sat on the main stream between the BatchNorm finalize of layer l-1 and the GEMM of layer l: nine serial launches on the
+    forward critical path.  The weights are known when the step starts, so a Trainer brackets its step with begin() / end():
+    the first bracketed step records which operands the layers ask for (in order), later steps issue the first one in line
+    and all the others on a side stream (a parallel branch of the captured graph) into persistent buffers; the layers pick
+    them up (`take`), the first pick-up after the first layer joins the branch -- by then it finished long ago.  Outside a
+    bracket, or for an operand that was not announced, the layer packs in line exactly as before.  MPB_PREPACK=0 disables."""
+
+    enabled = os.environ.get("MPB_PREPACK", "1") == "1"
+
+    def __init__(self):
+        self.requests = None          # [(key, kind, weight tensor, cout_p, cin_p, xyz_last, mode)]
+        self.bufs = {}
+        self.ready = {}
+        self.fork = None
+        self.log = None
+
+    def begin(self):
+        global _PACK_AHEAD
+        self.ready, self.fork, self.log = {}, None, None
+        if not self.enabled:
+            return
+        _PACK_AHEAD = self
+        if self.requests is None:
+            self.log = []
+            return
+        from .streams import Fork
+
+        def run(req):
+            key, kind, W, cout_p, cin_p, xyz_last, mode = req
+            bufs = self.bufs.get(key)
+            if bufs is None:
+                bufs = self.bufs[key] = _alloc_packed(kind, cout_p, cin_p, mode, W.device)
+            _fill_packed(bufs, kind, W, cout_p, cin_p, xyz_last, mode)
+            self.ready[key] = bufs
+
+        if self.requests:
+            run(self.requests[0])
+        if len(self.requests) > 1:
+            with Fork(self.requests[1][2], slot=5) as fork:
+                for req in self.requests[1:]:
+                    run(req)
+            self.fork = fork if fork.active else None
+            self._first = self.requests[0][0]
+
+    def take(self, key, kind, W, cout_p, cin_p, xyz_last, mode):
+        if self.log is not None:
+            self.log.append((key, kind, W, cout_p, cin_p, xyz_last, mode))
+            return None
+        hit = self.ready.pop(key, None)
+        if hit is not None and self.fork is not None and key != self._first:
+            self.fork.join()
+            self.fork = None
+        return hit
+
+    def end(self):
+        global _PACK_AHEAD
+        if self.log is not None:
+            self.requests, self.log = self.log, None
+        if self.fork is not None:
+            self.fork.join()
+            self.fork = None
+        self.ready = {}
+        if _PACK_AHEAD is self:
+            _PACK_AHEAD = None
+
+
+_PACK_AHEAD = None
+
+
+def _packed(kind, conv_weight, cout_p, cin_p, xyz_last, mode):
+    if _PACK_AHEAD is not None:
+        key = (kind, conv_weight.data_ptr(), tuple(conv_weight.shape), cout_p, cin_p, bool(xyz_last), mode)
+        hit = _PACK_AHEAD.take(key, kind, conv_weight, cout_p, cin_p, bool(xyz_last), mode)
+        if hit is not None:
+            return hit
+    bufs = _alloc_packed(kind, cout_p, cin_p, mode, conv_weight.device)
+    _fill_packed(bufs, kind, conv_weight, cout_p, cin_p, xyz_last, mode)
+    return bufs
+
+
 def _padded_weight(conv_weight, cout_p, cin_p, xyz_last, mode):
     """[Cout,Cin,1,1] fp32 -> the GEMM's B operand [cout_p, cin_p] (zero padded) and its transpose [cin_p, cout_p].
     bf16: (w, None, wt, None).  tf32 / fp32: hi = tf32(w) and lo = w - hi (lo is None for the single-pass mode).
     xyz_last: the rows come from mpb_group_points_bf16 (features first, the 3 centred coordinates last), so the
     reference's xyz-first input channels (:137) move to the end."""
-    cout, cin = conv_weight.shape[0], conv_weight.shape[1]
-    dev = conv_weight.device
-    src = conv_weight.detach()
-    if src.dtype != torch.float32 or not src.is_contiguous():
-        src = src.float().contiguous()
-    lib = _cabi.load()
-    if mode == "bf16":
-        w = torch.empty(cout_p, cin_p, dtype=torch.bfloat16, device=dev)
-        wt = torch.empty(cin_p, cout_p, dtype=torch.bfloat16, device=dev)
-        check(lib.mpb_pack_weight_bf16(ptr(src), cout, cin, cout_p, cin_p, 1 if xyz_last else 0, ptr(w), ptr(wt), stream_ptr()),
-              "mpb_pack_weight_bf16")
-        return w, None, wt, None
-    buf = torch.empty(4, cout_p * cin_p, dtype=torch.float32, device=dev)
-    w, w_lo, wt, wt_lo = buf[0].view(cout_p, cin_p), buf[1].view(cout_p, cin_p), buf[2].view(cin_p, cout_p), buf[3].view(cin_p, cout_p)
-    check(lib.mpb_pack_weight_tf32(ptr(src), cout, cin, cout_p, cin_p, 1 if xyz_last else 0, ptr(w), ptr(w_lo), ptr(wt), ptr(wt_lo),
-                                   stream_ptr()), "mpb_pack_weight_tf32")
-    return w, w_lo, wt, wt_lo
+    return _packed("gemm", conv_weight, cout_p, cin_p, xyz_last, mode)
 
 
 def _narrow_weight(conv_weight, cout_p, mode):
     """First-layer weight for the on-the-fly kernel: [cout_p, 8] in the activation storage type, xyz-last column order,
     UNSPLIT in the fp32 modes (the kernel's CUDA-core FMAs are exact fp32)."""
-    cout, cin = conv_weight.shape[0], conv_weight.shape[1]
-    dev = conv_weight.device
-    src = conv_weight.detach()
-    if src.dtype != torch.float32 or not src.is_contiguous():
-        src = src.float().contiguous()
-    lib = _cabi.load()
-    if mode == "bf16":
-        w = torch.empty(cout_p, NARROW_LDW, dtype=torch.bfloat16, device=dev)
-        wt = torch.empty(NARROW_LDW, cout_p, dtype=torch.bfloat16, device=dev)
-        check(lib.mpb_pack_weight_bf16(ptr(src), cout, cin, cout_p, NARROW_LDW, 1, ptr(w), ptr(wt), stream_ptr()), "mpb_pack_weight_bf16")
-        return w
-    buf = torch.empty(2, cout_p * NARROW_LDW, dtype=torch.float32, device=dev)
-    check(lib.mpb_pack_weight_tf32(ptr(src), cout, cin, cout_p, NARROW_LDW, 1, ptr(buf[0]), None, ptr(buf[1]), None, stream_ptr()),
-          "mpb_pack_weight_tf32")
-    return buf[0].view(cout_p, NARROW_LDW)
+    return _packed("narrow", conv_weight, cout_p, NARROW_LDW, True, mode)[0]
 
 
 NARROW_LDW = 8          # leading dimension of the packed first-layer weight on the narrow path (3 + D <= 8 channels)

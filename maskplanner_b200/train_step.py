@@ -177,6 +177,8 @@ class Trainer:
         self._plan_for = None                        # the cloud tensor `_plan_cur` was computed for
         self._next_static = None
         self._graph = None
+        from .shared_mlp import PackAhead
+        self._packs = PackAhead()
         self._static = None
         self._static_loss = None
         self._calls = 0
@@ -239,8 +241,10 @@ class Trainer:
         if self.heads_tf32:
             torch.backends.cuda.matmul.allow_tf32 = True  # head GEMMs (M = batch, library calls) on TF32 tensor cores
         try:
+            self._packs.begin()           # weight operands of all shared-MLP layers on a side branch (shared_mlp.PackAhead)
             return self._step_body(batch, fps_seeds, plan, nxt)
         finally:
+            self._packs.end()
             torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
     def _step_body(self, batch, fps_seeds, plan=None, nxt=None):
@@ -289,17 +293,24 @@ class Trainer:
                 self._heads_ready = None
             else:  # hooks did not all fire (a head without gradient): reduce the bucket here
                 reduce_(self.buckets.heads, self.world_size)
+        handover = None
+        if fork is not None:
+            fork.join()
+            if plan is not None:
+                # the plan just computed becomes the current one: backward has finished reading `plan` and the optimizer does
+                # not touch it, so the six copies run beside Adam instead of after it
+                flat_dst = [t for t3 in plan for t in t3]
+                flat_src = [t for t3 in nxt[2] for t in t3]
+                with streams.Fork(*flat_src, *flat_dst, slot=2) as handover:
+                    for dst, src in zip(flat_dst, flat_src):
+                        dst.copy_(src)
         if self.direct_grads:
             self.opt.step(grad_scale=1.0 / self.world_size)                       # :221 (the buffer holds the SUM over ranks)
         else:
             self.opt.step()                                                       # :221
         L.join_loss_value()       # the loss VALUE was reduced on a side stream, off the critical path
-        if fork is not None:
-            fork.join()
-            if plan is not None:          # the plan just computed becomes the current one (backward has finished reading `plan`)
-                for dst3, src3 in zip(plan, nxt[2]):
-                    for dst, src in zip(dst3, src3):
-                        dst.copy_(src)
+        if handover is not None:
+            handover.join()
         return loss.detach()
 
     def _ensure_plans(self, B):
