@@ -277,8 +277,8 @@ class FusedHeads:
                    eps=tuple(b.eps for b in bns))
         out, masks, scores = HeadsFunction.apply(feat, cfg, *params)
         if m.training:
-            for b in bns:
-                if b.num_batches_tracked is not None:
-                    b.num_batches_tracked += 1
+            counters = [b.num_batches_tracked for b in bns if b.num_batches_tracked is not None]
+            if counters:
+                torch._foreach_add_(counters, 1)      # BatchNorm1d's own bookkeeping, one launch for the four layers
         B = feat.shape[0]
         return out.view(B, m.out_vectors, -1), masks.view(B, m.n_stroke_masks, -1), scores

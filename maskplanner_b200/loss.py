@@ -278,6 +278,7 @@ class _FusedAsymmV6(torch.autograd.Function):
         ctx.dims = (B, P1, P2, D, P3, pose_dim, NM, float(no_stroke_w))
         ctx.shapes = (y_pred.shape, masks.shape, scores.shape)
         ctx.mark_non_differentiable(terms)
+        ctx.set_materialize_grads(False)       # no zero-filled gradient tensor for `terms` in front of the backward kernels
         ctx.match = idx_x
         return loss, terms
 
@@ -287,6 +288,8 @@ class _FusedAsymmV6(torch.autograd.Function):
         from ._cabi import check, ptr, stream_ptr
         while BACKWARD_START_HOOKS:
             BACKWARD_START_HOOKS.pop()()
+        if g_loss is None:
+            return (None,) * 10
         x, yy, pc, mk, sc, idx_x, idx_y, len_y, idx_y2, len_y2, ids, present, row, w5 = ctx.saved_tensors
         B, P1, P2, D, P3, D2, NM, nsw = ctx.dims
         g = g_loss.detach().float().reshape(1).contiguous()

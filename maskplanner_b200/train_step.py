@@ -179,6 +179,7 @@ class Trainer:
         self._graph = None
         from .shared_mlp import PackAhead
         self._packs = PackAhead()
+        self._unit_grad = None
         self._static = None
         self._static_loss = None
         self._calls = 0
@@ -284,7 +285,10 @@ class Trainer:
                                                     batch["traj_as_pc"], self.loss_cfg, fused=self.fused_loss,
                                                     weights=self.loss_weights, join_value=False)    # :212-218
         self._heads_pending = 0
-        loss.backward()                                                           # :220
+        if self._unit_grad is None:
+            self._unit_grad = torch.ones((), dtype=torch.float32, device=self.device)
+        # :220 (the root gradient handed in: autograd would otherwise launch a fill for its ones_like(loss))
+        loss.backward(self._unit_grad if loss.dtype == torch.float32 and loss.dim() == 0 else None)
         if self.world_size > 1:
             reduce_ = all_reduce_sum_ if self.direct_grads else all_reduce_mean_
             reduce_(self.buckets.encoder, self.world_size)

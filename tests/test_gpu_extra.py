@@ -144,3 +144,43 @@ def test_reference_gpu_arm_computes_the_same_step_as_the_cpu_oracle():
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     assert abs(l_cpu - l_gpu) <= 2e-3 * abs(l_cpu), (l_cpu, l_gpu)
+
+
+def test_stage_batch_copies_and_pads_every_segment_kind():
+    """mpb_stage_batch against torch slicing: plain copies (vector and word granularity, aligned and not), padded segments
+    whose rows are whole 16-byte vectors (traj: 24 words) and not (poses: 6 words), int64 payloads, empty sources."""
+    import ctypes
+    from maskplanner_b200 import _cabi
+    lib = _cabi.load()
+    dev = "cuda"
+    g = torch.Generator().manual_seed(5)
+    B = 5
+    cases = []          # (src, dst_rows, pad value)
+    cases.append((torch.randn(B, 37, 3, generator=g), 37, 0.0))            # plain, 555 words: word granularity
+    cases.append((torch.randn(B, 64, 3, generator=g), 64, 0.0))            # plain, 960 words: vectors
+    cases.append((torch.randn(B, 11, 24, generator=g), 19, -100.0))        # padded, vector rows
+    cases.append((torch.randn(B, 13, 6, generator=g), 29, -100.0))         # padded, word rows
+    cases.append((torch.randn(B, 0, 4, generator=g), 3, -1.0))             # empty source: all padding
+    cases.append((torch.randn(B, 7, 1, generator=g), 9, -1.0))             # one word per row
+    srcs = [c[0].to(dev) for c in cases]
+    misaligned = torch.randn(B * 64 * 3 + 1, generator=g).to(dev)[1:].view(B, 64, 3)     # plain copy from a 4-byte aligned source
+    srcs.append(misaligned)
+    cases.append((misaligned.cpu(), 64, 0.0))
+    seeds = torch.randint(0, 1 << 40, (B,), generator=g).to(dev)
+    dsts = [torch.full((B, c[1]) + tuple(c[0].shape[2:]), 7.0, device=dev) for c in cases]
+    seeds_dst = torch.zeros_like(seeds)
+    n = len(cases) + 1
+    assert n <= 8
+    bits = lambda v: int(np.float32(v).view(np.uint32))
+    row = lambda t: int(np.prod(t.shape[2:]))
+    vp, i64, u32 = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_uint32 * n
+    _cabi.check(lib.mpb_stage_batch(
+        n, vp(*[s.data_ptr() for s in srcs], seeds.data_ptr()), vp(*[d.data_ptr() for d in dsts], seeds_dst.data_ptr()),
+        i64(*[B] * len(cases), 1), i64(*[c[0].shape[1] for c in cases], 1), i64(*[c[1] for c in cases], 1),
+        i64(*[row(d) for d in dsts], 2 * B), u32(*[bits(c[2]) for c in cases], 0), _cabi.stream_ptr()), "mpb_stage_batch")
+    torch.cuda.synchronize()
+    for (src, rows, pad), s, d in zip(cases, srcs, dsts):
+        want = torch.full_like(d, pad)
+        want[:, :s.shape[1]] = s
+        assert torch.equal(d, want), (tuple(src.shape), rows)
+    assert torch.equal(seeds_dst, seeds)
