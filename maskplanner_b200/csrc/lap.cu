@@ -23,6 +23,13 @@ __global__ void __launch_bounds__(32) lap_kernel(const float *__restrict__ cost,
     __shared__ int job_of[33];    // p[j]: worker holding job j (1-based jobs; 0 = none); job_of[0] = worker being inserted
     __shared__ int way[33];
     __shared__ int worker_col[33];
+    // the cost matrix, transposed (target-major, pitch 33: lane = job reads consecutive words).  Every step of the path search
+    // reads one column of it; from global memory that is one dependent L2 round trip (~0.3 us) per step, ~250 steps per sample
+    __shared__ float cs[32 * 33];
+    for (int e = lane; e < P * T; e += 32) {
+        const int p = e / T, t = e - p * T;
+        cs[t * 33 + p] = c[e];
+    }
     // compact the present targets into workers 1..n
     int n = 0;
     for (int t = 0; t < T; ++t)
@@ -49,7 +56,7 @@ __global__ void __launch_bounds__(32) lap_kernel(const float *__restrict__ cost,
             const double ui0 = u[i0];
             double cand = 1e300;
             if (live && !used) {
-                const double cur = (double)c[(size_t)(j - 1) * T + col] - ui0 - v;
+                const double cur = (double)cs[col * 33 + (j - 1)] - ui0 - v;
                 if (cur < minv) {
                     minv = cur;
                     way[j] = j0;
