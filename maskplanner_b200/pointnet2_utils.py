@@ -247,7 +247,7 @@ def _identity_group(B, N, device):
     idx = _IDENTITY_GROUPS.get(key)
     if idx is None:
         idx = torch.arange(N, dtype=torch.long, device=device).expand(B, 1, N).contiguous()
-        if not torch.cuda.is_current_stream_capturing():     # a tensor born inside a capture lives in the graph's private pool
+        if not (idx.is_cuda and torch.cuda.is_current_stream_capturing()):   # a tensor born inside a capture lives in the graph's private pool
             _IDENTITY_GROUPS[key] = idx
     return idx
 
